@@ -1,0 +1,732 @@
+// engine.cu -- host side of the B200 PairHMM engine and its C-ABI (include/gklb_pairhmm.h).
+//
+// Replaces the native half of GKL's PairHMM binding:
+//   initNative / computeLikelihoodsNative / doneNative   pairhmm/IntelPairHmm.cc:55-118,125-181,189-192
+//   JavaData::getData (testcase expansion)                pairhmm/JavaData.h:65-111
+// The (read, haplotype) cross product is never materialised: reads are bucketed into length
+// classes and packed on the device, haplotypes become shared-memory panel images, and pairs are
+// addressed by (record, haplotype) index arithmetic inside the kernels.
+//
+// There is no CPU compute path in this file: without a compute-capability-10 device every
+// entry point fails with GKLB_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/gklb_pairhmm.h"
+#include "pairhmm_device.cuh"
+#include "pairhmm_kernels.h"
+#include "pairhmm_tables.h"
+
+using namespace gklb;
+
+namespace {
+
+thread_local std::string t_last_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  return code;
+}
+
+#define CU(call)                                                                                        \
+  do {                                                                                                  \
+    cudaError_t e_ = (call);                                                                            \
+    if (e_ != cudaSuccess)                                                                              \
+      return fail(e_ == cudaErrorMemoryAllocation ? GKLB_ERR_OOM : GKLB_ERR_CUDA, "%s failed: %s", #call, \
+                  cudaGetErrorString(e_));                                                              \
+  } while (0)
+
+// Length classes: rows per pass = G * K.  A read goes to the first class that holds it; reads
+// longer than the last class take n_pass passes of the multi-pass kernel.
+struct ClassDef { int G, K; };
+const ClassDef kClasses[] = {{8, 4},  {8, 5},  {8, 6},  {8, 7},  {8, 8},  {16, 5}, {16, 6},
+                             {16, 7}, {16, 8}, {32, 5}, {32, 6}, {32, 7}, {32, 8}};
+const int kNumClasses = (int)(sizeof(kClasses) / sizeof(kClasses[0]));
+const int kMultiG = 32, kMultiK = 8;
+const int kSmemMax = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, bytes); want = bytes; }
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct HostBuf {  // pinned
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct ClassInst {
+  int G = 0, K = 0, n_pass = 1, rows = 0, stride = 0;
+  bool multi = false;
+  const KernelEntry* kf = nullptr;  // fp32 task kernel
+  const KernelEntry* kd = nullptr;  // fp64 task + list kernel
+  std::vector<int32_t> rid, len;    // record order
+  int n_rec = 0;
+  // offsets into the meta upload / device buffers
+  size_t meta_rid = 0, meta_len = 0;
+  size_t rec_off = 0;   // into d_records
+  size_t fb_off = 0;    // into d_fb (uint2 units)
+  size_t carry_off = 0, carry_stride = 0;
+  int counter0 = 0;     // index of this class's first counter (fb count), then per-tile task counters
+};
+
+struct Tile {
+  int hap0 = 0, n = 0, max_len = 0;
+  size_t meta_off = 0;
+  uint32_t bytes = 0;
+};
+
+}  // namespace
+
+struct gklb_engine {
+  int device = 0;
+  bool use_double = false;
+  int num_sms = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::mutex mu;
+  // device tables
+  DevBuf d_tables;
+  const float *d_ph2pr_f = nullptr, *d_mm_f = nullptr;
+  const double *d_ph2pr_d = nullptr, *d_mm_d = nullptr;
+  // staged batch
+  bool staged = false;
+  int n_reads = 0, n_haps = 0;
+  std::vector<ClassInst> classes;
+  std::vector<Tile> tiles;
+  DevBuf d_read_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
+  HostBuf h_meta, h_counters;
+  size_t arena_pitch = 0;
+  int n_counters = 0;
+  gklb_pairhmm_stats stats{};
+  // forced kernel (measurement): policy,G,K,warps,var
+  bool forced = false;
+  int f_policy = 0, f_G = 0, f_K = 0, f_warps = 0, f_var = 0;
+};
+
+namespace {
+
+std::mutex g_mu;
+gklb_engine* g_engine = nullptr;
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int upload_tables(gklb_engine* e) {
+  const HostTables& t = host_tables();
+  const size_t bytes = sizeof(float) * (kPh2prSize + kMmSize) + sizeof(double) * (kPh2prSize + kMmSize);
+  CU(e->d_tables.ensure(bytes + 64));
+  uint8_t* base = static_cast<uint8_t*>(e->d_tables.p);
+  size_t off = 0;
+  e->d_ph2pr_d = reinterpret_cast<const double*>(base + off);
+  CU(cudaMemcpy(base + off, t.ph2pr_d, sizeof(t.ph2pr_d), cudaMemcpyHostToDevice));
+  off += sizeof(t.ph2pr_d);
+  e->d_mm_d = reinterpret_cast<const double*>(base + off);
+  CU(cudaMemcpy(base + off, t.mm_d, sizeof(t.mm_d), cudaMemcpyHostToDevice));
+  off += sizeof(t.mm_d);
+  e->d_ph2pr_f = reinterpret_cast<const float*>(base + off);
+  CU(cudaMemcpy(base + off, t.ph2pr_f, sizeof(t.ph2pr_f), cudaMemcpyHostToDevice));
+  off += sizeof(t.ph2pr_f);
+  e->d_mm_f = reinterpret_cast<const float*>(base + off);
+  CU(cudaMemcpy(base + off, t.mm_f, sizeof(t.mm_f), cudaMemcpyHostToDevice));
+  return GKLB_OK;
+}
+
+int parse_forced(gklb_engine* e) {
+  e->forced = false;
+  const char* s = getenv("GKLB_FORCE_KERNEL");
+  if (!s || !*s) return GKLB_OK;
+  char pol[8] = {0};
+  int G, K, W, V;
+  if (sscanf(s, "%7[^,],%d,%d,%d,%d", pol, &G, &K, &W, &V) != 5)
+    return fail(GKLB_ERR_INVALID, "GKLB_FORCE_KERNEL must be policy,G,K,warps,var (got '%s')", s);
+  int p = !strcmp(pol, "f2") ? POL_F2 : !strcmp(pol, "f1") ? POL_F1 : !strcmp(pol, "d1") ? POL_D1 : -1;
+  if (p < 0 || !find_kernel(p, G, K, W, 0, V)) return fail(GKLB_ERR_INVALID, "no compiled kernel for '%s'", s);
+  e->forced = true;
+  e->f_policy = p; e->f_G = G; e->f_K = K; e->f_warps = W; e->f_var = V;
+  return GKLB_OK;
+}
+
+int set_kernel_attrs() {
+  int n;
+  const KernelEntry* t = kernel_table(&n);
+  for (int i = 0; i < n; i++) {
+    CU(cudaFuncSetAttribute(t[i].fn_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    if (t[i].fn_list) CU(cudaFuncSetAttribute(t[i].fn_list, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  }
+  return GKLB_OK;
+}
+
+int validate(const gklb_pairhmm_batch* b) {
+  if (!b) return fail(GKLB_ERR_INVALID, "batch is null");
+  if (b->n_reads < 0 || b->n_haps < 0) return fail(GKLB_ERR_INVALID, "negative batch size");
+  if (b->n_reads == 0 || b->n_haps == 0) return GKLB_OK;
+  if (!b->read_off || !b->hap_off || !b->read_bases || !b->read_quals || !b->ins_gop || !b->del_gop || !b->gcp ||
+      !b->hap_bases)
+    return fail(GKLB_ERR_INVALID, "null pointer in batch");
+  if (b->read_off[0] != 0 || b->hap_off[0] != 0) return fail(GKLB_ERR_INVALID, "offsets must start at 0");
+  for (int r = 0; r < b->n_reads; r++)
+    if (b->read_off[r + 1] <= b->read_off[r]) return fail(GKLB_ERR_INVALID, "read %d is empty or offsets decrease", r);
+  for (int h = 0; h < b->n_haps; h++)
+    if (b->hap_off[h + 1] <= b->hap_off[h]) return fail(GKLB_ERR_INVALID, "haplotype %d is empty or offsets decrease", h);
+  return GKLB_OK;
+}
+
+// Build the class instances for this batch.
+int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
+  e->classes.clear();
+  std::vector<int> inst_of_class(kNumClasses, -1);
+  std::vector<std::pair<int, int>> multi_inst;  // (n_pass, inst)
+  int forced_inst = -1;
+  for (int r = 0; r < b->n_reads; r++) {
+    const int64_t len64 = b->read_off[r + 1] - b->read_off[r];
+    if (len64 > (1 << 24)) return fail(GKLB_ERR_INVALID, "read %d is too long (%lld)", r, (long long)len64);
+    const int len = (int)len64;
+    int inst = -1;
+    if (e->forced && len <= e->f_G * e->f_K) {
+      if (forced_inst < 0) {
+        ClassInst c;
+        c.G = e->f_G; c.K = e->f_K; c.n_pass = 1; c.multi = false;
+        c.kf = find_kernel(e->f_policy, c.G, c.K, e->f_warps, 0, e->f_var);
+        c.kd = find_kernel(POL_D1, c.G, c.K, -1, 0, -1);
+        forced_inst = (int)e->classes.size();
+        e->classes.push_back(c);
+      }
+      inst = forced_inst;
+    } else if (len <= kClasses[kNumClasses - 1].G * kClasses[kNumClasses - 1].K) {
+      int ci = 0;
+      while (kClasses[ci].G * kClasses[ci].K < len) ci++;
+      if (inst_of_class[ci] < 0) {
+        ClassInst c;
+        c.G = kClasses[ci].G; c.K = kClasses[ci].K; c.n_pass = 1; c.multi = false;
+        c.kf = find_kernel(POL_F2, c.G, c.K, -1, 0, -1);
+        c.kd = find_kernel(POL_D1, c.G, c.K, -1, 0, -1);
+        inst_of_class[ci] = (int)e->classes.size();
+        e->classes.push_back(c);
+      }
+      inst = inst_of_class[ci];
+    } else {
+      const int cap = kMultiG * kMultiK;
+      const int n_pass = (len + cap - 1) / cap;
+      for (auto& m : multi_inst)
+        if (m.first == n_pass) inst = m.second;
+      if (inst < 0) {
+        ClassInst c;
+        c.G = kMultiG; c.K = kMultiK; c.n_pass = n_pass; c.multi = true;
+        c.kf = find_kernel(POL_F2, c.G, c.K, -1, 1, -1);
+        c.kd = find_kernel(POL_D1, c.G, c.K, -1, 1, -1);
+        inst = (int)e->classes.size();
+        multi_inst.push_back({n_pass, inst});
+        e->classes.push_back(c);
+      }
+    }
+    e->classes[inst].rid.push_back(r);
+    e->classes[inst].len.push_back(len);
+  }
+  for (auto& c : e->classes) {
+    if (!c.kf || (!c.kd && !e->forced)) return fail(GKLB_ERR_STATE, "kernel for class G=%d K=%d is not compiled", c.G, c.K);
+    c.rows = c.n_pass * c.G * c.K;
+    c.stride = (int)align_up((size_t)c.rows, 16);
+    const int rpw = (32 / c.G) * 2;  // covers the packed (2 reads / lane) and the fp64 (1 read / lane) kernels
+    while (c.rid.size() % rpw) { c.rid.push_back(-1); c.len.push_back(0); }
+    c.n_rec = (int)c.rid.size();
+  }
+  return GKLB_OK;
+}
+
+uint32_t slot_bytes_total(const ClassInst& c, const KernelEntry* k) {
+  const uint32_t rpw = (uint32_t)((32 / c.G) * k->nr);
+  return (uint32_t)k->warps * (uint32_t)align_up((size_t)rpw * 5 * c.stride, 128);
+}
+
+// Split the haplotypes into tiles whose panel image fits beside the largest slot area.
+int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, size_t* meta_bytes) {
+  uint32_t worst_slots = 0;
+  for (auto& c : e->classes) {
+    worst_slots = std::max(worst_slots, slot_bytes_total(c, c.kf));
+    if (c.kd) worst_slots = std::max(worst_slots, slot_bytes_total(c, c.kd));
+  }
+  const long long budget = (long long)kSmemMax - 4096 - worst_slots;
+  e->tiles.clear();
+  int h = 0;
+  while (h < b->n_haps) {
+    Tile t;
+    t.hap0 = h;
+    size_t data = 0;
+    while (h < b->n_haps) {
+      const size_t len = (size_t)(b->hap_off[h + 1] - b->hap_off[h]);
+      const size_t add = kHapLeftMargin + len + kHapRightMargin;
+      const size_t header = align_up((size_t)8 * (t.n + 1), 16);
+      if (t.n > 0 && (long long)(header + data + add + 16) > budget) break;
+      if (t.n == 0 && (long long)(header + add + 16) > budget)
+        return fail(GKLB_ERR_INVALID, "haplotype %d (%zu bases) does not fit in shared memory", h, len);
+      data += add;
+      t.max_len = std::max(t.max_len, (int)len);
+      t.n++;
+      h++;
+    }
+    t.bytes = (uint32_t)align_up(align_up((size_t)8 * t.n, 16) + data, 16);
+    t.meta_off = *meta_bytes;
+    *meta_bytes += align_up(t.bytes, 128);
+    e->tiles.push_back(t);
+  }
+  return GKLB_OK;
+}
+
+void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) {
+  memset(img, 0, t.bytes);
+  int32_t* hpos = reinterpret_cast<int32_t*>(img);
+  int32_t* hlen = hpos + t.n;
+  size_t off = align_up((size_t)8 * t.n, 16);
+  for (int i = 0; i < t.n; i++) {
+    const int h = t.hap0 + i;
+    const int64_t o = b->hap_off[h];
+    const int len = (int)(b->hap_off[h + 1] - o);
+    hpos[i] = (int32_t)(off + kHapLeftMargin - 1);  // column 0; column c is at hpos + c
+    hlen[i] = len;
+    uint8_t* dst = img + off + kHapLeftMargin;
+    for (int c = 0; c < len; c++) dst[c] = base_nibble(b->hap_bases[o + c]);
+    off += kHapLeftMargin + len + kHapRightMargin;
+  }
+}
+
+int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
+  e->staged = false;
+  int rc = validate(b);
+  if (rc) return rc;
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));  // the pinned staging buffers are about to be rewritten
+  e->n_reads = b->n_reads;
+  e->n_haps = b->n_haps;
+  e->stats = gklb_pairhmm_stats{};
+  if (b->n_reads == 0 || b->n_haps == 0) {
+    e->classes.clear();
+    e->tiles.clear();
+    e->staged = true;
+    return GKLB_OK;
+  }
+  if ((rc = parse_forced(e))) return rc;
+  const int64_t total_read = b->read_off[b->n_reads];
+  const int64_t total_hap = b->hap_off[b->n_haps];
+  e->stats.pairs = (int64_t)b->n_reads * b->n_haps;
+  e->stats.cells = total_read * total_hap;
+
+  // the haplotype panel images are built on the host: fetch the bases if they live on the device
+  std::vector<uint8_t> hap_host;
+  gklb_pairhmm_batch hb = *b;
+  if (hap_on_device) {
+    hap_host.resize((size_t)total_hap);
+    CU(cudaMemcpyAsync(hap_host.data(), b->hap_bases, (size_t)total_hap, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaStreamSynchronize(e->stream));
+    hb.hap_bases = hap_host.data();
+  }
+
+  if ((rc = plan_classes(e, b))) return rc;
+  size_t meta_bytes = 0;
+  if ((rc = plan_tiles(e, &hb, &meta_bytes))) return rc;
+  size_t rec_bytes = 0, fb_items = 0, carry_bytes = 0;
+  int counters = 0;
+  for (auto& c : e->classes) {
+    c.meta_rid = meta_bytes;
+    meta_bytes += align_up(sizeof(int32_t) * c.n_rec, 128);
+    c.meta_len = meta_bytes;
+    meta_bytes += align_up(sizeof(int32_t) * c.n_rec, 128);
+    c.rec_off = rec_bytes;
+    rec_bytes += align_up((size_t)c.n_rec * 5 * c.stride, 128);
+    c.fb_off = fb_items;
+    if (!e->use_double) fb_items += (size_t)c.n_rec * b->n_haps;
+    c.counter0 = counters;
+    counters += 1 + 2 * (int)e->tiles.size();
+    if (c.multi) {
+      int max_len = 0;
+      for (auto& t : e->tiles) max_len = std::max(max_len, t.max_len);
+      const int warps = std::max(c.kf->warps, c.kd ? c.kd->warps : 0);
+      c.carry_stride = (size_t)(32 / c.G) * 6 * (max_len + 2) * 8;
+      c.carry_off = carry_bytes;
+      carry_bytes += c.carry_stride * warps * e->num_sms;
+    }
+  }
+  e->n_counters = counters;
+
+  CU(e->h_meta.ensure(meta_bytes));
+  CU(e->d_meta.ensure(meta_bytes));
+  CU(e->d_records.ensure(rec_bytes));
+  CU(e->d_read_off.ensure(sizeof(int64_t) * ((size_t)b->n_reads + 1)));
+  e->arena_pitch = align_up((size_t)total_read, 256);
+  CU(e->d_arenas.ensure(e->arena_pitch * 5));
+  CU(e->d_out.ensure(sizeof(double) * (size_t)e->stats.pairs));
+  if (fb_items) CU(e->d_fb.ensure(sizeof(uint2) * fb_items));
+  CU(e->d_counters.ensure(sizeof(unsigned int) * (size_t)counters));
+  CU(e->h_counters.ensure(sizeof(unsigned int) * (size_t)counters));
+  if (carry_bytes) CU(e->d_carry.ensure(carry_bytes));
+
+  uint8_t* hm = static_cast<uint8_t*>(e->h_meta.p);
+  for (auto& t : e->tiles) build_tile_image(t, &hb, hm + t.meta_off);
+  for (auto& c : e->classes) {
+    memcpy(hm + c.meta_rid, c.rid.data(), sizeof(int32_t) * c.n_rec);
+    memcpy(hm + c.meta_len, c.len.data(), sizeof(int32_t) * c.n_rec);
+  }
+  cudaStream_t s = e->stream;
+  CU(cudaMemcpyAsync(e->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->d_read_off.p, b->read_off, sizeof(int64_t) * ((size_t)b->n_reads + 1), cudaMemcpyHostToDevice, s));
+  uint8_t* da = static_cast<uint8_t*>(e->d_arenas.p);
+  const uint8_t* src[5] = {b->read_bases, b->read_quals, b->ins_gop, b->del_gop, b->gcp};
+  for (int i = 0; i < 5; i++)
+    CU(cudaMemcpyAsync(da + i * e->arena_pitch, src[i], (size_t)total_read, cudaMemcpyDefault, s));
+
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  for (auto& c : e->classes) {
+    PackParams pp;
+    pp.read_off = static_cast<const int64_t*>(e->d_read_off.p);
+    pp.bases = da;
+    pp.quals = da + e->arena_pitch;
+    pp.ins = da + 2 * e->arena_pitch;
+    pp.del = da + 3 * e->arena_pitch;
+    pp.gcp = da + 4 * e->arena_pitch;
+    pp.records = static_cast<uint8_t*>(e->d_records.p) + c.rec_off;
+    pp.rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
+    pp.n_rec = c.n_rec;
+    pp.rows = c.rows;
+    pp.stride = c.stride;
+    CU(launch_pack(pp, s));
+  }
+  e->staged = true;
+  return GKLB_OK;
+}
+
+int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index) {
+  const bool dbl = (k->policy == POL_D1);
+  const HostTables& ht = host_tables();
+  SweepParams p;
+  memset(&p, 0, sizeof(p));
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  p.panel.image = dm + t.meta_off;
+  p.panel.bytes = t.bytes;
+  p.panel.n_haps = t.n;
+  p.panel.hap0 = t.hap0;
+  p.panel.n_haps_total = e->n_haps;
+  p.panel.max_hap_len = t.max_len;
+  p.cls.records = static_cast<const uint8_t*>(e->d_records.p) + c.rec_off;
+  p.cls.rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
+  p.cls.rec_len = reinterpret_cast<const int32_t*>(dm + c.meta_len);
+  p.cls.n_rec = c.n_rec;
+  p.cls.rows = c.rows;
+  p.cls.stride = c.stride;
+  p.cls.n_pass = c.n_pass;
+  p.ph2pr = dbl ? (const void*)e->d_ph2pr_d : (const void*)e->d_ph2pr_f;
+  p.mm = dbl ? (const void*)e->d_mm_d : (const void*)e->d_mm_f;
+  p.out = static_cast<double*>(e->d_out.p);
+  unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
+  p.fb_count = counters + c.counter0;
+  p.fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + c.fb_off : nullptr;
+  p.task_counter = counters + c.counter0 + 1 + 2 * tile_index + (list_mode ? 1 : 0);
+  p.carry = c.multi ? static_cast<uint8_t*>(e->d_carry.p) + c.carry_off : nullptr;
+  p.carry_stride_bytes = c.carry_stride;
+  p.init_const = dbl ? ht.init_d : (double)ht.init_f;
+  p.log10_init = dbl ? ht.log10_init_d : (double)ht.log10_init_f;
+
+  const int gpw = 32 / c.G;
+  const int rpw = gpw * k->nr;
+  const int slots = e->num_sms * k->warps;
+  int grid;
+  size_t smem;
+  if (!list_mode) {
+    const int n_blocks = c.n_rec / rpw;
+    long long chunk = ((long long)n_blocks * t.n) / (12LL * slots);
+    chunk = std::max(1LL, std::min(chunk, 32LL));
+    if (c.multi) chunk = 1;
+    chunk = std::min<long long>(chunk, t.n);
+    p.hap_chunk = (int)chunk;
+    p.n_chunks = (t.n + p.hap_chunk - 1) / p.hap_chunk;
+    p.n_tasks = n_blocks * p.n_chunks;
+    grid = std::min(e->num_sms, (p.n_tasks + k->warps - 1) / k->warps);
+    smem = smem_layout(k->warps, t.bytes, (uint32_t)(rpw * 5 * c.stride), dbl ? 8 : 4).total;
+  } else {
+    p.list_items = p.fb_items;
+    p.list_count = p.fb_count;
+    grid = e->num_sms;
+    smem = smem_layout(k->warps, t.bytes, 0, 8).total;
+  }
+  if (smem > (size_t)kSmemMax) return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu)", smem);
+  if (grid <= 0) return GKLB_OK;
+  CU(launch_sweep(list_mode ? k->fn_list : k->fn_tasks, p, grid, k->warps * 32, smem, e->stream));
+  e->stats.kernel_launches++;
+  return GKLB_OK;
+}
+
+int do_run(gklb_engine* e) {
+  if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
+  CU(cudaSetDevice(e->device));
+  e->stats.kernel_launches = 0;
+  e->stats.n_classes = (int)e->classes.size();
+  if (e->classes.empty()) return GKLB_OK;
+  CU(cudaMemsetAsync(e->d_counters.p, 0, sizeof(unsigned int) * (size_t)e->n_counters, e->stream));
+  for (size_t ti = 0; ti < e->tiles.size(); ti++) {
+    for (auto& c : e->classes) {
+      int rc;
+      if (e->use_double) {
+        if ((rc = launch_one(e, c, e->tiles[ti], c.kd, false, (int)ti))) return rc;
+      } else {
+        if ((rc = launch_one(e, c, e->tiles[ti], c.kf, false, (int)ti))) return rc;
+        if (c.kd && c.kf->policy != POL_D1)
+          if ((rc = launch_one(e, c, e->tiles[ti], c.kd, true, (int)ti))) return rc;
+      }
+    }
+  }
+  return GKLB_OK;
+}
+
+int do_fetch(gklb_engine* e, double* out) {
+  if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
+  CU(cudaSetDevice(e->device));
+  if (e->classes.empty()) return GKLB_OK;
+  if (!out) return fail(GKLB_ERR_INVALID, "likelihoods is null");
+  CU(cudaMemcpyAsync(out, e->d_out.p, sizeof(double) * (size_t)e->stats.pairs, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(unsigned int) * (size_t)e->n_counters,
+                     cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaStreamSynchronize(e->stream));
+  int64_t fb = 0;
+  const unsigned int* hc = static_cast<const unsigned int*>(e->h_counters.p);
+  for (auto& c : e->classes) fb += hc[c.counter0];
+  e->stats.fallback_pairs = fb;
+  return GKLB_OK;
+}
+
+int do_compute(gklb_engine* e, const gklb_pairhmm_batch* b, double* out) {
+  int rc;
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  if ((rc = do_stage(e, b, false))) return rc;
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  if ((rc = do_run(e))) return rc;
+  CU(cudaEventRecord(e->ev[2], e->stream));
+  if ((rc = do_fetch(e, out))) return rc;
+  CU(cudaEventRecord(e->ev[3], e->stream));
+  CU(cudaEventSynchronize(e->ev[3]));
+  cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->stats.kernel_ms, e->ev[1], e->ev[2]);
+  cudaEventElapsedTime(&e->stats.d2h_ms, e->ev[2], e->ev[3]);
+  return GKLB_OK;
+}
+
+int create_engine(gklb_engine** out, int device, int use_double) {
+  int n = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n);
+  if (ce != cudaSuccess || n <= 0) return fail(GKLB_ERR_NO_DEVICE, "no CUDA device (%s)", cudaGetErrorString(ce));
+  if (device < 0 || device >= n) return fail(GKLB_ERR_NO_DEVICE, "device %d out of range (%d devices)", device, n);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return fail(GKLB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major,
+                prop.minor);
+  CU(cudaSetDevice(device));
+  gklb_engine* e = new gklb_engine;
+  e->device = device;
+  e->use_double = use_double != 0;
+  e->num_sms = prop.multiProcessorCount;
+  CU(cudaStreamCreateWithFlags(&e->own_stream, cudaStreamNonBlocking));
+  e->stream = e->own_stream;
+  for (auto& ev : e->ev) CU(cudaEventCreate(&ev));
+  int rc = set_kernel_attrs();
+  if (!rc) rc = upload_tables(e);
+  if (rc) { delete e; return rc; }
+  *out = e;
+  return GKLB_OK;
+}
+
+void destroy_engine(gklb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  for (DevBuf* b : {&e->d_tables, &e->d_read_off, &e->d_arenas, &e->d_meta, &e->d_records, &e->d_out, &e->d_fb,
+                    &e->d_counters, &e->d_carry})
+    b->release();
+  e->h_meta.release();
+  e->h_counters.release();
+  for (auto& ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->own_stream) cudaStreamDestroy(e->own_stream);
+  delete e;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gklb_pairhmm_init(int use_double, int max_threads) {
+  (void)max_threads;  // GKL's non-OpenMP library ignores it as well (IntelPairHmm.cc:85-89)
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_engine) { destroy_engine(g_engine); g_engine = nullptr; }
+  const char* dev = getenv("GKLB_DEVICE");
+  return create_engine(&g_engine, dev ? atoi(dev) : 0, use_double);
+}
+
+int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_engine) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
+  return do_compute(g_engine, batch, likelihoods);
+}
+
+int gklb_pairhmm_done(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_engine) { destroy_engine(g_engine); g_engine = nullptr; }
+  return GKLB_OK;
+}
+
+int gklb_engine_create(gklb_engine** out, int device, int use_double) {
+  if (!out) return fail(GKLB_ERR_INVALID, "out is null");
+  return create_engine(out, device, use_double);
+}
+
+int gklb_engine_destroy(gklb_engine* e) {
+  destroy_engine(e);
+  return GKLB_OK;
+}
+
+int gklb_engine_set_stream(gklb_engine* e, void* cuda_stream) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  cudaSetDevice(e->device);
+  cudaStreamSynchronize(e->stream);
+  e->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : e->own_stream;
+  return GKLB_OK;
+}
+
+int gklb_engine_compute(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_compute(e, batch, likelihoods);
+}
+
+int gklb_engine_stage(gklb_engine* e, const gklb_pairhmm_batch* batch) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_stage(e, batch, false);
+}
+
+int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_stage(e, batch, true);
+}
+
+int gklb_engine_run(gklb_engine* e) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_run(e);
+}
+
+int gklb_engine_fetch(gklb_engine* e, double* likelihoods) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_fetch(e, likelihoods);
+}
+
+int gklb_engine_result_device(gklb_engine* e, void** dev_ptr) {
+  if (!e || !dev_ptr) return fail(GKLB_ERR_INVALID, "null argument");
+  if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
+  *dev_ptr = e->d_out.p;
+  return GKLB_OK;
+}
+
+int gklb_engine_synchronize(gklb_engine* e) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  return GKLB_OK;
+}
+
+int gklb_engine_stats(gklb_engine* e, gklb_pairhmm_stats* out) {
+  if (!e || !out) return fail(GKLB_ERR_INVALID, "null argument");
+  *out = e->stats;
+  return GKLB_OK;
+}
+
+int gklb_engine_time_runs(gklb_engine* e, int iters, float* ms_per_run) {
+  if (!e || !ms_per_run || iters <= 0) return fail(GKLB_ERR_INVALID, "bad argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  for (int i = 0; i < iters; i++) {
+    int rc = do_run(e);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  CU(cudaEventSynchronize(e->ev[1]));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  *ms_per_run = ms / (float)iters;
+  return GKLB_OK;
+}
+
+const char* gklb_last_error(void) { return t_last_error.c_str(); }
+
+const char* gklb_version(void) { return "gkl_b200 0.1 (sm_100a)"; }
+
+int gklb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  int ok = 0;
+  for (int i = 0; i < n; i++) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+  }
+  return ok;
+}
+
+const void* gklb_pairhmm_table(int which, int* n) {
+  const HostTables& t = host_tables();
+  switch (which) {
+    case 0: if (n) *n = kPh2prSize; return t.ph2pr_f;
+    case 1: if (n) *n = kMmSize; return t.mm_f;
+    case 2: if (n) *n = kPh2prSize; return t.ph2pr_d;
+    case 3: if (n) *n = kMmSize; return t.mm_d;
+    default: if (n) *n = 0; return nullptr;
+  }
+}
+
+}  // extern "C"

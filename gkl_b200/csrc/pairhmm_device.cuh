@@ -1,0 +1,624 @@
+// pairhmm_device.cuh -- sm_100a device code of the PairHMM engine.
+//
+// What is computed (reference semantics, /root/reference/src/main/native/pairhmm):
+//   the three-state forward recurrence of computeMXY (avx-pairhmm-template.h:208-223) in its
+//   cell form
+//       M[r][c] = prior(r,c) * (M[r-1][c-1]*pMM_r + (X[r-1][c-1] + Y[r-1][c-1])*pGAPM_r)
+//       X[r][c] = M[r-1][c]*pMX_r + X[r-1][c]*pXX_r
+//       Y[r][c] = M[r][c-1]*pMY_r + Y[r][c-1]*pYY_r
+//   with row 0 = {M=0, X=0, Y=INITIAL_CONSTANT/haplen} (:114-121,160-202), column 0 = 0 for
+//   rows >= 1, result = sum_c (M[R][c] + X[R][c]) (:325-371), per-row probabilities from
+//   quals & 127 (:106-152) and the fp32 -> fp64 rerun / log10 of IntelPairHmm.cc:150-169.
+//
+// How it is mapped to the machine (nothing like the reference's striped AVX code):
+//   * a GROUP of G lanes (G = 8, 16 or 32; 32/G groups per warp) sweeps one read (two reads
+//     when packed) against one haplotype as a systolic array: lane t owns K consecutive read
+//     rows, holds their seven transition/prior constants and the M/Y/X+Y state of the previous
+//     column in registers, and at step s processes column c = s - t, top row to bottom row;
+//   * the bottom row of lane t-1 reaches lane t with three __shfl_up_sync per step; the
+//     diagonal inputs are simply the previous step's shuffle results;
+//   * packed fp32 (VF2): each lane carries TWO reads in the halves of 64-bit register pairs and
+//     all arithmetic is FFMA2/FMUL2/FADD2 (sm_100 fma.rn.ftz.f32x2) -- half the issue slots of
+//     scalar FFMA, which is what bounds this recurrence (selects and shuffles co-issue);
+//   * reads shorter than G*K rows are padded at the TOP with rows that reproduce row 0
+//     (A=G=pMX=pMY=0, pXX=pYY=1, Y(c=0)=init): the last read row is then always the last row
+//     of the last lane, so the running sum lives in one fixed register;
+//   * reads longer than G*K rows take several passes; the bottom row of a pass is carried to
+//     the next pass through a per-warp global scratch line (the analogue of the reference's
+//     shiftOut arrays, avx-pairhmm-template.h:249,313-317);
+//   * prior(r,c) is selected with one LOP3 (one-hot base nibbles AND) and two FSEL per cell
+//     from constants pre-multiplied per row ((1-e)*pMM, (e/3)*pMM, (1-e)*pGAPM, (e/3)*pGAPM);
+//   * the haplotype panel lives in shared memory as one image fetched with a single TMA bulk
+//     copy (cp.async.bulk + mbarrier) per CTA; the packed read records of each task are
+//     fetched the same way into a per-warp slot;
+//   * persistent CTAs (one per SM) pull tasks (a block of reads x a chunk of haplotypes) from
+//     an atomic counter -- the analogue of the reference's schedule(dynamic,1).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gklb {
+
+constexpr int kHapLeftMargin = 32;   // bytes of zero symbols before column 1 of each haplotype
+constexpr int kHapRightMargin = 48;  // and after its last column (covers c = s - t overshoot + prefetch)
+constexpr int kMmTableSize = (128 * 129) / 2;  // reachable part of matchToMatchProb (quals & 127)
+constexpr float kMinAccepted = 1e-28f;         // pairhmm_common.h:39
+
+// One-hot base nibbles.  ConvertChar (pairhmm_common.h:49-67): A C T G N, everything else == 'A'.
+// N matches everything (precompute_masks, avx-pairhmm-template.h:26-58).
+__host__ __device__ inline uint8_t base_nibble(uint8_t ch) {
+  switch (ch) {
+    case 'C': return 2;
+    case 'T': return 4;
+    case 'G': return 8;
+    case 'N': return 15;
+    default: return 1;  // 'A' and every other byte
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Lane arithmetic policies.  V is what one lane holds per matrix cell slot (64 bits for the
+// two product policies), S the scalar type, NR the number of reads carried per lane.
+// ------------------------------------------------------------------------------------------
+struct VF2 {  // two reads per lane, packed fp32
+  typedef float2 V;
+  typedef float S;
+  static constexpr int NR = 2;
+  static constexpr bool kDouble = false;
+  __device__ static __forceinline__ V mul(V a, V b) { return __fmul2_rn(a, b); }
+  __device__ static __forceinline__ V fma(V a, V b, V c) { return __ffma2_rn(a, b, c); }
+  __device__ static __forceinline__ V add(V a, V b) { return __fadd2_rn(a, b); }
+  __device__ static __forceinline__ V splat(S s) { return make_float2(s, s); }
+  __device__ static __forceinline__ S get(const V& v, int x) { return x == 0 ? v.x : v.y; }
+  __device__ static __forceinline__ void set(V& v, int x, S s) {
+    if (x == 0) v.x = s; else v.y = s;
+  }
+  // per-half select on the nibble test of each read's match word
+  __device__ static __forceinline__ V sel(const uint32_t* mw, uint32_t bit, V a, V b) {
+    return make_float2((mw[0] & bit) ? a.x : b.x, (mw[1] & bit) ? a.y : b.y);
+  }
+  __device__ static __forceinline__ V shfl_up(V v, int width) {
+    return make_float2(__shfl_up_sync(0xffffffffu, v.x, 1, width), __shfl_up_sync(0xffffffffu, v.y, 1, width));
+  }
+};
+
+struct VF1 {  // one read per lane, scalar fp32 (kept for measurement against VF2)
+  typedef float V;
+  typedef float S;
+  static constexpr int NR = 1;
+  static constexpr bool kDouble = false;
+  __device__ static __forceinline__ V mul(V a, V b) { return a * b; }
+  __device__ static __forceinline__ V fma(V a, V b, V c) { return fmaf(a, b, c); }
+  __device__ static __forceinline__ V add(V a, V b) { return a + b; }
+  __device__ static __forceinline__ V splat(S s) { return s; }
+  __device__ static __forceinline__ S get(const V& v, int) { return v; }
+  __device__ static __forceinline__ void set(V& v, int, S s) { v = s; }
+  __device__ static __forceinline__ V sel(const uint32_t* mw, uint32_t bit, V a, V b) {
+    return (mw[0] & bit) ? a : b;
+  }
+  __device__ static __forceinline__ V shfl_up(V v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
+};
+
+struct VD1 {  // one read per lane, fp64 (useDoublePrecision and the fallback rerun)
+  typedef double V;
+  typedef double S;
+  static constexpr int NR = 1;
+  static constexpr bool kDouble = true;
+  __device__ static __forceinline__ V mul(V a, V b) { return a * b; }
+  __device__ static __forceinline__ V fma(V a, V b, V c) { return ::fma(a, b, c); }
+  __device__ static __forceinline__ V add(V a, V b) { return a + b; }
+  __device__ static __forceinline__ V splat(S s) { return s; }
+  __device__ static __forceinline__ S get(const V& v, int) { return v; }
+  __device__ static __forceinline__ void set(V& v, int, S s) { v = s; }
+  __device__ static __forceinline__ V sel(const uint32_t* mw, uint32_t bit, V a, V b) {
+    return (mw[0] & bit) ? a : b;
+  }
+  __device__ static __forceinline__ V shfl_up(V v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
+};
+
+// ------------------------------------------------------------------------------------------
+// Kernel parameters
+// ------------------------------------------------------------------------------------------
+struct PanelRef {          // one haplotype tile, as an image that is bulk-copied to shared memory:
+  const uint8_t* image;    //   int32 hpos[n]  (byte offset of column 0 inside the image)
+  uint32_t bytes;          //   int32 hlen[n]
+  int n_haps;              //   pad to 16, then per haplotype: left margin | nibbles | right margin
+  int hap0;                // index of the tile's first haplotype in the batch
+  int n_haps_total;        // H of the batch (row pitch of the output)
+  int max_hap_len;         // longest haplotype in the tile
+};
+
+struct ClassRef {          // the reads of one length class, packed by k_pack_reads
+  const uint8_t* records;  // [n_rec][5 planes][stride]   planes: base nibble, qual, insGOP, delGOP, GCP (all & 127)
+  const int32_t* rec_rid;  // [n_rec] read index in the batch, -1 for filler records
+  const int32_t* rec_len;  // [n_rec] read length (0 for filler)
+  int n_rec;               // multiple of the reads-per-warp of the class kernel
+  int rows;                // rows per record = n_pass * G * K (reads are padded at the top up to this)
+  int stride;              // bytes per plane = rows rounded up to 16
+  int n_pass;              // passes of G*K rows
+};
+
+struct SweepParams {
+  PanelRef panel;
+  ClassRef cls;
+  const void* ph2pr;            // S[128]
+  const void* mm;               // S[kMmTableSize]
+  double* out;                  // [n_reads][n_haps_total] log10 likelihoods
+  // task mode
+  int hap_chunk;                // haplotypes per task
+  int n_chunks;                 // chunks per tile
+  int n_tasks;                  // (n_rec / RPW) * n_chunks
+  unsigned int* task_counter;
+  // list mode (fp64 rerun of flagged pairs): items are (record, haplotype-in-batch)
+  const uint2* list_items;
+  const unsigned int* list_count;
+  // where the fp32 kernel appends pairs whose scaled sum is < 1e-28f (IntelPairHmm.cc:159)
+  uint2* fb_items;
+  unsigned int* fb_count;
+  // multi-pass carry scratch: per warp, per group, 3 * (max_hap_len + 2) V's
+  void* carry;
+  size_t carry_stride_bytes;    // bytes per warp
+  double init_const;            // 2^120 (fp32) or 2^1020 (fp64)   Context.h:142,183
+  double log10_init;            // log10f(2^120) widened, or log10(2^1020)
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + 1-D bulk TMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-lane constants of K rows (x NR reads)
+// ------------------------------------------------------------------------------------------
+template <class P, int K>
+struct LaneRows {
+  // VAR 0 (premultiplied): Am=(1-e)*pMM, Ax=(e/3)*pMM, Gm=(1-e)*pGAPM, Gx=(e/3)*pGAPM
+  // VAR 1 (plain):         Am=pMM, Ax=pGAPM, Gm=1-e, Gx=e/3
+  typename P::V Am[K], Ax[K], Gm[K], Gx[K];
+  typename P::V pMX[K], pXX[K], pMY[K];      // pYY == pXX (both ph2pr[gcp], avx-pairhmm-template.h:142-146)
+  typename P::V pXXtop;                      // pXX[0] as used by the X update (zeroed on the first lane of pass 0)
+  uint32_t rbm[P::NR][(K + 7) / 8];          // read-base one-hot nibbles, row j at bits 4*(j%8) of word j/8
+  uint32_t padmask[P::NR];                   // bit j set: row j is a top-padding row
+};
+
+__device__ __forceinline__ int mm_index(int ins_q, int del_q) {  // Context.h:156-167,197-209
+  int mx = max(ins_q, del_q), mn = min(ins_q, del_q);
+  return ((mx * (mx + 1)) >> 1) + mn;
+}
+
+// rec: one read's 5 planes (generic pointer: shared slot or global), rows [row0, row0+K).
+// first_pad: number of top-padding rows of the whole read; top_is_row0: lane 0 of pass 0.
+template <class P, int K, int VAR>
+__device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const uint8_t* rec, int stride, int row0,
+                                               int n_pad, bool top_is_row0, const typename P::S* __restrict__ ph2pr,
+                                               const typename P::S* __restrict__ mm) {
+  typedef typename P::S S;
+  uint32_t pm = 0;
+#pragma unroll
+  for (int w = 0; w < (K + 7) / 8; w++) L.rbm[x][w] = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const int row = row0 + j;
+    const bool pad = row < n_pad;
+    const uint32_t nib = rec[row];
+    const int q = rec[stride + row], ig = rec[2 * stride + row], dg = rec[3 * stride + row], cg = rec[4 * stride + row];
+    S e = ph2pr[q];
+    S om = (S)1 - e;    // stripeINITIALIZATION: _1_distm = 1 - distm
+    S th = e / (S)3;    //                       distm = distm / 3
+    S pmm = __ldg(mm + mm_index(ig, dg));
+    S pc = ph2pr[cg];
+    S pgap = (S)1 - pc;
+    S am, ax, gm, gx;
+    if (VAR == 0) { am = om * pmm; ax = th * pmm; gm = om * pgap; gx = th * pgap; }
+    else { am = pmm; ax = pgap; gm = om; gx = th; }
+    S mx = ph2pr[ig], my = ph2pr[dg], xx = pc;
+    if (pad) { am = ax = gm = gx = (S)0; mx = my = (S)0; xx = (S)1; pm |= 1u << j; }
+    S xxtop = xx;
+    if (j == 0 && top_is_row0) {  // row 0 above: M = X = 0, so the M-diagonal and X inputs are killed
+      am = (S)0;
+      if (VAR == 0) ax = (S)0;
+      mx = (S)0;
+      xxtop = (S)0;
+    }
+    P::set(L.Am[j], x, am); P::set(L.Ax[j], x, ax); P::set(L.Gm[j], x, gm); P::set(L.Gx[j], x, gx);
+    P::set(L.pMX[j], x, mx); P::set(L.pXX[j], x, xx); P::set(L.pMY[j], x, my);
+    if (j == 0) P::set(L.pXXtop, x, xxtop);
+    L.rbm[x][j / 8] |= (pad ? 0u : nib) << (4 * (j % 8));
+  }
+  L.padmask[x] = pm;
+}
+
+// ------------------------------------------------------------------------------------------
+// One sweep of a group over one haplotype (one pass of G*K rows).
+//   hap      shared-memory pointer to column 0 of this lane's haplotype (margins on both sides)
+//   haplen   its length;  n_steps: warp-uniform loop bound >= haplen + G - 1
+//   first    lane 0 of the group;  initY: INITIAL_CONSTANT / haplen
+//   carry_in / carry_out: bottom row of the previous / this pass (nullptr when unused),
+//   layout [3][max_hap_len + 2] V, index c
+// Returns the running sum of M+X over the lane's bottom row (meaningful on the last lane).
+// ------------------------------------------------------------------------------------------
+template <class P, int G, int K, bool MULTI, int VAR>
+__device__ __forceinline__ typename P::V sweep(const LaneRows<P, K>& L, const uint8_t* hap, int haplen, int n_steps,
+                                               int t, typename P::S initY, bool pass0,
+                                               const typename P::V* carry_in, typename P::V* carry_out,
+                                               int carry_pitch) {
+  typedef typename P::V V;
+  const V zero = P::splat(0);
+  V Ml[K], Yl[K], XYl[K];
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    Ml[j] = zero;
+    V y0 = zero;
+#pragma unroll
+    for (int x = 0; x < P::NR; x++)
+      if (L.padmask[x] & (1u << j)) P::set(y0, x, initY);
+    Yl[j] = y0;
+    XYl[j] = y0;
+  }
+  V botX = zero, sum = zero;
+  const bool first = (t == 0);
+  const bool row0_above = first && pass0;
+  const V initYv = P::splat(initY);
+  // bottom row of the lane above at the previous step's column; for the first lane that is
+  // column 0 of row 0 (M = 0, Y = init) or of the previous pass's bottom row
+  V dMp = zero, dXYp = row0_above ? initYv : zero;
+  if (MULTI) {
+    if (first && !pass0) {
+      dMp = carry_in[0];
+      dXYp = carry_in[2 * carry_pitch];
+    }
+    if (carry_out != nullptr && t == G - 1) {  // column 0 of this pass's bottom row
+      carry_out[0] = zero;
+      carry_out[carry_pitch] = zero;
+      carry_out[2 * carry_pitch] = XYl[K - 1];
+    }
+  }
+  int c = 1 - t;
+  uint32_t hb = hap[max(c, -kHapLeftMargin + 1)];
+#pragma unroll 2
+  for (int s = 1; s <= n_steps; s++, c++) {
+    // what the lane above computed one step ago (its column c)
+    V uM = P::shfl_up(Ml[K - 1], G);
+    V uX = P::shfl_up(botX, G);
+    V uXY = P::shfl_up(XYl[K - 1], G);
+    if (row0_above) uXY = initYv;  // row 0: M = X = 0 (killed by the zeroed top constants), Y = init
+    if (MULTI) {
+      if (first && !pass0) {
+        const int cc = min(max(c, 0), haplen + 1);
+        uM = carry_in[cc];
+        uX = carry_in[carry_pitch + cc];
+        uXY = carry_in[2 * carry_pitch + cc];
+      }
+    }
+    const uint32_t hrep = hb * 0x11111111u;
+    hb = hap[min(c + 1, haplen + 1)];  // prefetch next column's symbol
+    if ((unsigned)(c - 1) < (unsigned)haplen) {
+      uint32_t mw[P::NR][(K + 7) / 8];
+#pragma unroll
+      for (int x = 0; x < P::NR; x++)
+#pragma unroll
+        for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = L.rbm[x][w] & hrep;
+      V dM = dMp, dXY = dXYp, upM = uM, upX = uX;
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        uint32_t m2[P::NR];
+#pragma unroll
+        for (int x = 0; x < P::NR; x++) m2[x] = mw[x][j / 8];
+        const uint32_t bit = 0xFu << (4 * (j % 8));
+        V Mn;
+        if (VAR == 0) {
+          const V A = P::sel(m2, bit, L.Am[j], L.Ax[j]);
+          const V Gs = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
+          Mn = P::fma(A, dM, P::mul(Gs, dXY));
+        } else {
+          const V prior = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
+          Mn = P::mul(prior, P::fma(L.Am[j], dM, P::mul(L.Ax[j], dXY)));
+        }
+        const V Xn = P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
+        const V Yn = P::fma(L.pXX[j], Yl[j], P::mul(L.pMY[j], Ml[j]));
+        dM = Ml[j];
+        dXY = XYl[j];
+        Ml[j] = Mn;
+        Yl[j] = Yn;
+        XYl[j] = P::add(Xn, Yn);
+        upM = Mn;
+        upX = Xn;
+      }
+      botX = upX;
+      sum = P::add(sum, P::add(upM, upX));
+      if (MULTI) {
+        if (carry_out != nullptr && t == G - 1) {
+          carry_out[c] = upM;
+          carry_out[carry_pitch + c] = upX;
+          carry_out[2 * carry_pitch + c] = XYl[K - 1];
+        }
+      }
+    }
+    dMp = uM;
+    dXYp = uXY;
+  }
+  return sum;
+}
+
+// Result of one pair (IntelPairHmm.cc:157-167).  Returns false when the pair must be rerun in fp64.
+template <class P>
+__device__ __forceinline__ bool finish_pair(typename P::S sum, double log10_init, double* out) {
+  if (P::kDouble) {
+    *out = log10((double)sum) - log10_init;
+    return true;
+  } else {
+    if ((float)sum < kMinAccepted) return false;
+    // log10f(result_float) - log10f(2^120), evaluated in float, widened
+    const float lg = (float)log10((double)sum);
+    *out = (double)(lg - (float)log10_init);
+    return true;
+  }
+}
+
+// Shared memory layout of the sweep kernels.
+struct SmemLayout {
+  uint32_t bars;     // offset of mbarriers: [0] panel, [1 + w] slot of warp w
+  uint32_t ph2pr;    // S[128]
+  uint32_t panel;    // panel image
+  uint32_t slots;    // per-warp record slots
+  uint32_t slot_bytes;
+  uint32_t total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int warps, uint32_t panel_bytes, uint32_t slot_bytes,
+                                                  uint32_t scalar_bytes) {
+  SmemLayout l;
+  l.bars = 0;
+  l.ph2pr = (uint32_t)((8 * (1 + warps) + 127) / 128 * 128);
+  l.panel = l.ph2pr + 128 * scalar_bytes;
+  l.slots = (l.panel + panel_bytes + 127) / 128 * 128;
+  l.slot_bytes = (slot_bytes + 127) / 128 * 128;
+  l.total = l.slots + (uint32_t)warps * l.slot_bytes;
+  return l;
+}
+
+// ------------------------------------------------------------------------------------------
+// Task kernel: persistent CTAs; a task = (block of RPW records) x (chunk of haplotypes).
+// ------------------------------------------------------------------------------------------
+template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams p) {
+  typedef typename P::V V;
+  typedef typename P::S S;
+  constexpr int GPW = 32 / G;           // groups per warp
+  constexpr int RPW = GPW * P::NR;      // records per warp-task
+  extern __shared__ __align__(128) uint8_t smem[];
+  const SmemLayout lay = smem_layout(WARPS, p.panel.bytes, (uint32_t)(RPW * 5 * p.cls.stride), sizeof(S));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
+  S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
+  const uint8_t* panel_s = smem + lay.panel;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane % G, g = lane / G;
+  uint8_t* slot = smem + lay.slots + (size_t)warp * lay.slot_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 1 + WARPS; i++) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = reinterpret_cast<const S*>(p.ph2pr)[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], p.panel.bytes);
+    tma_bulk_g2s(smem + lay.panel, p.panel.image, p.panel.bytes, &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  const int32_t* hpos = reinterpret_cast<const int32_t*>(panel_s);
+  const int32_t* hlen = hpos + p.panel.n_haps;
+
+  const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
+  uint32_t slot_parity = 0;
+  const int cap = G * K;
+  V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) +
+                                          ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride_bytes)
+                   : nullptr;
+  const int carry_pitch = p.panel.max_hap_len + 2;
+
+  for (;;) {
+    unsigned int task = 0;
+    if (lane == 0) task = atomicAdd(p.task_counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= (unsigned)p.n_tasks) break;
+    const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
+    const int rec0 = blk * RPW;
+    // stage the block's packed records into this warp's slot
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(&bars[1 + warp], RPW * rec_bytes);
+      tma_bulk_g2s(slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, &bars[1 + warp]);
+    }
+    mbar_wait(&bars[1 + warp], slot_parity);
+    slot_parity ^= 1;
+
+    int rid[P::NR], npad[P::NR];
+#pragma unroll
+    for (int x = 0; x < P::NR; x++) {
+      const int rec = rec0 + g * P::NR + x;
+      rid[x] = p.cls.rec_rid[rec];
+      npad[x] = p.cls.rows - p.cls.rec_len[rec];
+    }
+    const int h_begin = chunk * p.hap_chunk, h_end = min(p.panel.n_haps, h_begin + p.hap_chunk);
+
+    LaneRows<P, K> L;
+    if (!MULTI) {
+#pragma unroll
+      for (int x = 0; x < P::NR; x++)
+        load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, t * K, npad[x], t == 0,
+                             ph2pr_s, reinterpret_cast<const S*>(p.mm));
+    }
+    for (int h = h_begin; h < h_end; h++) {
+      const int haplen = hlen[h];
+      const uint8_t* hap = panel_s + hpos[h];
+      const S initY = (S)p.init_const / (S)haplen;
+      const int n_steps = haplen + G - 1;
+      V sum = P::splat(0);
+      if (!MULTI) {
+        sum = sweep<P, G, K, false, VAR>(L, hap, haplen, n_steps, t, initY, true, nullptr, nullptr, 0);
+      } else {
+        V* cg = carry + (size_t)g * 6 * carry_pitch;  // two buffers of 3 lines, ping-pong
+        for (int pass = 0; pass < p.cls.n_pass; pass++) {
+#pragma unroll
+          for (int x = 0; x < P::NR; x++)
+            load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, pass * cap + t * K,
+                                 npad[x], t == 0 && pass == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
+          V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
+          V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
+          sum = sweep<P, G, K, true, VAR>(L, hap, haplen, n_steps, t, initY, pass == 0, cin,
+                                     pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
+          __syncwarp();  // carry written by lane G-1 is read by lane 0 of the next pass
+        }
+      }
+      if (t == G - 1) {
+#pragma unroll
+        for (int x = 0; x < P::NR; x++) {
+          if (rid[x] >= 0) {
+            double* o = p.out + (size_t)rid[x] * p.panel.n_haps_total + (p.panel.hap0 + h);
+            if (!finish_pair<P>(P::get(sum, x), p.log10_init, o)) {
+              *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the fp64 rerun
+              const unsigned int k = atomicAdd(p.fb_count, 1u);
+              p.fb_items[k] = make_uint2((unsigned)(rec0 + g * P::NR + x), (unsigned)(p.panel.hap0 + h));
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// List kernel: every group takes one (record, haplotype) item at a time -- the fp64 rerun of the
+// pairs the fp32 kernel flagged.  NR must be 1.
+// ------------------------------------------------------------------------------------------
+template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams p) {
+  typedef typename P::V V;
+  typedef typename P::S S;
+  static_assert(P::NR == 1, "list kernel carries one read per lane");
+  constexpr int GPW = 32 / G;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const unsigned int n_items = *p.list_count;
+  if (n_items == 0) return;
+  const SmemLayout lay = smem_layout(WARPS, p.panel.bytes, 0, sizeof(S));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
+  S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
+  const uint8_t* panel_s = smem + lay.panel;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane % G, g = lane / G;
+  if (threadIdx.x == 0) {
+    mbar_init(&bars[0], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = reinterpret_cast<const S*>(p.ph2pr)[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], p.panel.bytes);
+    tma_bulk_g2s(smem + lay.panel, p.panel.image, p.panel.bytes, &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  const int32_t* hpos = reinterpret_cast<const int32_t*>(panel_s);
+  const int32_t* hlen = hpos + p.panel.n_haps;
+  const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
+  const int cap = G * K;
+  V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) +
+                                          ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride_bytes)
+                   : nullptr;
+  const int carry_pitch = p.panel.max_hap_len + 2;
+  const unsigned int n_warp_items = (n_items + GPW - 1) / GPW;
+
+  for (;;) {
+    unsigned int wi = 0;
+    if (lane == 0) wi = atomicAdd(p.task_counter, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= n_warp_items) break;
+    const unsigned int item = wi * GPW + g;
+    const bool valid = item < n_items;
+    const uint2 it = valid ? p.list_items[item] : make_uint2(0u, 0u);
+    const int h = (int)it.y - p.panel.hap0;
+    const bool mine = valid && h >= 0 && h < p.panel.n_haps;  // items of other tiles are skipped
+    const int rec = (int)it.x;
+    const int haplen = mine ? hlen[h] : 0;
+    const uint8_t* hap = panel_s + (mine ? hpos[h] : hpos[0]);
+    const int rid = mine ? p.cls.rec_rid[rec] : -1;
+    const int npad = mine ? p.cls.rows - p.cls.rec_len[rec] : 0;
+    const S initY = (S)p.init_const / (S)max(haplen, 1);
+    int n_steps = mine ? haplen + G - 1 : 0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) n_steps = max(n_steps, __shfl_xor_sync(0xffffffffu, n_steps, o));
+    const uint8_t* recp = p.cls.records + (size_t)rec * rec_bytes;
+    LaneRows<P, K> L;
+    V sum = P::splat(0);
+    if (!MULTI) {
+      load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, t * K, npad, t == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
+      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, n_steps, t, initY, true, nullptr, nullptr, 0);
+    } else {
+      V* cg = carry + (size_t)g * 6 * carry_pitch;
+      for (int pass = 0; pass < p.cls.n_pass; pass++) {
+        load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, pass * cap + t * K, npad, t == 0 && pass == 0, ph2pr_s,
+                             reinterpret_cast<const S*>(p.mm));
+        V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
+        V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
+        sum = sweep<P, G, K, true, VAR>(L, hap, haplen, n_steps, t, initY, pass == 0, cin,
+                                   pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
+        __syncwarp();
+      }
+    }
+    if (t == G - 1 && mine && rid >= 0) {
+      double* o = p.out + (size_t)rid * p.panel.n_haps_total + (p.panel.hap0 + h);
+      finish_pair<P>(P::get(sum, 0), p.log10_init, o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Packing kernel: raw batch arenas -> class records (top-padded, planes of `stride` bytes).
+// One warp per record.
+// ------------------------------------------------------------------------------------------
+struct PackParams {
+  const int64_t* read_off;
+  const uint8_t* bases;
+  const uint8_t* quals;
+  const uint8_t* ins;
+  const uint8_t* del;
+  const uint8_t* gcp;
+  uint8_t* records;
+  const int32_t* rec_rid;
+  int n_rec;
+  int rows;
+  int stride;
+};
+
+}  // namespace gklb

@@ -1,0 +1,100 @@
+// pairhmm_kernels.cu -- instantiations of the sweep kernels and their registry.
+//
+// Product instantiations: packed-fp32 (VF2) and fp64 (VD1) for every length class of
+// engine.cu's class table, plus the multi-pass variants for reads longer than 256 rows.
+// The remaining entries (VF1, VAR 0, alternative warp counts) exist so that the design choices
+// can be re-measured on the GPU (bench/sweep.py); the engine only uses them when told to
+// through GKLB_FORCE_KERNEL.
+#include "pairhmm_kernels.h"
+
+namespace gklb {
+
+// One warp per record: raw batch arenas -> top-padded class records.
+__global__ void k_pack_reads(const PackParams p) {
+  const int rec = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (rec >= p.n_rec) return;
+  const int rid = p.rec_rid[rec];
+  int64_t off = 0;
+  int len = 0;
+  if (rid >= 0) {
+    off = p.read_off[rid];
+    len = (int)(p.read_off[rid + 1] - off);
+  }
+  const int npad = p.rows - len;
+  uint8_t* r = p.records + (size_t)rec * 5 * p.stride;
+  for (int row = lane; row < p.stride; row += 32) {
+    uint8_t b = 0, q = 0, i = 0, d = 0, c = 0;
+    if (row >= npad && row < p.rows) {
+      const int64_t s = off + (row - npad);
+      b = base_nibble(p.bases[s]);
+      q = p.quals[s] & 127;  // avx-pairhmm-template.h:134-136,149
+      i = p.ins[s] & 127;
+      d = p.del[s] & 127;
+      c = p.gcp[s] & 127;
+    }
+    r[row] = b;
+    r[p.stride + row] = q;
+    r[2 * p.stride + row] = i;
+    r[3 * p.stride + row] = d;
+    r[4 * p.stride + row] = c;
+  }
+}
+
+#define GKLB_TASKS(P, G, K, W, M, V) reinterpret_cast<const void*>(&k_sweep_tasks<P, G, K, W, M, V>)
+#define GKLB_LIST(P, G, K, W, M, V) reinterpret_cast<const void*>(&k_sweep_list<P, G, K, W, M, V>)
+#define E_F2(G, K, W, M, V) {POL_F2, G, K, W, M, V, 2, GKLB_TASKS(VF2, G, K, W, M, V), nullptr}
+#define E_F1(G, K, W, M, V) {POL_F1, G, K, W, M, V, 1, GKLB_TASKS(VF1, G, K, W, M, V), nullptr}
+#define E_D1(G, K, W, M, V) {POL_D1, G, K, W, M, V, 1, GKLB_TASKS(VD1, G, K, W, M, V), GKLB_LIST(VD1, G, K, W, M, V)}
+
+static const KernelEntry g_table[] = {
+    // ---- product: packed fp32, plain form (VAR 1) ----
+    E_F2(8, 4, 8, false, 1),  E_F2(8, 5, 8, false, 1),  E_F2(8, 6, 8, false, 1),  E_F2(8, 7, 8, false, 1),
+    E_F2(8, 8, 8, false, 1),  E_F2(16, 5, 8, false, 1), E_F2(16, 6, 8, false, 1), E_F2(16, 7, 8, false, 1),
+    E_F2(16, 8, 8, false, 1), E_F2(32, 5, 8, false, 1), E_F2(32, 6, 8, false, 1), E_F2(32, 7, 8, false, 1),
+    E_F2(32, 8, 8, false, 1), E_F2(32, 8, 8, true, 1),
+    // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
+    E_D1(8, 4, 8, false, 1),  E_D1(8, 5, 8, false, 1),  E_D1(8, 6, 8, false, 1),  E_D1(8, 7, 8, false, 1),
+    E_D1(8, 8, 8, false, 1),  E_D1(16, 5, 8, false, 1), E_D1(16, 6, 8, false, 1), E_D1(16, 7, 8, false, 1),
+    E_D1(16, 8, 8, false, 1), E_D1(32, 5, 8, false, 1), E_D1(32, 6, 8, false, 1), E_D1(32, 7, 8, false, 1),
+    E_D1(32, 8, 8, false, 1), E_D1(32, 8, 8, true, 1),
+#ifdef GKLB_EXPERIMENTAL
+    // ---- measurement only ----
+    E_F2(16, 7, 8, false, 0), E_F2(16, 6, 12, false, 1), E_F2(16, 6, 12, false, 0), E_F2(16, 7, 12, false, 1),
+    E_F2(32, 4, 8, false, 1), E_F2(32, 4, 12, false, 1), E_F2(32, 4, 16, false, 1), E_F2(32, 4, 16, false, 0),
+    E_F2(16, 8, 8, false, 0), E_F2(16, 7, 10, false, 1),
+    E_F1(8, 13, 8, false, 1), E_F1(8, 13, 8, false, 0), E_F1(8, 13, 12, false, 1), E_F1(16, 7, 12, false, 1),
+    E_F1(16, 7, 16, false, 1), E_F1(16, 7, 16, false, 0), E_F1(32, 4, 16, false, 1),
+#endif
+};
+
+const KernelEntry* kernel_table(int* n) {
+  *n = (int)(sizeof(g_table) / sizeof(g_table[0]));
+  return g_table;
+}
+
+const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, int var) {
+  int n;
+  const KernelEntry* t = kernel_table(&n);
+  for (int i = 0; i < n; i++)
+    if (t[i].policy == policy && t[i].G == G && t[i].K == K && (warps <= 0 || t[i].warps == warps) &&
+        t[i].multi == multi && (var < 0 || t[i].var == var))
+      return &t[i];
+  return nullptr;
+}
+
+cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
+  void* args[] = {const_cast<SweepParams*>(&p)};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, s);
+}
+
+cudaError_t launch_pack(const PackParams& p, cudaStream_t s) {
+  const int threads = 256;
+  const long long total = (long long)p.n_rec * 32;
+  const int grid = (int)((total + threads - 1) / threads);
+  if (grid == 0) return cudaSuccess;
+  k_pack_reads<<<grid, threads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace gklb

@@ -1,0 +1,27 @@
+// pairhmm_kernels.h -- host-side registry of the compiled sweep kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "pairhmm_device.cuh"
+
+namespace gklb {
+
+enum Policy { POL_F2 = 0, POL_F1 = 1, POL_D1 = 2 };
+
+struct KernelEntry {
+  int policy, G, K, warps, multi, var;
+  int nr;                  // reads carried per lane
+  const void* fn_tasks;    // k_sweep_tasks instantiation
+  const void* fn_list;     // k_sweep_list instantiation (nullptr when nr != 1)
+};
+
+// All compiled instantiations.
+const KernelEntry* kernel_table(int* n);
+const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, int var);
+
+cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s);
+cudaError_t launch_pack(const PackParams& p, cudaStream_t s);
+
+}  // namespace gklb

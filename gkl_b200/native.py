@@ -1,0 +1,195 @@
+"""ctypes binding of libgkl_pairhmm.so (the C-ABI of include/gklb_pairhmm.h).
+
+The library holds sm_100a code only.  There is no Python or CPU implementation behind these
+calls: if the shared object is missing or no B200-class device is visible, they raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from .batch import PairHmmBatch
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libgkl_pairhmm.so"
+
+OK, ERR_OOM, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = range(6)
+
+
+class GklbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"gklb error {code}: {msg}")
+        self.code = code
+
+
+class _Batch(C.Structure):
+    _fields_ = [("n_reads", C.c_int32), ("n_haps", C.c_int32),
+                ("read_off", C.c_void_p), ("read_bases", C.c_void_p), ("read_quals", C.c_void_p),
+                ("ins_gop", C.c_void_p), ("del_gop", C.c_void_p), ("gcp", C.c_void_p),
+                ("hap_off", C.c_void_p), ("hap_bases", C.c_void_p)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("pairs", C.c_int64), ("cells", C.c_int64), ("fallback_pairs", C.c_int64),
+                ("kernel_launches", C.c_int32), ("n_classes", C.c_int32),
+                ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float)]
+
+
+EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_engine_create",
+           "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_stage",
+           "gklb_engine_stage_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
+           "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
+           "gklb_version", "gklb_device_count", "gklb_pairhmm_table"]
+
+_lib = None
+
+
+def build(experimental: bool = False) -> None:
+    """Compile the library in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    cmd = ["make", "-s", "-C", str(PKG / "csrc")]
+    if experimental:
+        cmd.append("EXPERIMENTAL=1")
+    subprocess.run(cmd, check=True)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(f"{LIB_PATH} is not built: run `make -C gkl_b200/csrc` "
+                                    "(there is no fallback implementation)")
+        l = C.CDLL(str(LIB_PATH))
+        l.gklb_last_error.restype = C.c_char_p
+        l.gklb_version.restype = C.c_char_p
+        l.gklb_pairhmm_table.restype = C.c_void_p
+        l.gklb_pairhmm_table.argtypes = [C.c_int, C.POINTER(C.c_int)]
+        l.gklb_engine_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int]
+        for name in ("gklb_engine_destroy", "gklb_engine_run", "gklb_engine_synchronize"):
+            getattr(l, name).argtypes = [C.c_void_p]
+        l.gklb_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        l.gklb_engine_compute.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
+        l.gklb_engine_stage.argtypes = [C.c_void_p, C.POINTER(_Batch)]
+        l.gklb_engine_stage_device.argtypes = [C.c_void_p, C.POINTER(_Batch)]
+        l.gklb_engine_fetch.argtypes = [C.c_void_p, C.c_void_p]
+        l.gklb_engine_result_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        l.gklb_engine_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
+        l.gklb_engine_time_runs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
+        l.gklb_pairhmm_init.argtypes = [C.c_int, C.c_int]
+        l.gklb_pairhmm_compute.argtypes = [C.POINTER(_Batch), C.c_void_p]
+        _lib = l
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != OK:
+        raise GklbError(rc, lib().gklb_last_error().decode(errors="replace"))
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array, a torch tensor (host or device), or a raw integer address."""
+    if a is None:
+        return 0
+    if isinstance(a, int):
+        return a
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if hasattr(a, "data_ptr"):
+        return a.data_ptr()
+    raise TypeError(type(a))
+
+
+def make_batch(b: PairHmmBatch, arenas=None, hap=None) -> _Batch:
+    """C struct for a batch.  ``arenas`` (5 objects) / ``hap`` override where the byte arenas are
+    read from (e.g. pinned or device tensors); offsets always come from the host arrays."""
+    src = arenas if arenas is not None else (b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp)
+    s = _Batch()
+    s.n_reads, s.n_haps = b.n_reads, b.n_haps
+    s.read_off = _ptr(b.read_off)
+    s.read_bases, s.read_quals, s.ins_gop, s.del_gop, s.gcp = (_ptr(x) for x in src)
+    s.hap_off = _ptr(b.hap_off)
+    s.hap_bases = _ptr(hap if hap is not None else b.hap_bases)
+    return s
+
+
+def tables() -> dict:
+    out = {}
+    for which, (name, dt) in enumerate((("ph2pr_f", np.float32), ("mm_f", np.float32),
+                                        ("ph2pr_d", np.float64), ("mm_d", np.float64))):
+        n = C.c_int(0)
+        p = lib().gklb_pairhmm_table(which, C.byref(n))
+        out[name] = np.ctypeslib.as_array(C.cast(p, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(n.value,)).copy()
+    return out
+
+
+class Engine:
+    """One engine = one device + one stream.  Thin wrapper over the gklb_engine_* entry points."""
+
+    def __init__(self, device: int = 0, use_double: bool = False):
+        self._h = C.c_void_p()
+        _check(lib().gklb_engine_create(C.byref(self._h), device, int(use_double)))
+        self._keep = None
+
+    def close(self) -> None:
+        if self._h:
+            lib().gklb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int | None) -> None:
+        _check(lib().gklb_engine_set_stream(self._h, cuda_stream or 0))
+
+    def compute(self, b: PairHmmBatch, out: np.ndarray | None = None, arenas=None, hap=None, out_ptr=None):
+        """Host buffers in, log10 likelihoods[r * n_haps + h] out (synchronous)."""
+        b.validate()
+        if out is None and out_ptr is None:
+            out = np.empty(b.n_reads * b.n_haps, dtype=np.float64)
+        s = make_batch(b, arenas, hap)
+        _check(lib().gklb_engine_compute(self._h, C.byref(s), out_ptr if out_ptr is not None else _ptr(out)))
+        return out
+
+    def stage(self, b: PairHmmBatch, arenas=None, hap=None, device: bool = False) -> None:
+        b.validate()
+        s = make_batch(b, arenas, hap)
+        self._keep = (b, arenas, hap)
+        fn = lib().gklb_engine_stage_device if device else lib().gklb_engine_stage
+        _check(fn(self._h, C.byref(s)))
+
+    def run(self) -> None:
+        _check(lib().gklb_engine_run(self._h))
+
+    def fetch(self, n: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty(n if n is not None else self.stats().pairs, dtype=np.float64)
+        _check(lib().gklb_engine_fetch(self._h, _ptr(out)))
+        return out
+
+    def synchronize(self) -> None:
+        _check(lib().gklb_engine_synchronize(self._h))
+
+    def result_device_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib().gklb_engine_result_device(self._h, C.byref(p)))
+        return p.value
+
+    def time_runs(self, iters: int) -> float:
+        ms = C.c_float(0)
+        _check(lib().gklb_engine_time_runs(self._h, iters, C.byref(ms)))
+        return ms.value
+
+    def stats(self) -> Stats:
+        s = Stats()
+        _check(lib().gklb_engine_stats(self._h, C.byref(s)))
+        return s
+
+
+def device_count() -> int:
+    return int(lib().gklb_device_count())

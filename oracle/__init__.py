@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE ONLY.
+
+ctypes access to the two CPU checkers:
+
+* ``port_*``  -- oracle/libgklb_oracle.so, the CPU restatement written in this repo
+  (pairhmm_oracle.c / pdhmm_oracle.c; ``make -C oracle port``);
+* ``ref_*``   -- oracle/_ref/libgkl_ref.so, GKL's own unmodified translation units compiled from
+  /root/reference (``make -C oracle ref``; only buildable in the development container, the
+  built .so travels to the GPU box).
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` leg
+may import this package.  The product (gkl_b200/) never does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+PORT_SO = HERE / "libgklb_oracle.so"
+REF_SO = HERE / "_ref" / "libgkl_ref.so"
+REFERENCE_ROOT = Path("/root/reference")
+
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+_f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+
+
+def build(ref: bool | None = None) -> None:
+    """Compile the checkers (idempotent; make decides what is stale)."""
+    targets = ["port"]
+    if ref is None:
+        ref = REFERENCE_ROOT.is_dir()
+    if ref:
+        targets.append("ref")
+    subprocess.run(["make", "-s", "-C", str(HERE), *targets], check=True)
+
+
+_port = None
+_ref = None
+
+
+def _load_port():
+    global _port
+    if _port is None:
+        if not PORT_SO.exists():
+            build(ref=False)
+        lib = C.CDLL(str(PORT_SO))
+        lib.gklport_pairhmm.restype = C.c_int
+        lib.gklport_pairhmm.argtypes = [C.c_int, C.c_int, _i64p, _u8p, _u8p, _u8p, _u8p, _u8p, _i64p, _u8p,
+                                        C.c_int, C.c_int, _f64p, C.c_void_p, C.POINTER(C.c_double)]
+        lib.gklport_max_threads.restype = C.c_int
+        for name, ty in (("gklport_ph2pr_f", C.c_float), ("gklport_mm_f", C.c_float),
+                         ("gklport_ph2pr_d", C.c_double), ("gklport_mm_d", C.c_double)):
+            getattr(lib, name).restype = C.POINTER(ty)
+        _port = lib
+    return _port
+
+
+def ref_available() -> bool:
+    return REF_SO.exists()
+
+
+def _load_ref():
+    global _ref
+    if _ref is None:
+        if not REF_SO.exists():
+            if REFERENCE_ROOT.is_dir():
+                build(ref=True)
+            else:
+                raise FileNotFoundError(f"{REF_SO} missing and /root/reference absent: run `make -C oracle ref` "
+                                        "in the development container")
+        lib = C.CDLL(str(REF_SO))
+        lib.gklref_pairhmm.restype = C.c_int
+        lib.gklref_pairhmm.argtypes = [C.c_int, C.c_int, _i64p, _u8p, _u8p, _u8p, _u8p, _u8p, _i64p, _u8p,
+                                       C.c_int, C.c_int, C.c_int, _f64p, C.POINTER(C.c_int),
+                                       C.POINTER(C.c_double)]
+        lib.gklref_max_threads.restype = C.c_int
+        lib.gklref_avx512_supported.restype = C.c_int
+        _ref = lib
+    return _ref
+
+
+def host_threads() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def port_pairhmm(batch, use_double: bool = False, threads: int = 1):
+    """CPU restatement.  Returns (log10 likelihoods[R*H], fallback flags[R*H], pair-loop seconds)."""
+    lib = _load_port()
+    n = batch.n_reads * batch.n_haps
+    out = np.empty(n, dtype=np.float64)
+    fb = np.zeros(n, dtype=np.uint8)
+    secs = C.c_double(0)
+    rc = lib.gklport_pairhmm(batch.n_reads, batch.n_haps, batch.read_off, batch.read_bases, batch.read_quals,
+                             batch.ins_gop, batch.del_gop, batch.gcp, batch.hap_off, batch.hap_bases,
+                             int(use_double), int(threads), out, fb.ctypes.data_as(C.c_void_p), C.byref(secs))
+    if rc != 0:
+        raise RuntimeError(f"gklport_pairhmm failed: {rc}")
+    return out, fb, secs.value
+
+
+def ref_pairhmm(batch, use_double: bool = False, threads: int = 1, engine: int = 0):
+    """GKL's own compiled AVX / AVX-512 PairHMM driven by the loop of IntelPairHmm.cc:150-169.
+
+    engine: 0 = GKL's CPUID dispatch, 1 = force AVX, 2 = force AVX-512.
+    Returns (log10 likelihoods[R*H], used_avx512, pair-loop seconds)."""
+    lib = _load_ref()
+    n = batch.n_reads * batch.n_haps
+    out = np.empty(n, dtype=np.float64)
+    used = C.c_int(0)
+    secs = C.c_double(0)
+    rc = lib.gklref_pairhmm(batch.n_reads, batch.n_haps, batch.read_off, batch.read_bases, batch.read_quals,
+                            batch.ins_gop, batch.del_gop, batch.gcp, batch.hap_off, batch.hap_bases,
+                            int(use_double), int(threads), int(engine), out, C.byref(used), C.byref(secs))
+    if rc != 0:
+        raise RuntimeError(f"gklref_pairhmm failed: {rc}")
+    return out, bool(used.value), secs.value
+
+
+def ref_avx512_supported() -> bool:
+    return bool(_load_ref().gklref_avx512_supported())
+
+
+def port_tables():
+    """Host tables of the restatement (for bit-exact comparison with the engine's tables)."""
+    lib = _load_port()
+    mm_size = (255 * 256) // 2
+    return {
+        "ph2pr_f": np.ctypeslib.as_array(lib.gklport_ph2pr_f(), shape=(128,)).copy(),
+        "mm_f": np.ctypeslib.as_array(lib.gklport_mm_f(), shape=(mm_size,)).copy(),
+        "ph2pr_d": np.ctypeslib.as_array(lib.gklport_ph2pr_d(), shape=(128,)).copy(),
+        "mm_d": np.ctypeslib.as_array(lib.gklport_mm_d(), shape=(mm_size,)).copy(),
+    }
