@@ -205,9 +205,13 @@ template <class P, int K>
 struct LaneRows {
   // VAR 0 (premultiplied): Am=(1-e)*pMM, Ax=(e/3)*pMM, Gm=(1-e)*pGAPM, Gx=(e/3)*pGAPM
   // VAR 1 (plain):         Am=pMM, Ax=pGAPM, Gm=1-e, Gx=e/3
+  // VAR 2 (folded):        Am=pMM, Ax=pGAPM(next row), Gm=1-e, Gx=e/3, pMY holds pMY*pGAPM(next row):
+  //                        the Y state is Y/pMY and the diagonal state is pGAPM(next row)*(X+Y), which
+  //                        takes one multiply out of the Y update and one out of the M update
   typename P::V Am[K], Ax[K], Gm[K], Gx[K];
   typename P::V pMX[K], pXX[K], pMY[K];      // pYY == pXX (both ph2pr[gcp], avx-pairhmm-template.h:142-146)
   typename P::V pXXtop;                      // pXX[0] as used by the X update (zeroed on the first lane of pass 0)
+  typename P::V gTop;                        // VAR 2: pGAPM of the lane's first row (0 if it is padding)
   uint32_t rbm[P::NR][(K + 7) / 8];          // read-base one-hot nibbles, row j at bits 4*(j%8) of word j/8
   uint32_t padmask[P::NR];                   // bit j set: row j is a top-padding row
 };
@@ -220,8 +224,8 @@ __device__ __forceinline__ int mm_index(int ins_q, int del_q) {  // Context.h:15
 // rec: one read's 5 planes (generic pointer: shared slot or global), rows [row0, row0+K).
 // first_pad: number of top-padding rows of the whole read; top_is_row0: lane 0 of pass 0.
 template <class P, int K, int VAR>
-__device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const uint8_t* rec, int stride, int row0,
-                                               int n_pad, bool top_is_row0, const typename P::S* __restrict__ ph2pr,
+__device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const uint8_t* rec, int stride, int n_rows,
+                                               int row0, int n_pad, bool top_is_row0, const typename P::S* __restrict__ ph2pr,
                                                const typename P::S* __restrict__ mm) {
   typedef typename P::S S;
   uint32_t pm = 0;
@@ -244,6 +248,14 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
     else { am = pmm; ax = pgap; gm = om; gx = th; }
     S mx = ph2pr[ig], my = ph2pr[dg], xx = pc;
     if (pad) { am = ax = gm = gx = (S)0; mx = my = (S)0; xx = (S)1; pm |= 1u << j; }
+    if (VAR == 2) {
+      // pGAPM of the row below (0 past the last row and for padding rows, whose M must stay 0)
+      S gnext = (S)0;
+      if (row + 1 < n_rows && row + 1 >= n_pad) gnext = (S)1 - ph2pr[rec[4 * stride + row + 1]];
+      ax = gnext;
+      my = (pad ? (S)1 : my) * gnext;
+      if (j == 0) P::set(L.gTop, x, pad ? (S)0 : pgap);
+    }
     S xxtop = xx;
     if (j == 0 && top_is_row0) {  // row 0 above: M = X = 0, so the M-diagonal and X inputs are killed
       am = (S)0;
@@ -261,114 +273,174 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
 
 // ------------------------------------------------------------------------------------------
 // One sweep of a group over one haplotype (one pass of G*K rows).
-//   hap      shared-memory pointer to column 0 of this lane's haplotype (margins on both sides)
-//   haplen   its length;  n_steps: warp-uniform loop bound >= haplen + G - 1
-//   first    lane 0 of the group;  initY: INITIAL_CONSTANT / haplen
+//   hap       shared-memory pointer to column 0 of this lane's haplotype (margins on both sides)
+//   haplen    its length
+//   steady_end  warp-uniform: every lane of the warp has 1 <= c <= haplen for steps G..steady_end
+//   n_steps   warp-uniform loop bound >= haplen + G - 1
 //   carry_in / carry_out: bottom row of the previous / this pass (nullptr when unused),
-//   layout [3][max_hap_len + 2] V, index c
+//   layout [3][carry_pitch] V, index c
+// Steps G..steady_end run without the per-lane activity test: one basic block in which the
+// shuffles for the next step are issued last, so that their latency is covered by the M block of
+// the next step (which depends only on the previous step's registers).
 // Returns the running sum of M+X over the lane's bottom row (meaningful on the last lane).
 // ------------------------------------------------------------------------------------------
 template <class P, int G, int K, bool MULTI, int VAR>
-__device__ __forceinline__ typename P::V sweep(const LaneRows<P, K>& L, const uint8_t* hap, int haplen, int n_steps,
-                                               int t, typename P::S initY, bool pass0,
-                                               const typename P::V* carry_in, typename P::V* carry_out,
-                                               int carry_pitch) {
+struct Sweeper {
   typedef typename P::V V;
-  const V zero = P::splat(0);
-  V Ml[K], Yl[K], XYl[K];
-#pragma unroll
-  for (int j = 0; j < K; j++) {
-    Ml[j] = zero;
-    V y0 = zero;
-#pragma unroll
-    for (int x = 0; x < P::NR; x++)
-      if (L.padmask[x] & (1u << j)) P::set(y0, x, initY);
-    Yl[j] = y0;
-    XYl[j] = y0;
-  }
-  V botX = zero, sum = zero;
-  const bool first = (t == 0);
-  const bool row0_above = first && pass0;
-  const V initYv = P::splat(initY);
-  // bottom row of the lane above at the previous step's column; for the first lane that is
-  // column 0 of row 0 (M = 0, Y = init) or of the previous pass's bottom row
-  V dMp = zero, dXYp = row0_above ? initYv : zero;
-  if (MULTI) {
-    if (first && !pass0) {
-      dMp = carry_in[0];
-      dXYp = carry_in[2 * carry_pitch];
-    }
-    if (carry_out != nullptr && t == G - 1) {  // column 0 of this pass's bottom row
-      carry_out[0] = zero;
-      carry_out[carry_pitch] = zero;
-      carry_out[2 * carry_pitch] = XYl[K - 1];
-    }
-  }
-  int c = 1 - t;
-  uint32_t hb = hap[max(c, -kHapLeftMargin + 1)];
-#pragma unroll 2
-  for (int s = 1; s <= n_steps; s++, c++) {
-    // what the lane above computed one step ago (its column c)
-    V uM = P::shfl_up(Ml[K - 1], G);
-    V uX = P::shfl_up(botX, G);
-    V uXY = P::shfl_up(XYl[K - 1], G);
-    if (row0_above) uXY = initYv;  // row 0: M = X = 0 (killed by the zeroed top constants), Y = init
+  const LaneRows<P, K>& L;
+  V Ml[K], Yl[K], Zl[K];  // previous column: M, Y (VAR 2: Y / pMY), X+Y (VAR 2: pGAPM_next * (X+Y))
+  V botX, sum;
+  V uM, uX, uZ;           // bottom row of the lane above at this step's column
+  V dMp, dZp;             // ... and at the previous column
+  V inj;                  // what row 0 feeds the first row's M update
+  const uint8_t* hap;
+  int haplen, c;
+  uint32_t hb;
+  bool first, row0_above, last;
+  const V* carry_in;
+  V* carry_out;
+  int carry_pitch;
+
+  __device__ __forceinline__ Sweeper(const LaneRows<P, K>& L_) : L(L_) {}
+
+  __device__ __forceinline__ void fetch_up() {
+    uM = P::shfl_up(Ml[K - 1], G);
+    uX = P::shfl_up(botX, G);
+    uZ = P::shfl_up(Zl[K - 1], G);
+    if (row0_above) uZ = inj;  // row 0: M = X = 0 (killed by the zeroed top constants), Y = init
     if (MULTI) {
-      if (first && !pass0) {
+      if (first && carry_in != nullptr) {
         const int cc = min(max(c, 0), haplen + 1);
         uM = carry_in[cc];
         uX = carry_in[carry_pitch + cc];
-        uXY = carry_in[2 * carry_pitch + cc];
+        uZ = carry_in[2 * carry_pitch + cc];
       }
     }
+  }
+
+  __device__ __forceinline__ void cells(uint32_t hrep) {
+    uint32_t mw[P::NR][(K + 7) / 8];
+#pragma unroll
+    for (int x = 0; x < P::NR; x++)
+#pragma unroll
+      for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = L.rbm[x][w] & hrep;
+    V dM = dMp, dZ = dZp, upM = uM, upX = uX;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      uint32_t m2[P::NR];
+#pragma unroll
+      for (int x = 0; x < P::NR; x++) m2[x] = mw[x][j / 8];
+      const uint32_t bit = 0xFu << (4 * (j % 8));
+      V Mn, Yn, Zn;
+      const V Xn = P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
+      if (VAR == 0) {
+        const V A = P::sel(m2, bit, L.Am[j], L.Ax[j]);
+        const V Gs = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
+        Mn = P::fma(A, dM, P::mul(Gs, dZ));
+        Yn = P::fma(L.pXX[j], Yl[j], P::mul(L.pMY[j], Ml[j]));
+        Zn = P::add(Xn, Yn);
+      } else if (VAR == 1) {
+        const V prior = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
+        Mn = P::mul(prior, P::fma(L.Am[j], dM, P::mul(L.Ax[j], dZ)));
+        Yn = P::fma(L.pXX[j], Yl[j], P::mul(L.pMY[j], Ml[j]));
+        Zn = P::add(Xn, Yn);
+      } else {
+        const V prior = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
+        Mn = P::mul(prior, P::fma(L.Am[j], dM, dZ));       // dZ already carries this row's pGAPM
+        Yn = P::fma(L.pXX[j], Yl[j], Ml[j]);               // Y / pMY
+        Zn = P::fma(L.pMY[j], Yn, P::mul(L.Ax[j], Xn));    // pGAPM_next * (X + pMY * Y/pMY)
+      }
+      dM = Ml[j];
+      dZ = Zl[j];
+      Ml[j] = Mn;
+      Yl[j] = Yn;
+      Zl[j] = Zn;
+      upM = Mn;
+      upX = Xn;
+    }
+    botX = upX;
+    sum = P::add(sum, P::add(upM, upX));
+    if (MULTI) {
+      if (carry_out != nullptr && last) {
+        carry_out[c] = upM;
+        carry_out[carry_pitch + c] = upX;
+        carry_out[2 * carry_pitch + c] = Zl[K - 1];
+      }
+    }
+  }
+
+  template <bool GUARD>
+  __device__ __forceinline__ void step() {
     const uint32_t hrep = hb * 0x11111111u;
-    hb = hap[min(c + 1, haplen + 1)];  // prefetch next column's symbol
-    if ((unsigned)(c - 1) < (unsigned)haplen) {
-      uint32_t mw[P::NR][(K + 7) / 8];
+    hb = hap[min(c + 1, haplen + 1)];  // prefetch the next column's symbol
+    if (!GUARD || (unsigned)(c - 1) < (unsigned)haplen) cells(hrep);
+    dMp = uM;
+    dZp = uZ;
+    c++;
+    fetch_up();
+  }
+
+  __device__ __forceinline__ V run(const uint8_t* hap_, int haplen_, int steady_end, int n_steps, int t,
+                                   typename P::S initY, bool pass0, const V* carry_in_, V* carry_out_,
+                                   int carry_pitch_) {
+    const V zero = P::splat(0);
+    hap = hap_;
+    haplen = haplen_;
+    first = (t == 0);
+    last = (t == G - 1);
+    row0_above = first && pass0;
+    carry_in = (MULTI && !pass0) ? carry_in_ : nullptr;
+    carry_out = carry_out_;
+    carry_pitch = carry_pitch_;
+    const V initYv = P::splat(initY);
+    inj = (VAR == 2) ? P::mul(L.gTop, initYv) : initYv;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      Ml[j] = zero;
+      V y0 = zero;
 #pragma unroll
       for (int x = 0; x < P::NR; x++)
-#pragma unroll
-        for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = L.rbm[x][w] & hrep;
-      V dM = dMp, dXY = dXYp, upM = uM, upX = uX;
-#pragma unroll
-      for (int j = 0; j < K; j++) {
-        uint32_t m2[P::NR];
-#pragma unroll
-        for (int x = 0; x < P::NR; x++) m2[x] = mw[x][j / 8];
-        const uint32_t bit = 0xFu << (4 * (j % 8));
-        V Mn;
-        if (VAR == 0) {
-          const V A = P::sel(m2, bit, L.Am[j], L.Ax[j]);
-          const V Gs = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
-          Mn = P::fma(A, dM, P::mul(Gs, dXY));
-        } else {
-          const V prior = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
-          Mn = P::mul(prior, P::fma(L.Am[j], dM, P::mul(L.Ax[j], dXY)));
-        }
-        const V Xn = P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
-        const V Yn = P::fma(L.pXX[j], Yl[j], P::mul(L.pMY[j], Ml[j]));
-        dM = Ml[j];
-        dXY = XYl[j];
-        Ml[j] = Mn;
-        Yl[j] = Yn;
-        XYl[j] = P::add(Xn, Yn);
-        upM = Mn;
-        upX = Xn;
+        if (L.padmask[x] & (1u << j)) P::set(y0, x, initY);
+      Yl[j] = y0;
+      Zl[j] = (VAR == 2) ? P::mul(L.pMY[j], y0) : y0;
+    }
+    botX = zero;
+    sum = zero;
+    // column 0 of the row above the lane's first row: row 0 (M = 0, Y = init) for the first lane
+    // of pass 0, the previous pass's bottom row for the first lane of later passes
+    dMp = zero;
+    dZp = row0_above ? inj : zero;
+    c = 1 - t;
+    if (MULTI) {
+      if (first && carry_in != nullptr) {
+        dMp = carry_in[0];
+        dZp = carry_in[2 * carry_pitch];
       }
-      botX = upX;
-      sum = P::add(sum, P::add(upM, upX));
-      if (MULTI) {
-        if (carry_out != nullptr && t == G - 1) {
-          carry_out[c] = upM;
-          carry_out[carry_pitch + c] = upX;
-          carry_out[2 * carry_pitch + c] = XYl[K - 1];
-        }
+      if (carry_out != nullptr && last) {  // column 0 of this pass's bottom row
+        carry_out[0] = zero;
+        carry_out[carry_pitch] = zero;
+        carry_out[2 * carry_pitch] = Zl[K - 1];
       }
     }
-    dMp = uM;
-    dXYp = uXY;
+    hb = hap[max(c, -kHapLeftMargin + 1)];
+    fetch_up();
+    int s = 1;
+    const int pre_end = min(G - 1, n_steps);
+    for (; s <= pre_end; s++) step<true>();
+#pragma unroll 2
+    for (; s <= steady_end; s++) step<false>();
+    for (; s <= n_steps; s++) step<true>();
+    return sum;
   }
-  return sum;
+};
+
+template <class P, int G, int K, bool MULTI, int VAR>
+__device__ __forceinline__ typename P::V sweep(const LaneRows<P, K>& L, const uint8_t* hap, int haplen,
+                                               int steady_end, int n_steps, int t, typename P::S initY, bool pass0,
+                                               const typename P::V* carry_in, typename P::V* carry_out,
+                                               int carry_pitch) {
+  Sweeper<P, G, K, MULTI, VAR> sw(L);
+  return sw.run(hap, haplen, steady_end, n_steps, t, initY, pass0, carry_in, carry_out, carry_pitch);
 }
 
 // Result of one pair (IntelPairHmm.cc:157-167).  Returns false when the pair must be rerun in fp64.
@@ -477,7 +549,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams
     if (!MULTI) {
 #pragma unroll
       for (int x = 0; x < P::NR; x++)
-        load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, t * K, npad[x], t == 0,
+        load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K, npad[x], t == 0,
                              ph2pr_s, reinterpret_cast<const S*>(p.mm));
     }
     for (int h = h_begin; h < h_end; h++) {
@@ -485,19 +557,20 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams
       const uint8_t* hap = panel_s + hpos[h];
       const S initY = (S)p.init_const / (S)haplen;
       const int n_steps = haplen + G - 1;
+      const int steady_end = haplen;
       V sum = P::splat(0);
       if (!MULTI) {
-        sum = sweep<P, G, K, false, VAR>(L, hap, haplen, n_steps, t, initY, true, nullptr, nullptr, 0);
+        sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
       } else {
         V* cg = carry + (size_t)g * 6 * carry_pitch;  // two buffers of 3 lines, ping-pong
         for (int pass = 0; pass < p.cls.n_pass; pass++) {
 #pragma unroll
           for (int x = 0; x < P::NR; x++)
-            load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, pass * cap + t * K,
+            load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, pass * cap + t * K,
                                  npad[x], t == 0 && pass == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
           V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
           V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
-          sum = sweep<P, G, K, true, VAR>(L, hap, haplen, n_steps, t, initY, pass == 0, cin,
+          sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
                                      pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
           __syncwarp();  // carry written by lane G-1 is read by lane 0 of the next pass
         }
@@ -578,20 +651,23 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
     int n_steps = mine ? haplen + G - 1 : 0;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) n_steps = max(n_steps, __shfl_xor_sync(0xffffffffu, n_steps, o));
+    int steady_end = haplen;  // steps G..min(haplen) are unguarded; a warp with an idle group has none
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) steady_end = min(steady_end, __shfl_xor_sync(0xffffffffu, steady_end, o));
     const uint8_t* recp = p.cls.records + (size_t)rec * rec_bytes;
     LaneRows<P, K> L;
     V sum = P::splat(0);
     if (!MULTI) {
-      load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, t * K, npad, t == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
-      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, n_steps, t, initY, true, nullptr, nullptr, 0);
+      load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
+      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
     } else {
       V* cg = carry + (size_t)g * 6 * carry_pitch;
       for (int pass = 0; pass < p.cls.n_pass; pass++) {
-        load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, pass * cap + t * K, npad, t == 0 && pass == 0, ph2pr_s,
+        load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, pass * cap + t * K, npad, t == 0 && pass == 0, ph2pr_s,
                              reinterpret_cast<const S*>(p.mm));
         V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
         V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
-        sum = sweep<P, G, K, true, VAR>(L, hap, haplen, n_steps, t, initY, pass == 0, cin,
+        sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
                                    pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
         __syncwarp();
       }

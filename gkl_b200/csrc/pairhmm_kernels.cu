@@ -48,23 +48,23 @@ __global__ void k_pack_reads(const PackParams p) {
 #define E_D1(G, K, W, M, V) {POL_D1, G, K, W, M, V, 1, GKLB_TASKS(VD1, G, K, W, M, V), GKLB_LIST(VD1, G, K, W, M, V)}
 
 static const KernelEntry g_table[] = {
-    // ---- product: packed fp32, plain form (VAR 1) ----
-    E_F2(8, 4, 8, false, 1),  E_F2(8, 5, 8, false, 1),  E_F2(8, 6, 8, false, 1),  E_F2(8, 7, 8, false, 1),
-    E_F2(8, 8, 8, false, 1),  E_F2(16, 5, 8, false, 1), E_F2(16, 6, 8, false, 1), E_F2(16, 7, 8, false, 1),
-    E_F2(16, 8, 8, false, 1), E_F2(32, 5, 8, false, 1), E_F2(32, 6, 8, false, 1), E_F2(32, 7, 8, false, 1),
-    E_F2(32, 8, 8, false, 1), E_F2(32, 8, 8, true, 1),
+    // ---- product: packed fp32, folded form (VAR 2) ----
+    E_F2(8, 4, 8, false, 2),  E_F2(8, 5, 8, false, 2),  E_F2(8, 6, 8, false, 2),  E_F2(8, 7, 8, false, 2),
+    E_F2(8, 8, 8, false, 2),  E_F2(16, 5, 8, false, 2), E_F2(16, 6, 8, false, 2), E_F2(16, 7, 8, false, 2),
+    E_F2(16, 8, 8, false, 2), E_F2(32, 5, 8, false, 2), E_F2(32, 6, 8, false, 2), E_F2(32, 7, 8, false, 2),
+    E_F2(32, 8, 8, false, 2), E_F2(32, 8, 8, true, 2),
     // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
-    E_D1(8, 4, 8, false, 1),  E_D1(8, 5, 8, false, 1),  E_D1(8, 6, 8, false, 1),  E_D1(8, 7, 8, false, 1),
-    E_D1(8, 8, 8, false, 1),  E_D1(16, 5, 8, false, 1), E_D1(16, 6, 8, false, 1), E_D1(16, 7, 8, false, 1),
-    E_D1(16, 8, 8, false, 1), E_D1(32, 5, 8, false, 1), E_D1(32, 6, 8, false, 1), E_D1(32, 7, 8, false, 1),
-    E_D1(32, 8, 8, false, 1), E_D1(32, 8, 8, true, 1),
+    E_D1(8, 4, 8, false, 2),  E_D1(8, 5, 8, false, 2),  E_D1(8, 6, 8, false, 2),  E_D1(8, 7, 8, false, 2),
+    E_D1(8, 8, 8, false, 2),  E_D1(16, 5, 8, false, 2), E_D1(16, 6, 8, false, 2), E_D1(16, 7, 8, false, 2),
+    E_D1(16, 8, 8, false, 2), E_D1(32, 5, 8, false, 2), E_D1(32, 6, 8, false, 2), E_D1(32, 7, 8, false, 2),
+    E_D1(32, 8, 8, false, 2), E_D1(32, 8, 8, true, 2),
 #ifdef GKLB_EXPERIMENTAL
     // ---- measurement only ----
-    E_F2(16, 7, 8, false, 0), E_F2(16, 6, 12, false, 1), E_F2(16, 6, 12, false, 0), E_F2(16, 7, 12, false, 1),
-    E_F2(32, 4, 8, false, 1), E_F2(32, 4, 12, false, 1), E_F2(32, 4, 16, false, 1), E_F2(32, 4, 16, false, 0),
-    E_F2(16, 8, 8, false, 0), E_F2(16, 7, 10, false, 1),
-    E_F1(8, 13, 8, false, 1), E_F1(8, 13, 8, false, 0), E_F1(8, 13, 12, false, 1), E_F1(16, 7, 12, false, 1),
-    E_F1(16, 7, 16, false, 1), E_F1(16, 7, 16, false, 0), E_F1(32, 4, 16, false, 1),
+    E_F2(16, 7, 8, false, 0), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 12, false, 2), E_F2(16, 7, 10, false, 2),
+    E_F2(32, 4, 8, false, 2), E_F2(32, 4, 12, false, 2), E_F2(32, 4, 16, false, 2),
+    E_F1(8, 13, 8, false, 2), E_F1(8, 13, 8, false, 1), E_F1(8, 13, 12, false, 2), E_F1(16, 7, 12, false, 2),
+    E_F1(16, 7, 16, false, 2), E_F1(16, 7, 16, false, 1), E_F1(32, 4, 16, false, 2),
+    E_D1(8, 13, 8, false, 2), E_D1(32, 4, 8, false, 2),
 #endif
 };
 

@@ -1,0 +1,187 @@
+"""GPU: parity of the CUDA path (through the C-ABI) with the oracle.
+
+Tolerances: BASELINE.json asks for 1e-5 relative on the log10 likelihoods against GKL's AVX fp32
+PairHMM (with its fp64 rerun); GKL's own tests hold 1e-5 absolute against the golden file."""
+import numpy as np
+import pytest
+
+import oracle
+from gkl_b200 import (HaplotypeDataHolder, IntelPairHmm, PairHMMNativeArguments, ReadDataHolder, fixtures, native,
+                      synth)
+from gkl_b200.pairhmm import IllegalArgumentException, NullPointerException
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+def checker(b, use_double=False):
+    """GKL's own compiled code when oracle/_ref travelled with the repo, else the restatement."""
+    t = oracle.host_threads()
+    if oracle.ref_available():
+        return oracle.ref_pairhmm(b, use_double, threads=t)[0]
+    return oracle.port_pairhmm(b, use_double, threads=t)[0]
+
+
+def rel(a, ref):
+    return np.abs(a - ref) / np.maximum(np.abs(ref), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = native.Engine(0, False)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def eng_d():
+    e = native.Engine(0, True)
+    yield e
+    e.close()
+
+
+def test_golden_file_fp32_and_fp64(golden_pairhmm, eng, eng_d):
+    batches, expected = golden_pairhmm
+    got = np.array([eng.compute(b)[0] for b in batches])
+    assert np.abs(got - expected).max() <= 1e-5  # PairHmmUnitTest.dataFileTest
+    got_d = np.array([eng_d.compute(b)[0] for b in batches])
+    assert np.abs(got_d - expected).max() <= 1e-5
+    ref = np.array([checker(b)[0] for b in batches])
+    assert rel(got, ref).max() <= REL_TOL
+
+
+def test_simple_test_known_answer_through_operator_interface():
+    hmm = IntelPairHmm()
+    assert hmm.load()
+    hmm.initialize(PairHMMNativeArguments(False, 1))
+    q = b"++++"
+    out = np.zeros(1)
+    hmm.computeLikelihoods([ReadDataHolder(b"ACGT", q, q, q, q)], [HaplotypeDataHolder(b"ACGT")], out)
+    assert abs(out[0] - (-6.022797e-01)) <= 1e-5  # PairHmmUnitTest.simpleTest
+    with pytest.raises(NullPointerException):
+        hmm.computeLikelihoods(None, [HaplotypeDataHolder(b"ACGT")], out)
+    with pytest.raises(NullPointerException):
+        hmm.computeLikelihoods([ReadDataHolder(b"ACGT", q, q, q, q)], None, out)
+    with pytest.raises(NullPointerException):
+        hmm.computeLikelihoods([ReadDataHolder(b"ACGT", q, q, q, q)], [HaplotypeDataHolder(b"ACGT")], None)
+    with pytest.raises(IllegalArgumentException):
+        hmm.computeLikelihoods([ReadDataHolder(b"ACGT", q, q, q, q)], [HaplotypeDataHolder(b"")], out)
+    hmm.computeLikelihoods([], [HaplotypeDataHolder(b"ACGT")], out)  # empty input: no-op
+    hmm.done()
+    hmm.done()  # idempotent
+    hmm.initialize(None)  # re-initialise after done
+    hmm.computeLikelihoods([ReadDataHolder(b"ACGT", q, q, q, q)], [HaplotypeDataHolder(b"ACGT")], out)
+    assert abs(out[0] - (-6.022797e-01)) <= 1e-5
+    hmm.done()
+
+
+def test_config1(eng):
+    b = synth.config1()
+    assert rel(eng.compute(b), checker(b)).max() <= REL_TOL
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (31, {}),                                                  # ragged lengths, N and unknown bytes
+    (32, dict(low_quality=0.1, unrelated=0.3)),                # quals over 0..127, many fp64 reruns
+    (33, dict(read_len=(1, 12), hap_len=(1, 12))),             # tiny sequences
+    (34, dict(read_len=(250, 700), hap_len=(300, 900))),       # multi-pass reads
+])
+def test_random_batches_fp32_path_with_fallback(eng, seed, kw):
+    b = synth.random_batch(seed, 120, 30, **kw)
+    out = eng.compute(b)
+    ref = checker(b)
+    assert np.all(np.isfinite(out) == np.isfinite(ref))
+    ok = np.isfinite(ref)
+    assert rel(out[ok], ref[ok]).max() <= REL_TOL
+    if kw.get("unrelated"):
+        assert eng.stats().fallback_pairs > 0
+
+
+@pytest.mark.parametrize("seed,kw", [(41, dict(low_quality=0.1, unrelated=0.3)),
+                                     (42, dict(read_len=(250, 600), hap_len=(300, 700)))])
+def test_random_batches_double_precision_mode(eng_d, seed, kw):
+    b = synth.random_batch(seed, 60, 20, **kw)
+    out = eng_d.compute(b)
+    ref = checker(b, True)
+    assert rel(out, ref).max() <= 1e-9
+
+
+def test_every_length_class_boundary(eng):
+    # one read at each class capacity and one past it (32, 33, 40, 41, ... 256, 257, 512, 513)
+    rng = np.random.default_rng(7)
+    lens = sorted({c + d for c in (32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 512) for d in (0, 1)} | {1, 2})
+    hap = synth.ACGT[rng.integers(0, 4, size=300)]
+    reads = [hap[:min(L, 300)] if L <= 300 else np.concatenate([hap, synth.ACGT[rng.integers(0, 4, size=L - 300)]])
+             for L in lens]
+    mk = lambda v: [bytes([v]) * len(r) for r in reads]
+    b = fixtures.PairHmmBatch.from_lists([bytes(r) for r in reads], mk(30), mk(40), mk(40), mk(10),
+                                         [bytes(hap), bytes(hap[:150]), bytes(hap[40:])])
+    out = eng.compute(b)
+    ref = checker(b)
+    assert rel(out, ref).max() <= REL_TOL
+
+
+def test_haplotype_panel_larger_than_shared_memory_is_tiled(eng):
+    b = synth.random_batch(51, 24, 800, read_len=(60, 120), hap_len=(250, 450))
+    assert rel(eng.compute(b), checker(b)).max() <= REL_TOL
+
+
+def test_config3_regions(eng):
+    for reg in synth.config3(4, seed=3):
+        out = eng.compute(reg)
+        assert rel(out, checker(reg)).max() <= REL_TOL
+
+
+def test_config2_full_size_properties(eng):
+    """Full BASELINE size (10 000 x 128): compared with the checker on a read sample, plus
+    size-independent properties on the whole output."""
+    b = synth.config2()
+    out = eng.compute(b).reshape(b.n_reads, b.n_haps)
+    assert np.all(np.isfinite(out)) and out.max() < 0
+    idx = np.arange(0, b.n_reads, 25)
+    for r in idx[:200]:
+        pass
+    sample = np.concatenate([checker(b.read_slice(int(r), int(r) + 1)) for r in idx[:120]])
+    assert rel(out[idx[:120]].ravel(), sample).max() <= REL_TOL
+    # rows are independent of batch composition: recomputing a slice gives identical bits
+    again = eng.compute(b.read_slice(1000, 1200)).reshape(200, b.n_haps)
+    assert np.array_equal(again, out[1000:1200])
+    # permuting haplotypes permutes columns
+    perm = np.random.default_rng(0).permutation(b.n_haps)
+    haps = [bytes(b.hap_bases[b.hap_off[h]:b.hap_off[h + 1]]) for h in perm]
+    off = np.zeros(b.n_haps + 1, dtype=np.int64)
+    np.cumsum([len(h) for h in haps], out=off[1:])
+    sl = b.read_slice(0, 300)
+    pb = fixtures.PairHmmBatch(sl.read_off, sl.read_bases, sl.read_quals, sl.ins_gop, sl.del_gop, sl.gcp, off,
+                               np.frombuffer(b"".join(haps), dtype=np.uint8).copy())
+    assert np.array_equal(eng.compute(pb).reshape(300, b.n_haps), out[:300][:, perm])
+
+
+def test_staged_run_fetch_equals_compute(eng):
+    b = synth.config2(300, 64)
+    a = eng.compute(b)
+    eng.stage(b)
+    eng.run()
+    eng.run()  # re-running a staged batch is allowed
+    assert np.array_equal(eng.fetch(b.n_reads * b.n_haps), a)
+
+
+def test_device_resident_inputs(eng):
+    import torch
+    b = synth.config2(200, 32)
+    dev = [torch.from_numpy(x).cuda() for x in (b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp)]
+    hap = torch.from_numpy(b.hap_bases).cuda()
+    eng.stage(b, arenas=dev, hap=hap, device=True)
+    eng.run()
+    assert np.array_equal(eng.fetch(b.n_reads * b.n_haps), eng.compute(b))
+
+
+def test_invalid_batches_are_rejected(eng):
+    b = synth.config2(4, 4)
+    bad = fixtures.PairHmmBatch(b.read_off.copy(), b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp,
+                                b.hap_off.copy(), b.hap_bases)
+    bad.read_off[2] = bad.read_off[1]  # empty read
+    with pytest.raises(native.GklbError) as ei:
+        eng.compute(bad)
+    assert ei.value.code == native.ERR_INVALID
+    assert rel(eng.compute(b), checker(b)).max() <= REL_TOL  # the engine stays usable

@@ -1,0 +1,82 @@
+"""CPU: host-side logic -- batch layout, fixtures, synthetic configurations, C-ABI surface."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle
+from gkl_b200 import fixtures, native, synth
+from gkl_b200.batch import PairHmmBatch
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+def test_batch_from_lists_and_slices():
+    b = PairHmmBatch.from_lists([b"ACGT", b"AC"], [b"\x1e" * 4, b"\x1e" * 2], [b"\x28" * 4, b"\x28" * 2],
+                                [b"\x28" * 4, b"\x28" * 2], [b"\x0a" * 4, b"\x0a" * 2], [b"ACGTT", b"ACG", b"A"])
+    b.validate()
+    assert (b.n_reads, b.n_haps) == (2, 3)
+    assert b.cells() == (4 + 2) * (5 + 3 + 1)
+    s = b.read_slice(1, 2)
+    s.validate()
+    assert s.n_reads == 1 and bytes(s.read_bases) == b"AC" and s.n_haps == 3
+    with pytest.raises(ValueError):
+        PairHmmBatch.from_lists([b"ACGT"], [b"\x1e" * 3], [b"\x28" * 4], [b"\x28" * 4], [b"\x0a" * 4], [b"A"])
+
+
+def test_golden_file_decoding_matches_gkl_test_harness(golden_pairhmm):
+    # PairHmmUnitTest.java:206-212: quals - 33, read quals clamped to >= 6
+    batches, expected = golden_pairhmm
+    assert len(batches) == len(expected) == 104
+    for b in batches:
+        assert b.read_quals.min() >= 6
+        assert b.ins_gop.max() < 94
+    assert -15 < expected.min() < expected.max() < -1
+
+
+def test_synthetic_configs_are_deterministic_and_shaped():
+    c1 = synth.config1()
+    assert (c1.n_reads, c1.n_haps, int(c1.read_lens[0]), int(c1.hap_lens[0])) == (1, 1, 50, 100)
+    a, b = synth.config2(50, 16), synth.config2(50, 16)
+    assert np.array_equal(a.read_bases, b.read_bases) and np.array_equal(a.hap_bases, b.hap_bases)
+    assert set(a.read_lens) == {101} and a.hap_lens.min() >= 200 and a.hap_lens.max() <= 400
+    regs = synth.config3(2)
+    assert all(35 <= r.read_lens.min() and r.read_lens.max() <= 250 for r in regs)
+
+
+def test_library_exports_every_symbol_of_the_header():
+    header = (ROOT / "include" / "gklb_pairhmm.h").read_text()
+    declared = set(re.findall(r"GKLB_API\s+[\w\s\*]+?\b(gklb_\w+)\s*\(", header))
+    assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
+    lib = native.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert b"sm_100a" in lib.gklb_version()
+
+
+def test_host_tables_are_bit_identical_to_the_oracle():
+    # Context.h:65-89,133-189 evaluated by two independent restatements
+    ours, ref = native.tables(), oracle.port_tables()
+    for k in ours:
+        assert np.array_equal(ours[k], ref[k][:len(ours[k])]), k
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(native.GklbError) as ei:
+        native.Engine(0)
+    assert ei.value.code == native.ERR_NO_DEVICE
+    rc = native.lib().gklb_pairhmm_compute(None, None)
+    assert rc == native.ERR_STATE  # not initialised; never computes on the host
+
+
+def test_product_package_does_not_touch_the_oracle():
+    for p in (ROOT / "gkl_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".cc", ".h") and p.is_file():
+            text = p.read_text()
+            assert "import oracle" not in text and "from oracle" not in text, p
+            assert "libgklb_oracle" not in text and "libgkl_ref" not in text, p
