@@ -128,6 +128,8 @@ struct gklb_engine {
   int num_sms = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> kev;  // pairs of events around each forward-sweep task kernel of the last run
+  int kev_used = 0;
   std::mutex mu;
   // device tables
   DevBuf d_tables;
@@ -492,7 +494,19 @@ int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEn
   }
   if (smem > (size_t)kSmemMax) return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu)", smem);
   if (grid <= 0) return GKLB_OK;
+  if (!list_mode) {
+    while ((int)e->kev.size() < e->kev_used + 2) {
+      cudaEvent_t ev;
+      CU(cudaEventCreate(&ev));
+      e->kev.push_back(ev);
+    }
+    CU(cudaEventRecord(e->kev[e->kev_used], e->stream));
+  }
   CU(launch_sweep(list_mode ? k->fn_list : k->fn_tasks, p, grid, k->warps * 32, smem, e->stream));
+  if (!list_mode) {
+    CU(cudaEventRecord(e->kev[e->kev_used + 1], e->stream));
+    e->kev_used += 2;
+  }
   e->stats.kernel_launches++;
   return GKLB_OK;
 }
@@ -501,6 +515,7 @@ int do_run(gklb_engine* e) {
   if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
   CU(cudaSetDevice(e->device));
   e->stats.kernel_launches = 0;
+  e->kev_used = 0;
   e->stats.n_classes = (int)e->classes.size();
   if (e->classes.empty()) return GKLB_OK;
   CU(cudaMemsetAsync(e->d_counters.p, 0, sizeof(unsigned int) * (size_t)e->n_counters, e->stream));
@@ -588,6 +603,7 @@ void destroy_engine(gklb_engine* e) {
   e->h_counters.release();
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& ev : e->kev) cudaEventDestroy(ev);
   if (e->own_stream) cudaStreamDestroy(e->own_stream);
   delete e;
 }
@@ -681,6 +697,16 @@ int gklb_engine_synchronize(gklb_engine* e) {
 
 int gklb_engine_stats(gklb_engine* e, gklb_pairhmm_stats* out) {
   if (!e || !out) return fail(GKLB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  e->stats.sweep_ms = 0;
+  e->stats.sweep_launches = e->kev_used / 2;
+  for (int i = 0; i + 1 < e->kev_used; i += 2) {
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e->kev[i], e->kev[i + 1]));
+    e->stats.sweep_ms += ms;
+  }
   *out = e->stats;
   return GKLB_OK;
 }

@@ -36,7 +36,8 @@ class _Batch(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("pairs", C.c_int64), ("cells", C.c_int64), ("fallback_pairs", C.c_int64),
                 ("kernel_launches", C.c_int32), ("n_classes", C.c_int32),
-                ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float)]
+                ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
+                ("sweep_ms", C.c_float), ("sweep_launches", C.c_int32)]
 
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_engine_create",

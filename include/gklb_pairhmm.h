@@ -82,6 +82,9 @@ typedef struct gklb_pairhmm_stats {
   float h2d_ms;             /* cudaEvent-timed phases of the last gklb_pairhmm_compute; 0 if not timed */
   float kernel_ms;
   float d2h_ms;
+  float sweep_ms;           /* device time of the forward-sweep task kernels alone in the last run (the
+                               dominant kernel; excludes packing and the fp64 rerun of flagged pairs) */
+  int32_t sweep_launches;   /* how many launches sweep_ms covers */
 } gklb_pairhmm_stats;
 
 typedef struct gklb_engine gklb_engine;
