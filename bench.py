@@ -184,15 +184,16 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the engine has no CPU path")
     torch.cuda.set_device(local)
     distributed = world > 1
-    if distributed:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if distributed:
+        dist.init_process_group("nccl", device_id=dev)
 
     b = workload(rank, args.reads, args.haps)
     cells = b.cells()
     pairs = b.n_reads * b.n_haps
     eng = native.Engine(local, False)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream(device=dev)  # one stream for the engine's kernels, the collectives and the events
+    torch.cuda.set_stream(stream)
     eng.set_stream(stream.cuda_stream)
 
     # ---- resident path: inputs staged in HBM, K steps timed with CUDA events ----
