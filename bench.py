@@ -201,15 +201,18 @@ def run_ours(args):
     arenas_dev = [torch.from_numpy(x).to(dev) for x in (b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp)]
     eng.stage(b, arenas=arenas_dev, hap=hap_dev, device=True)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gathered = [torch.empty(pairs, dtype=torch.float64, device=dev) for _ in range(world)] if (distributed and rank == 0) else None
+
+    from gkl_b200 import multi
 
     def step():
         if distributed:
-            dist.broadcast(hap_dev, src=0)  # the haplotype panel travels from GPU 0 over NVLink
+            # the haplotype panel travels from GPU 0 over NVLink and is consumed by this step's sweep
+            _, panel = multi.broadcast_panel(b.hap_off if rank == 0 else None, hap_dev if rank == 0 else None, 0, dev)
+            eng.update_haps_device(panel)
         eng.run()
         if distributed:
             res = torch.as_tensor(_DevArray(eng.result_device_ptr(), pairs), device=dev)
-            dist.gather(res, gathered, dst=0)  # likelihood slabs back to GPU 0
+            multi.gather_slabs(res, [pairs] * world, 0)  # likelihood slabs back to GPU 0
 
     for _ in range(args.warmup):
         step()

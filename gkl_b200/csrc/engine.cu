@@ -140,7 +140,7 @@ struct gklb_engine {
   int n_reads = 0, n_haps = 0;
   std::vector<ClassInst> classes;
   std::vector<Tile> tiles;
-  DevBuf d_read_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
+  DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
   HostBuf h_meta, h_counters;
   size_t arena_pitch = 0;
   int n_counters = 0;
@@ -397,6 +397,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
   CU(e->d_meta.ensure(meta_bytes));
   CU(e->d_records.ensure(rec_bytes));
   CU(e->d_read_off.ensure(sizeof(int64_t) * ((size_t)b->n_reads + 1)));
+  CU(e->d_hap_off.ensure(sizeof(int64_t) * ((size_t)b->n_haps + 1)));
   e->arena_pitch = align_up((size_t)total_read, 256);
   CU(e->d_arenas.ensure(e->arena_pitch * 5));
   CU(e->d_out.ensure(sizeof(double) * (size_t)e->stats.pairs));
@@ -414,6 +415,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
   cudaStream_t s = e->stream;
   CU(cudaMemcpyAsync(e->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, s));
   CU(cudaMemcpyAsync(e->d_read_off.p, b->read_off, sizeof(int64_t) * ((size_t)b->n_reads + 1), cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->d_hap_off.p, b->hap_off, sizeof(int64_t) * ((size_t)b->n_haps + 1), cudaMemcpyHostToDevice, s));
   uint8_t* da = static_cast<uint8_t*>(e->d_arenas.p);
   const uint8_t* src[5] = {b->read_bases, b->read_quals, b->ins_gop, b->del_gop, b->gcp};
   for (int i = 0; i < 5; i++)
@@ -596,7 +598,7 @@ void destroy_engine(gklb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
-  for (DevBuf* b : {&e->d_tables, &e->d_read_off, &e->d_arenas, &e->d_meta, &e->d_records, &e->d_out, &e->d_fb,
+  for (DevBuf* b : {&e->d_tables, &e->d_hap_off, &e->d_read_off, &e->d_arenas, &e->d_meta, &e->d_records, &e->d_out, &e->d_fb,
                     &e->d_counters, &e->d_carry})
     b->release();
   e->h_meta.release();
@@ -667,6 +669,18 @@ int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
   std::lock_guard<std::mutex> lk(e->mu);
   return do_stage(e, batch, true);
+}
+
+int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_bases_dev) {
+  if (!e || !hap_bases_dev) return fail(GKLB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
+  CU(cudaSetDevice(e->device));
+  uint8_t* dm = static_cast<uint8_t*>(e->d_meta.p);
+  for (auto& t : e->tiles)
+    CU(launch_fill_panel(dm + t.meta_off, t.n, t.hap0, static_cast<const int64_t*>(e->d_hap_off.p),
+                         static_cast<const uint8_t*>(hap_bases_dev), e->stream));
+  return GKLB_OK;
 }
 
 int gklb_engine_run(gklb_engine* e) {

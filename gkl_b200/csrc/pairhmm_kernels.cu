@@ -41,6 +41,25 @@ __global__ void k_pack_reads(const PackParams p) {
   }
 }
 
+// One block per haplotype of a tile: rewrite the nibbles of a panel image from device-resident bases
+// (the lengths, and therefore the image layout, are those of the staged batch).
+__global__ void k_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases) {
+  const int i = blockIdx.x;
+  if (i >= n_haps) return;
+  const int32_t* hpos = reinterpret_cast<const int32_t*>(image);
+  const int32_t* hlen = hpos + n_haps;
+  const int64_t o = hap_off[hap0 + i];
+  uint8_t* dst = image + hpos[i] + 1;
+  for (int c = threadIdx.x; c < hlen[i]; c += blockDim.x) dst[c] = base_nibble(bases[o + c]);
+}
+
+cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,
+                              cudaStream_t s) {
+  if (n_haps <= 0) return cudaSuccess;
+  k_fill_panel<<<n_haps, 128, 0, s>>>(image, n_haps, hap0, hap_off, bases);
+  return cudaGetLastError();
+}
+
 #define GKLB_TASKS(P, G, K, W, M, V) reinterpret_cast<const void*>(&k_sweep_tasks<P, G, K, W, M, V>)
 #define GKLB_LIST(P, G, K, W, M, V) reinterpret_cast<const void*>(&k_sweep_list<P, G, K, W, M, V>)
 #define E_F2(G, K, W, M, V) {POL_F2, G, K, W, M, V, 2, GKLB_TASKS(VF2, G, K, W, M, V), nullptr}

@@ -23,5 +23,7 @@ const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, i
 
 cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s);
 cudaError_t launch_pack(const PackParams& p, cudaStream_t s);
+cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,
+                              cudaStream_t s);
 
 }  // namespace gklb

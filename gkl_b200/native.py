@@ -42,7 +42,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_engine_create",
            "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_stage",
-           "gklb_engine_stage_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
+           "gklb_engine_stage_device", "gklb_engine_update_haps_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
            "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
            "gklb_version", "gklb_device_count", "gklb_pairhmm_table"]
 
@@ -76,6 +76,7 @@ def lib() -> C.CDLL:
         l.gklb_engine_stage.argtypes = [C.c_void_p, C.POINTER(_Batch)]
         l.gklb_engine_stage_device.argtypes = [C.c_void_p, C.POINTER(_Batch)]
         l.gklb_engine_fetch.argtypes = [C.c_void_p, C.c_void_p]
+        l.gklb_engine_update_haps_device.argtypes = [C.c_void_p, C.c_void_p]
         l.gklb_engine_result_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         l.gklb_engine_stats.argtypes = [C.c_void_p, C.POINTER(Stats)]
         l.gklb_engine_time_runs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
@@ -163,6 +164,10 @@ class Engine:
         self._keep = (b, arenas, hap)
         fn = lib().gklb_engine_stage_device if device else lib().gklb_engine_stage
         _check(fn(self._h, C.byref(s)))
+
+    def update_haps_device(self, hap_dev) -> None:
+        """New haplotype bases (same lengths) from a device buffer, e.g. the target of an NCCL broadcast."""
+        _check(lib().gklb_engine_update_haps_device(self._h, _ptr(hap_dev)))
 
     def run(self) -> None:
         _check(lib().gklb_engine_run(self._h))

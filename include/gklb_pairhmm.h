@@ -127,6 +127,10 @@ GKLB_API int gklb_engine_compute(gklb_engine* e, const gklb_pairhmm_batch* batch
  * run may be called repeatedly on one staged batch. */
 GKLB_API int gklb_engine_stage(gklb_engine* e, const gklb_pairhmm_batch* batch);
 GKLB_API int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch);
+/* Replace the haplotype bases of the staged batch by device-resident ones of the same lengths (e.g. the
+ * buffer an NCCL broadcast just filled): the panel images are rewritten by a kernel on the engine's stream,
+ * no host round trip.  [async] */
+GKLB_API int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_bases_dev);
 GKLB_API int gklb_engine_run(gklb_engine* e);
 GKLB_API int gklb_engine_fetch(gklb_engine* e, double* likelihoods);
 GKLB_API int gklb_engine_result_device(gklb_engine* e, void** dev_ptr);

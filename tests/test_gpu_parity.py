@@ -174,6 +174,20 @@ def test_device_resident_inputs(eng):
     assert np.array_equal(eng.fetch(b.n_reads * b.n_haps), eng.compute(b))
 
 
+def test_update_haps_device_rewrites_the_panel(eng):
+    import torch
+    a = synth.config2(100, 24, seed=5)
+    rng = np.random.default_rng(9)
+    other = a.hap_bases.copy()
+    flip = rng.random(len(other)) < 0.05
+    other[flip] = synth.ACGT[rng.integers(0, 4, size=int(flip.sum()))]
+    b = fixtures.PairHmmBatch(a.read_off, a.read_bases, a.read_quals, a.ins_gop, a.del_gop, a.gcp, a.hap_off, other)
+    eng.stage(a)
+    eng.update_haps_device(torch.from_numpy(other).cuda())
+    eng.run()
+    assert np.array_equal(eng.fetch(a.n_reads * a.n_haps), eng.compute(b))
+
+
 def test_invalid_batches_are_rejected(eng):
     b = synth.config2(4, 4)
     bad = fixtures.PairHmmBatch(b.read_off.copy(), b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp,

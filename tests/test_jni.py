@@ -1,0 +1,83 @@
+"""The JNI face of libgkl_pairhmm.so, driven by a fake JVM (no JDK in this image).
+CPU: symbols, failover without a GPU, exception classes.  GPU: results through the JNI path."""
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from gkl_b200 import native, synth
+from tests import jni_fake
+
+LIB = native.LIB_PATH
+
+
+def has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_exports_exactly_the_symbols_intelpairhmm_binds():
+    # IntelPairHmm.java:157-164 declares initNative, computeLikelihoodsNative, doneNative
+    out = subprocess.run(["nm", "-D", "--defined-only", str(LIB)], capture_output=True, text=True, check=True).stdout
+    syms = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    for s in ("Java_com_intel_gkl_pairhmm_IntelPairHmm_initNative",
+              "Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihoodsNative",
+              "Java_com_intel_gkl_pairhmm_IntelPairHmm_doneNative", "JNI_OnLoad"):
+        assert s in syms
+    assert not [s for s in syms if s.startswith("Java_") and "IntelPairHmm" not in s]
+
+
+def test_library_refuses_to_load_into_a_jvm_without_a_gpu():
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    assert jni_fake.onload(LIB) == -1  # JNI_ERR -> UnsatisfiedLinkError -> IntelPairHmm.load() == false
+
+
+def test_missing_field_is_illegal_argument_exception():
+    b = synth.config2(3, 2)
+    rc, _, cls, msg, leaks = jni_fake.pairhmm(LIB, b, fault=1)
+    assert rc == 1 and cls == "java/lang/IllegalArgumentException" and msg == "Unable to get field ID"  # JavaData.h:127-133
+    assert leaks == (0, 0)
+
+
+def test_compute_before_init_and_no_device_raise_java_exceptions():
+    b = synth.config2(3, 2)
+    rc, _, cls, _, leaks = jni_fake.pairhmm(LIB, b, fault=5)
+    assert rc == 1 and cls == "java/lang/IllegalStateException" and leaks == (0, 0)
+    if not has_gpu():
+        rc, _, cls, msg, leaks = jni_fake.pairhmm(LIB, b)
+        assert rc == 1 and cls == "java/lang/RuntimeException" and "CUDA" in msg and leaks == (0, 0)
+
+
+@pytest.mark.gpu
+def test_onload_accepts_with_a_gpu():
+    assert jni_fake.onload(LIB) == 0x00010006
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_double", [False, True])
+def test_results_through_the_jni_path(use_double):
+    b = synth.random_batch(61, 40, 12, low_quality=0.05, unrelated=0.2)
+    rc, out, cls, msg, leaks = jni_fake.pairhmm(LIB, b, use_double)
+    assert rc == 0, (cls, msg)
+    assert leaks == (0, 0)  # every local reference deleted, the output array released (copy-back mode 0)
+    ref = (oracle.ref_pairhmm if oracle.ref_available() else oracle.port_pairhmm)(b, use_double)[0]
+    assert (np.abs(out - ref) / np.abs(ref)).max() <= 1e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fault,cls", [(2, "java/lang/NullPointerException"), (3, "java/lang/OutOfMemoryError"),
+                                       (4, "java/lang/IllegalArgumentException"), (6, "java/lang/IllegalArgumentException")])
+def test_fault_injection_maps_to_gkl_exception_classes(fault, cls):
+    b = synth.config2(5, 3)
+    rc, _, got, _, leaks = jni_fake.pairhmm(LIB, b, fault=fault)
+    assert rc == 1 and got == cls and leaks == (0, 0)
+
+
+@pytest.mark.gpu
+def test_done_is_idempotent_and_reinitialise_works():
+    b = synth.config2(6, 4)
+    rc, out, cls, msg, leaks = jni_fake.pairhmm(LIB, b, fault=7)
+    assert rc == 0 and leaks == (0, 0), (cls, msg)
+    assert (np.abs(out - oracle.port_pairhmm(b)[0]) / np.abs(out)).max() <= 1e-5
