@@ -181,12 +181,7 @@ int gklport_pairhmm(int n_reads, int n_haps, const int64_t* read_off, const uint
     int l = (int)(hap_off[h + 1] - hap_off[h]);
     if (l > max_hap) max_hap = l;
   }
-  int threads = 1;
-#ifdef _OPENMP
-  threads = n_threads < omp_get_max_threads() ? n_threads : omp_get_max_threads();
-  if (threads < 1) threads = 1;
-#endif
-  (void)n_threads;
+  const int threads = n_threads < 1 ? 1 : n_threads; /* honoured even under OMP_NUM_THREADS=1 (torchrun) */
   const long n = (long)n_reads * (long)n_haps;
   double t0 = now_s();
 #ifdef _OPENMP

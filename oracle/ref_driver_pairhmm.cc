@@ -76,11 +76,10 @@ int gklref_pairhmm(int n_reads, int n_haps, const int64_t* read_off, const uint8
     }
   }
 
-  int max_threads = 1;
-#ifdef _OPENMP
-  max_threads = n_threads < omp_get_max_threads() ? n_threads : omp_get_max_threads();
-  if (max_threads < 1) max_threads = 1;
-#endif
+  // GKL clamps the request to omp_get_max_threads() (IntelPairHmm.cc:72-74).  The caller here passes the
+  // number of host cores it wants used; the num_threads clause below honours it even when a launcher
+  // (torchrun) exported OMP_NUM_THREADS=1 for this process.
+  int max_threads = n_threads < 1 ? 1 : n_threads;
   const bool g_use_double = use_double != 0;
   const long n = (long)testcases.size();
 
