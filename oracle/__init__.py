@@ -126,6 +126,37 @@ def ref_avx512_supported() -> bool:
     return bool(_load_ref().gklref_avx512_supported())
 
 
+_i8p = np.ctypeslib.ndpointer(dtype=np.int8, flags="C_CONTIGUOUS")
+_PD_ARGS = [_i8p] * 7 + [_f64p, C.c_int64, _i64p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+
+
+def _pd_call(fn, b, mode: int, threads: int):
+    out = np.empty(b.n, dtype=np.float64)
+    secs = C.c_double(0)
+    rc = fn(b.hap_bases, b.hap_pdbases, b.read_bases, b.read_qual, b.read_ins_qual, b.read_del_qual, b.gcp, out, b.n,
+            b.hap_lengths, b.read_lengths, int(b.max_read), int(b.max_hap), int(mode), int(threads), C.byref(secs))
+    return out, rc, secs.value
+
+
+def port_pdhmm(batch, carry_state: bool = True, threads: int = 1):
+    """CPU restatement of the PDHMM (gkl_b200.pdhmm_batch.PdhmmBatch in).  carry_state=True is the serial
+    reference path (and GATK's Java); False resets the column state per row like the AVX paths.
+    Returns (log10 likelihoods[n], status, seconds)."""
+    lib = _load_port()
+    lib.gklport_pdhmm.restype = C.c_int
+    lib.gklport_pdhmm.argtypes = _PD_ARGS
+    return _pd_call(lib.gklport_pdhmm, batch, 1 if carry_state else 0, threads)
+
+
+def ref_pdhmm(batch, level: int = 0, threads: int = 1):
+    """GKL's own compiled PDHMM.  level: 0 fastest available, 1 scalar, 2 AVX2, 3 AVX-512.
+    Returns (log10 likelihoods[n], reference status code, seconds)."""
+    lib = _load_ref()
+    lib.gklref_pdhmm.restype = C.c_int
+    lib.gklref_pdhmm.argtypes = _PD_ARGS
+    return _pd_call(lib.gklref_pdhmm, batch, level, threads)
+
+
 def port_tables():
     """Host tables of the restatement (for bit-exact comparison with the engine's tables)."""
     lib = _load_port()
