@@ -41,6 +41,21 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
+}  // namespace
+
+// shared with pdhmm_engine.cu
+int gklb_internal_fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  t_last_error = buf;
+  return code;
+}
+
+namespace {
+
 #define CU(call)                                                                                        \
   do {                                                                                                  \
     cudaError_t e_ = (call);                                                                            \

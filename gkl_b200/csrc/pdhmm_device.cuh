@@ -1,0 +1,257 @@
+// pdhmm_device.cuh -- sm_100a device code of the partially-determined-haplotype PairHMM (PDHMM, config 5).
+//
+// Reference semantics (/root/reference/src/main/native/pdhmm): the scalar path pdhmm-serial.cc:279-411 --
+// M/I/D plus the three "branch" matrices, a NORMAL / INSIDE_DEL / AFTER_DEL state per haplotype column driven by
+// the PD flag bytes (DEL_START=2, DEL_END=4), SNP alleles (SNP=1, A=8, C=16, G=32, T=64) widening the match test,
+// fp64 throughout, INITIAL_CONDITION = 2^1020, result log10(sum_j M[R][j] + I[R][j]) - log10(2^1020).
+// `currentState` is declared outside the row loop there (pdhmm-serial.cc:306), so the state after the last column
+// of a row is the state the next row starts in; that is reproduced (carry_state = 1).  carry_state = 0 resets
+// it per row like the reference's AVX paths (pdhmm.h:507-511,736-737).
+//
+// Mapping: the same systolic sweep as the PairHMM kernels -- a group of G lanes owns G*K read rows (K per lane,
+// padded at the TOP with rows that reproduce row 0: M = I = 0, D = init), lane t processes column s - t at step
+// s, the bottom row of lane t-1 arrives by warp shuffle (six doubles: M, I, D and their branch twins), reads
+// longer than G*K rows take several passes with the bottom row carried through a global scratch line.
+// The column state does not depend on the data, only on the PD bytes and on the state the row started in, so it
+// is precomputed per pair: one byte per column holds the state for each of the three possible row-start states
+// plus the DEL_END flag, and each row's start state follows from the 3-entry end-state map.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gklb {
+
+constexpr int kPdMargin = 40;  // zero columns on both sides of a haplotype in shared memory
+
+struct PdhmmParams {
+  // flat layout (IntelPDHMM.computePDHMM): pair k at k * max_hap / k * max_read; or cross layout
+  // (IntelPDHMM.computeLikelihoods): pair k = r * n_haps + h with reads/haps stored once
+  const int8_t* hap_bases;
+  const int8_t* hap_pdbases;
+  const int8_t* read_bases;
+  const int8_t* read_qual;
+  const int8_t* read_ins_qual;
+  const int8_t* read_del_qual;
+  const int8_t* gcp;
+  const int64_t* hap_lengths;   // [n] flat, [n_haps] cross
+  const int64_t* read_lengths;  // [n] flat, [n_reads] cross
+  long long n;                  // pairs
+  int n_haps;                   // cross layout: haplotypes per read; 0 = flat layout
+  int max_hap, max_read;
+  const double* q2err;          // [255]   10^(-q/10)
+  const double* mm;             // [32640] matchToMatchProb
+  double init_cond;             // 2^1020
+  double log10_init;
+  double* out;                  // [n]
+  unsigned int* counter;        // work counter
+  unsigned int* error_flag;     // set when a negative insertion/deletion/gcp quality is met
+  double* carry;                // per warp: GPW * 2 * 6 * (max_hap + 2) doubles
+  size_t carry_stride;          // doubles per warp
+  int carry_state;
+};
+
+__device__ __forceinline__ double shfl_up_d(double v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
+
+// Smem per group: y[c], info[c], allele[c] for c in [-kPdMargin, max_hap + kPdMargin)
+template <int G, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
+  constexpr int GPW = 32 / G;
+  constexpr int CAP = G * K;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane % G, g = lane / G;
+  const int col_pitch = p.max_hap + 2 * kPdMargin;
+  uint8_t* gs = smem + (size_t)(warp * GPW + g) * 3 * col_pitch;
+  uint8_t* ys = gs + kPdMargin;                  // haplotype byte of column c at ys[c] (c = 1..H)
+  uint8_t* infos = gs + col_pitch + kPdMargin;   // state bits + DEL_END
+  uint8_t* alleles = gs + 2 * col_pitch + kPdMargin;
+  const int carry_pitch = p.max_hap + 2;
+  double* carry_g = p.carry + ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride + (size_t)g * 12 * carry_pitch;
+  const unsigned long long n_warp_items = ((unsigned long long)p.n + GPW - 1) / GPW;
+
+  for (;;) {
+    unsigned int wi = 0;
+    if (lane == 0) wi = atomicAdd(p.counter, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= n_warp_items) break;
+    const long long item = (long long)wi * GPW + g;
+    const bool mine = item < p.n;
+    long long hi = 0, ri = 0;
+    if (mine) {
+      if (p.n_haps > 0) { ri = item / p.n_haps; hi = item - ri * p.n_haps; }
+      else { ri = item; hi = item; }
+    }
+    const int H = mine ? (int)p.hap_lengths[hi] : 0;
+    const int R = mine ? (int)p.read_lengths[ri] : 0;
+    const int8_t* hap = p.hap_bases + hi * p.max_hap;
+    const int8_t* pd = p.hap_pdbases + hi * p.max_hap;
+    const int64_t ro = ri * (int64_t)p.max_read;
+
+    // ---- per-pair column tables in shared memory ----
+    __syncwarp();
+    for (int c = t - kPdMargin; c < p.max_hap + kPdMargin; c += G) {
+      uint8_t y = 0, al = 0;
+      if (c >= 1 && c <= H) {
+        y = (uint8_t)hap[c - 1];
+        const uint8_t f = (uint8_t)pd[c - 1];
+        al = (f & 1) ? (f & 0x78) : 0;
+      }
+      ys[c] = y;
+      alleles[c] = al;
+      infos[c] = 0;
+    }
+    __syncwarp();
+    int end_state = 0;  // packed 2-bit end states for the three start states
+    if (t == 0) {
+      int s0 = 0, s1 = 1, s2 = 2;  // state entering column c when the row started NORMAL / INSIDE / AFTER
+      for (int c = 1; c <= H; c++) {
+        const uint8_t f = (uint8_t)pd[c - 1];
+        infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0));
+        // pdhmm-serial.cc:370-385
+        if (s0 == 2) s0 = 0;
+        if (s1 == 2) s1 = 0;
+        if (s2 == 2) s2 = 0;
+        if (f & 2) s0 = s1 = s2 = 1;
+        if (f & 4) s0 = s1 = s2 = 2;
+      }
+      end_state = s0 | (s1 << 2) | (s2 << 4);
+    }
+    end_state = __shfl_sync(0xffffffffu, end_state, g * G);
+    __syncwarp();
+
+    const int n_pass = max(1, (R + CAP - 1) / CAP);
+    int n_pass_w = n_pass;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) n_pass_w = max(n_pass_w, __shfl_xor_sync(0xffffffffu, n_pass_w, o));
+    const int n_pad = n_pass * CAP - R;
+    const double init = p.init_cond / (double)max(H, 1);
+    int n_steps = mine ? H + G - 1 : 0;
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) n_steps = max(n_steps, __shfl_xor_sync(0xffffffffu, n_steps, o));
+    double sum = 0.0;
+
+    for (int pass = 0; pass < n_pass_w; pass++) {
+      const bool live = mine && pass < n_pass;
+      // ---- per-row constants ----
+      double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];
+      uint32_t xb[K], xbit[K], shift[K];  // read byte, its allele bit, 2 * row-start state
+      bool padrow[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int row = pass * CAP + t * K + j - n_pad;  // 0-based read row; < 0: top padding
+        padrow[j] = !(live && row >= 0);
+        tMM[j] = tIM[j] = tMI[j] = tMD[j] = 0.0;
+        tII[j] = 1.0;
+        pMa[j] = pMi[j] = 0.0;
+        xb[j] = 0x100;  // matches nothing
+        xbit[j] = 0;
+        shift[j] = 0;
+        if (!padrow[j]) {
+          const int8_t iq = p.read_ins_qual[ro + row], dq = p.read_del_qual[ro + row], gq = p.gcp[ro + row];
+          if (iq < 0 || dq < 0 || gq < 0) atomicOr(p.error_flag, 1u);  // pdhmm-serial.cc:184-198
+          const int qi = iq & 0xFF, qd = dq & 0xFF, qg = gq & 0xFF, qq = p.read_qual[ro + row] & 0xFF;
+          const int mn = min(qi, qd), mx = max(qi, qd);
+          // MAX_QUAL (254) < maxQual only for 255: 1 - 10^(approximate log10 sum) -- evaluated directly
+          tMM[j] = (mx > 254) ? 1.0 - (pow(10.0, -0.1 * mn) + pow(10.0, -0.1 * mx))
+                              : __ldg(p.mm + ((mx * (mx + 1)) >> 1) + mn);
+          tMI[j] = __ldg(p.q2err + min(qi, 254));
+          tMD[j] = __ldg(p.q2err + min(qd, 254));
+          const double eg = __ldg(p.q2err + min(qg, 254));
+          tIM[j] = 1.0 - eg;
+          tII[j] = eg;
+          const double eq = __ldg(p.q2err + min(qq, 254));
+          pMa[j] = 1.0 - eq;
+          pMi[j] = eq / 3.0;
+          const uint32_t x = (uint8_t)p.read_bases[ro + row];
+          xb[j] = x;
+          const uint32_t u = x & 0xDF;  // upper case
+          xbit[j] = (u == 'A') ? 8u : (u == 'C') ? 16u : (u == 'G') ? 32u : (u == 'T') ? 64u : 0u;
+          // state the row starts in: NORMAL for the first row, then the end state of the previous row
+          int st = 0;
+          if (p.carry_state)
+            for (int r = 0; r < row; r++) st = (end_state >> (2 * st)) & 3;
+          shift[j] = 2u * (uint32_t)st;
+        }
+      }
+      // ---- state of the previous column ----
+      double M[K], I[K], D[K], bM[K], bI[K], bD[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        M[j] = I[j] = bM[j] = bI[j] = bD[j] = 0.0;
+        D[j] = (padrow[j] && live) ? init : 0.0;
+      }
+      const bool first = (t == 0);
+      const bool from_carry = first && pass > 0;
+      const double* cin = carry_g + (size_t)(pass & 1) * 6 * carry_pitch;
+      double* cout = carry_g + (size_t)((pass + 1) & 1) * 6 * carry_pitch;
+      const bool write_carry = live && (t == G - 1) && (pass + 1 < n_pass);
+      // diagonal inputs of the lane's first row at its first column: column 0 of the row above
+      double gM = 0, gI = 0, gD = (first && pass == 0) ? init : 0.0, gbM = 0, gbI = 0, gbD = 0;
+      if (from_carry && live) {
+        gM = cin[0]; gI = cin[carry_pitch]; gD = cin[2 * carry_pitch];
+        gbM = cin[3 * carry_pitch]; gbI = cin[4 * carry_pitch]; gbD = cin[5 * carry_pitch];
+      }
+      if (write_carry) {
+#pragma unroll
+        for (int q = 0; q < 6; q++) cout[q * carry_pitch] = 0.0;
+        cout[2 * carry_pitch] = D[K - 1];  // column 0 of a padding bottom row is init, of a real row 0
+      }
+      int c = 1 - t;
+      for (int s = 1; s <= n_steps; s++, c++) {
+        // bottom row of the lane above at column c (it computed it one step ago)
+        double uM = shfl_up_d(M[K - 1], G), uI = shfl_up_d(I[K - 1], G), uD = shfl_up_d(D[K - 1], G);
+        double ubM = shfl_up_d(bM[K - 1], G), ubI = shfl_up_d(bI[K - 1], G), ubD = shfl_up_d(bD[K - 1], G);
+        if (first) {
+          if (pass == 0) { uM = uI = ubM = ubI = ubD = 0.0; uD = init; }  // row 0: D = init, everything else 0
+          else if (live) {
+            const int cc = min(max(c, 0), H + 1);
+            uM = cin[cc]; uI = cin[carry_pitch + cc]; uD = cin[2 * carry_pitch + cc];
+            ubM = cin[3 * carry_pitch + cc]; ubI = cin[4 * carry_pitch + cc]; ubD = cin[5 * carry_pitch + cc];
+          }
+        }
+        if (live && (unsigned)(c - 1) < (unsigned)H) {
+          const uint32_t y = ys[c], info = infos[c], al = alleles[c];
+          const bool del_end = (info & 0x40) != 0;
+          double tM = uM, tI = uI, tD = uD, tbM = ubM, tbI = ubI, tbD = ubD;          // top of row j
+          double dM = gM, dI = gI, dD = gD, dbM = gbM, dbI = gbI, dbD = gbD;          // diagonal of row j
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            const uint32_t st = (info >> shift[j]) & 3u;
+            double lM = M[j], lI = I[j], lD = D[j];
+            const double lbM = bM[j], lbI = bI[j], lbD = bD[j];
+            double nbM, nbI, nbD;
+            if (st == 0) { nbM = lM; nbD = lD; nbI = lI; }
+            else if (st == 1) { nbM = lbM; nbD = lbD; nbI = lbI; }
+            else {
+              nbM = fmax(lbM, lM); nbD = fmax(lbD, lD); nbI = fmax(lbI, lI);
+              dM = fmax(dM, dbM); dI = fmax(dI, dbI); dD = fmax(dD, dbD);
+              lM = fmax(lM, lbM); lD = fmax(lD, lbD);
+            }
+            const bool match = (xb[j] == y) || (xb[j] == 'N') || (y == 'N') || ((xbit[j] & al) != 0);
+            const double prior = match ? pMa[j] : pMi[j];
+            const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+            const double nD = lM * tMD[j] + lD * tII[j];  // deletionToDeletion == insertionToInsertion
+            const double nI = del_end ? fmax(tbM, tM) * tMI[j] + fmax(tbI, tI) * tII[j] : tM * tMI[j] + tI * tII[j];
+            // the next row's diagonal is this row's previous column, its top this row's new column
+            dM = M[j]; dI = I[j]; dD = D[j]; dbM = lbM; dbI = lbI; dbD = lbD;
+            M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
+            tM = nM; tI = nI; tD = nD; tbM = nbM; tbI = nbI; tbD = nbD;
+          }
+          (void)tD; (void)tbD;
+          if (pass == n_pass - 1) sum += M[K - 1] + I[K - 1];
+          if (write_carry) {
+            cout[c] = M[K - 1]; cout[carry_pitch + c] = I[K - 1]; cout[2 * carry_pitch + c] = D[K - 1];
+            cout[3 * carry_pitch + c] = bM[K - 1]; cout[4 * carry_pitch + c] = bI[K - 1];
+            cout[5 * carry_pitch + c] = bD[K - 1];
+          }
+        }
+        gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
+      }
+      __syncwarp();
+    }
+    if (mine && t == G - 1) p.out[item] = log10(sum) - p.log10_init;
+  }
+}
+
+}  // namespace gklb

@@ -1,0 +1,312 @@
+// pdhmm_engine.cu -- host side and C-ABI (include/gklb_pdhmm.h) of the PDHMM engine.
+// Replaces pdhmm/IntelPDHMM.cc + pdhmm-implementation.h:292-396 below the JNI boundary.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+#include <vector>
+
+#include "../../include/gklb_pdhmm.h"
+#include "pdhmm_device.cuh"
+
+using namespace gklb;
+
+extern int gklb_internal_fail(int code, const char* fmt, ...);  // engine.cu: sets gklb_last_error()
+
+namespace {
+
+#define CU(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return gklb_internal_fail(e_ == cudaErrorMemoryAllocation ? GKLB_ERR_OOM : GKLB_ERR_CUDA, "%s failed: %s", \
+                                #call, cudaGetErrorString(e_));                                           \
+  } while (0)
+
+constexpr int kG = 32, kK = 4, kWarps = 8;
+constexpr int kMaxQual = 254;
+constexpr int kMmSizePd = ((kMaxQual + 1) * (kMaxQual + 2)) >> 1;
+constexpr int kSmemMax = 232448;
+
+struct PdTables {
+  double q2err[kMaxQual + 1];
+  double mm[kMmSizePd];
+  double init_cond, log10_init;
+};
+
+// ProbabilityCache::initialize + JacobianLogTable (pdhmm-common.h:149-195, MathUtils.cc:31-109), host libm
+const PdTables& pd_tables() {
+  static const PdTables* t = [] {
+    PdTables* p = new PdTables;
+    std::vector<double> jac(80001);
+    for (int k = 0; k < 80001; k++) jac[k] = log10(1.0 + pow(10.0, -k * 0.0001));
+    const double inv_ln10 = 1.0 / log(10);
+    for (int i = 0, off = 0; i <= kMaxQual; off += ++i)
+      for (int j = 0; j <= i; j++) {
+        double a = -0.1 * i, b = -0.1 * j;
+        if (a > b) std::swap(a, b);
+        const double diff = b - a;
+        double ls = b;
+        if (diff < 8.0) {
+          const double v = diff * (1.0 / 0.0001);
+          ls = b + jac[(v > 0.0) ? (int)(v + 0.5) : (int)(v - 0.5)];
+        }
+        p->mm[off + j] = pow(10, log1p(-std::min(1.0, pow(10, ls))) * inv_ln10);
+      }
+    for (int i = 0; i <= kMaxQual; i++) p->q2err[i] = pow(10.0, ((double)i) / -10.0);
+    p->init_cond = pow(2, 1020);
+    p->log10_init = log10(p->init_cond);
+    return p;
+  }();
+  return *t;
+}
+
+struct Buf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, n + n / 4 + 256);
+    if (e == cudaSuccess) cap = n + n / 4 + 256;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct PdEngine {
+  int device = 0, num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  Buf tables, hap, pd, rd[5], hl, rl, out, misc, carry;
+  int carry_state = 1;
+  PdhmmParams last{};
+  bool have_last = false;
+  size_t last_smem = 0;
+  int last_grid = 0;
+  gklb_pdhmm_stats stats{};
+};
+
+std::mutex g_mu;
+PdEngine* g_pd = nullptr;
+
+void destroy(PdEngine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  if (e->stream) cudaStreamSynchronize(e->stream);
+  for (Buf* b : {&e->tables, &e->hap, &e->pd, &e->rd[0], &e->rd[1], &e->rd[2], &e->rd[3], &e->rd[4], &e->hl, &e->rl,
+                 &e->out, &e->misc, &e->carry})
+    b->release();
+  for (auto& ev : e->ev)
+    if (ev) cudaEventDestroy(ev);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int launch(PdEngine* e) {
+  CU(cudaMemsetAsync(e->misc.p, 0, 8, e->stream));
+  void* args[] = {&e->last};
+  CU(cudaLaunchKernel(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps>), dim3(e->last_grid), dim3(kWarps * 32), args,
+                      e->last_smem, e->stream));
+  e->stats.kernel_launches++;
+  return GKLB_OK;
+}
+
+// n_reads/n_haps > 0: cross layout; else flat with b->n pairs.
+int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, double* out) {
+  if (!b || !out) return gklb_internal_fail(GKLB_ERR_INVALID, "null argument");
+  const bool cross = n_haps > 0;
+  const long long n = cross ? (long long)n_reads * n_haps : (long long)b->n;
+  const long long n_hap_rows = cross ? n_haps : n, n_read_rows = cross ? n_reads : n;
+  if (n <= 0) return gklb_internal_fail(GKLB_ERR_INVALID, "batchSize must be greater than 0");
+  if (b->max_hap <= 0 || b->max_read <= 0)
+    return gklb_internal_fail(GKLB_ERR_INVALID, "maxHapLength / maxReadLength must be greater than 0");
+  if (!b->hap_bases || !b->hap_pdbases || !b->read_bases || !b->read_qual || !b->read_ins_qual || !b->read_del_qual ||
+      !b->gcp || !b->hap_lengths || !b->read_lengths)
+    return gklb_internal_fail(GKLB_ERR_INVALID, "null array in batch");
+  long long cells = 0, sum_h = 0, sum_r = 0;
+  for (long long k = 0; k < n_hap_rows; k++) {
+    if (b->hap_lengths[k] <= 0 || b->hap_lengths[k] > b->max_hap)
+      return gklb_internal_fail(GKLB_ERR_INVALID, "haplotype %lld has length %lld outside 1..%d", k,
+                                (long long)b->hap_lengths[k], b->max_hap);
+    sum_h += b->hap_lengths[k];
+  }
+  for (long long k = 0; k < n_read_rows; k++) {
+    if (b->read_lengths[k] <= 0 || b->read_lengths[k] > b->max_read)
+      return gklb_internal_fail(GKLB_ERR_INVALID, "read %lld has length %lld outside 1..%d", k,
+                                (long long)b->read_lengths[k], b->max_read);
+    sum_r += b->read_lengths[k];
+  }
+  if (cross) cells = sum_h * sum_r;
+  else for (long long k = 0; k < n; k++) cells += b->hap_lengths[k] * b->read_lengths[k];
+
+  constexpr int gpw = 32 / kG;
+  const size_t col_pitch = (size_t)b->max_hap + 2 * kPdMargin;
+  const size_t smem = (size_t)kWarps * gpw * 3 * col_pitch;
+  if (smem > (size_t)kSmemMax)
+    return gklb_internal_fail(GKLB_ERR_INVALID, "maxHapLength %d does not fit in shared memory", b->max_hap);
+
+  CU(cudaSetDevice(e->device));
+  cudaStream_t s = e->stream;
+  CU(cudaEventRecord(e->ev[0], s));
+  const size_t hb = (size_t)n_hap_rows * b->max_hap, rb = (size_t)n_read_rows * b->max_read;
+  CU(e->hap.ensure(hb));
+  CU(e->pd.ensure(hb));
+  for (auto& r : e->rd) CU(r.ensure(rb));
+  CU(e->hl.ensure(sizeof(int64_t) * n_hap_rows));
+  CU(e->rl.ensure(sizeof(int64_t) * n_read_rows));
+  CU(e->out.ensure(sizeof(double) * n));
+  CU(e->misc.ensure(64));
+  const size_t carry_stride = (size_t)gpw * 12 * ((size_t)b->max_hap + 2);
+  CU(e->carry.ensure(sizeof(double) * carry_stride * kWarps * e->num_sms));
+  CU(cudaMemcpyAsync(e->hap.p, b->hap_bases, hb, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->pd.p, b->hap_pdbases, hb, cudaMemcpyHostToDevice, s));
+  const int8_t* src[5] = {b->read_bases, b->read_qual, b->read_ins_qual, b->read_del_qual, b->gcp};
+  for (int i = 0; i < 5; i++) CU(cudaMemcpyAsync(e->rd[i].p, src[i], rb, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->hl.p, b->hap_lengths, sizeof(int64_t) * n_hap_rows, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(e->rl.p, b->read_lengths, sizeof(int64_t) * n_read_rows, cudaMemcpyHostToDevice, s));
+
+  const PdTables& t = pd_tables();
+  PdhmmParams& p = e->last;
+  p.hap_bases = static_cast<const int8_t*>(e->hap.p);
+  p.hap_pdbases = static_cast<const int8_t*>(e->pd.p);
+  p.read_bases = static_cast<const int8_t*>(e->rd[0].p);
+  p.read_qual = static_cast<const int8_t*>(e->rd[1].p);
+  p.read_ins_qual = static_cast<const int8_t*>(e->rd[2].p);
+  p.read_del_qual = static_cast<const int8_t*>(e->rd[3].p);
+  p.gcp = static_cast<const int8_t*>(e->rd[4].p);
+  p.hap_lengths = static_cast<const int64_t*>(e->hl.p);
+  p.read_lengths = static_cast<const int64_t*>(e->rl.p);
+  p.n = n;
+  p.n_haps = cross ? n_haps : 0;
+  p.max_hap = b->max_hap;
+  p.max_read = b->max_read;
+  p.q2err = static_cast<const double*>(e->tables.p);
+  p.mm = p.q2err + (kMaxQual + 1);
+  p.init_cond = t.init_cond;
+  p.log10_init = t.log10_init;
+  p.out = static_cast<double*>(e->out.p);
+  p.counter = static_cast<unsigned int*>(e->misc.p);
+  p.error_flag = p.counter + 1;
+  p.carry = static_cast<double*>(e->carry.p);
+  p.carry_stride = carry_stride;
+  p.carry_state = e->carry_state;
+  e->last_smem = smem;
+  const long long warp_items = (n + gpw - 1) / gpw;
+  e->last_grid = (int)std::min<long long>(e->num_sms, (warp_items + kWarps - 1) / kWarps);
+  e->have_last = true;
+  e->stats = gklb_pdhmm_stats{};
+  e->stats.pairs = n;
+  e->stats.cells = cells;
+
+  CU(cudaEventRecord(e->ev[1], s));
+  int rc = launch(e);
+  if (rc) return rc;
+  CU(cudaEventRecord(e->ev[2], s));
+  unsigned int flags[2] = {0, 0};
+  CU(cudaMemcpyAsync(out, e->out.p, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(flags, e->misc.p, sizeof(flags), cudaMemcpyDeviceToHost, s));
+  CU(cudaEventRecord(e->ev[3], s));
+  CU(cudaStreamSynchronize(s));
+  cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]);
+  cudaEventElapsedTime(&e->stats.kernel_ms, e->ev[1], e->ev[2]);
+  cudaEventElapsedTime(&e->stats.d2h_ms, e->ev[2], e->ev[3]);
+  if (flags[1])  // pdhmm-serial.cc:184-198 -> PDHMM_INPUT_DATA_ERROR -> IllegalArgumentException
+    return gklb_internal_fail(GKLB_ERR_INVALID, "insertion, deletion or gcp quality is negative");
+  return GKLB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_memory_mb) {
+  (void)openmp_setting; (void)max_threads; (void)avx_level; (void)max_memory_mb;
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_pd) { destroy(g_pd); g_pd = nullptr; }
+  int n = 0;
+  cudaError_t ce = cudaGetDeviceCount(&n);
+  if (ce != cudaSuccess || n <= 0) return gklb_internal_fail(GKLB_ERR_NO_DEVICE, "no CUDA device (%s)", cudaGetErrorString(ce));
+  const char* dev = getenv("GKLB_DEVICE");
+  const int device = dev ? atoi(dev) : 0;
+  if (device < 0 || device >= n) return gklb_internal_fail(GKLB_ERR_NO_DEVICE, "device %d out of range", device);
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return gklb_internal_fail(GKLB_ERR_NO_DEVICE, "device %d is sm_%d%d; sm_100a code only", device, prop.major, prop.minor);
+  CU(cudaSetDevice(device));
+  PdEngine* e = new PdEngine;
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  const char* rs = getenv("GKLB_PDHMM_ROW_STATE");
+  e->carry_state = (rs && !strcmp(rs, "reset")) ? 0 : 1;
+  CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  for (auto& ev : e->ev) CU(cudaEventCreate(&ev));
+  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps>),
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  const PdTables& t = pd_tables();
+  CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
+  CU(cudaMemcpy(e->tables.p, t.q2err, sizeof(t.q2err), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(static_cast<double*>(e->tables.p) + (kMaxQual + 1), t.mm, sizeof(t.mm), cudaMemcpyHostToDevice));
+  g_pd = e;
+  return GKLB_OK;
+}
+
+int gklb_pdhmm_compute(const gklb_pdhmm_batch* batch, double* likelihoods) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_pd) return gklb_internal_fail(GKLB_ERR_STATE, "gklb_pdhmm_init has not been called");
+  return compute(g_pd, batch, 0, 0, likelihoods);
+}
+
+int gklb_pdhmm_compute_cross(const gklb_pdhmm_batch* operands, int32_t n_reads, int32_t n_haps, double* likelihoods) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_pd) return gklb_internal_fail(GKLB_ERR_STATE, "gklb_pdhmm_init has not been called");
+  if (n_reads <= 0 || n_haps <= 0) return gklb_internal_fail(GKLB_ERR_INVALID, "empty read or haplotype array");
+  return compute(g_pd, operands, n_reads, n_haps, likelihoods);
+}
+
+int gklb_pdhmm_done(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_pd) { destroy(g_pd); g_pd = nullptr; }
+  return GKLB_OK;
+}
+
+int gklb_pdhmm_last_stats(gklb_pdhmm_stats* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_pd || !out) return gklb_internal_fail(GKLB_ERR_STATE, "no engine");
+  *out = g_pd->stats;
+  return GKLB_OK;
+}
+
+int gklb_pdhmm_time_runs(int iters, float* ms_per_run) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!g_pd || !g_pd->have_last || iters <= 0 || !ms_per_run) return gklb_internal_fail(GKLB_ERR_STATE, "nothing to time");
+  PdEngine* e = g_pd;
+  CU(cudaSetDevice(e->device));
+  CU(cudaEventRecord(e->ev[0], e->stream));
+  for (int i = 0; i < iters; i++) {
+    int rc = launch(e);
+    if (rc) return rc;
+  }
+  CU(cudaEventRecord(e->ev[1], e->stream));
+  CU(cudaEventSynchronize(e->ev[1]));
+  float ms = 0;
+  CU(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  *ms_per_run = ms / iters;
+  return GKLB_OK;
+}
+
+const void* gklb_pdhmm_table(int which, int* n) {
+  const PdTables& t = pd_tables();
+  if (which == 0) { if (n) *n = kMaxQual + 1; return t.q2err; }
+  if (which == 1) { if (n) *n = kMmSizePd; return t.mm; }
+  if (n) *n = 0;
+  return nullptr;
+}
+
+}  // extern "C"
