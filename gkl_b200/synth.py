@@ -130,6 +130,35 @@ def config4(n_reads: int = 1_000_000, n_haps: int = 256, read_len: int = 150, se
     return _assemble(haps, reads)
 
 
+def config5(n_reads: int = 10_000, n_haps: int = 128, read_len: int = 101, seed: int = 5):
+    """C5: the PDHMM variant of C2 -- same shapes, plus one PD flag byte per haplotype base drawn from the
+    frequencies of the reference's real-data fixture: 97.2 % plain, 1.8 % SNP|G (33), 0.3 % SNP|A (9),
+    and DEL_START (2) ... DEL_END (4) spans opened at 0.4 % of the positions (1-8 bases; a 1-base span carries both
+    flags).  Returns (reads, haps) for gkl_b200.pdhmm_batch.PdhmmBatch.cross / IntelPDHMM.computeLikelihoods:
+    reads = [(bases, qual, ins, del, gcp)], haps = [(bases, pd)], all int8."""
+    b = config2(n_reads, n_haps, read_len, seed=seed)
+    rng = np.random.default_rng(seed + 1000)
+    haps = []
+    for h in range(b.n_haps):
+        bases = b.hap_bases[b.hap_off[h]:b.hap_off[h + 1]]
+        L = len(bases)
+        pd = np.zeros(L, dtype=np.int8)
+        u = rng.random(L)
+        pd[u < 0.018] = 33
+        pd[(u >= 0.018) & (u < 0.021)] = 9
+        for pos in np.flatnonzero(rng.random(L) < 0.004):
+            span = int(rng.integers(1, 9))
+            end = min(L - 1, pos + span - 1)
+            pd[pos] |= 2
+            pd[end] |= 4
+        haps.append((bases.view(np.int8).copy(), pd))
+    reads = []
+    for r in range(b.n_reads):
+        a, e = int(b.read_off[r]), int(b.read_off[r + 1])
+        reads.append(tuple(x[a:e].view(np.int8).copy() for x in (b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp)))
+    return reads, haps
+
+
 def random_batch(seed: int, n_reads: int, n_haps: int, read_len=(10, 250), hap_len=(10, 450),
                  low_quality: float = 0.0, n_frac: float = 0.02, unrelated: float = 0.0) -> PairHmmBatch:
     """Adversarial parity batch: ragged lengths, N and non-ACGT bytes on both sides, a share of
