@@ -29,6 +29,9 @@
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+#if defined(__SSE__)
+#include <xmmintrin.h>
+#endif
 
 #define MAX_QUAL 254
 #define MM_SIZE (((MAX_QUAL + 1) * (MAX_QUAL + 2)) >> 1)
@@ -163,6 +166,12 @@ int gklport_pdhmm(const int8_t* hap_bases, const int8_t* hap_pdbases, const int8
 #pragma omp parallel num_threads(threads)
 #endif
   {
+#if defined(__SSE__)
+    /* The PDHMM never turns flush-to-zero on (only GKL's PairHMM init does, IntelPairHmm.cc:93-96) and its
+     * lowest likelihoods live in the fp64 denormal range: make sure a PairHMM run earlier in this process did
+     * not leave FTZ set on this (pooled) thread. */
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_OFF);
+#endif
     double* work = (double*)malloc(sizeof(double) * 6 * (size_t)(max_hap + 1));
 #ifdef _OPENMP
 #pragma omp for schedule(dynamic, 16)

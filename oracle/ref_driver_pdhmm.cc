@@ -33,6 +33,14 @@ int gklref_pdhmm(const int8_t* hap_bases, const int8_t* hap_pdbases, const int8_
   } catch (JavaException& e) {
     return -1;
   }
+  // GKL's PDHMM never enables flush-to-zero, but its PairHMM init leaves it on for the thread that called it
+  // (IntelPairHmm.cc:93-96) and the OpenMP pool threads keep whatever a previous PairHMM run set.  The PDHMM's
+  // lowest likelihoods are fp64 denormals, so start from the JVM's default (FTZ off) on every pool thread.
+  _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_OFF);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads > 1 ? threads : 1)
+  { _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_OFF); }
+#endif
   const double t0 = now_s();
   const int rc = computePDHMM(hap_bases, hap_pdbases, read_bases, read_qual, read_ins_qual, read_del_qual, gcp, result, n,
                               hap_lengths, read_lengths, max_read, max_hap);
