@@ -57,8 +57,9 @@ typedef JavaVM_ JavaVM;
 enum {
   kJniFindClass = 6, kJniThrowNew = 14, kJniExceptionClear = 17, kJniPushLocalFrame = 19, kJniPopLocalFrame = 20,
   kJniDeleteLocalRef = 23, kJniGetFieldID = 94, kJniGetObjectField = 95, kJniGetArrayLength = 171,
-  kJniGetObjectArrayElement = 173, kJniGetByteArrayElements = 184, kJniGetDoubleArrayElements = 190,
+  kJniGetObjectArrayElement = 173, kJniNewDoubleArray = 182, kJniGetByteArrayElements = 184, kJniGetDoubleArrayElements = 190,
   kJniReleaseByteArrayElements = 192, kJniReleaseDoubleArrayElements = 198, kJniGetByteArrayRegion = 200,
+  kJniSetDoubleArrayRegion = 214, kJniGetPrimitiveArrayCritical = 222, kJniReleasePrimitiveArrayCritical = 223,
   kJniExceptionCheck = 228
 };
 
@@ -91,6 +92,16 @@ struct JNIEnv_ {
   }
   void ReleaseDoubleArrayElements(jdoubleArray a, jdouble* p, jint mode) {
     slot<void (*)(JNIEnv_*, jdoubleArray, jdouble*, jint)>(kJniReleaseDoubleArrayElements)(this, a, p, mode);
+  }
+  jdoubleArray NewDoubleArray(jsize n) { return slot<jdoubleArray (*)(JNIEnv_*, jsize)>(kJniNewDoubleArray)(this, n); }
+  void SetDoubleArrayRegion(jdoubleArray a, jsize start, jsize len, const jdouble* buf) {
+    slot<void (*)(JNIEnv_*, jdoubleArray, jsize, jsize, const jdouble*)>(kJniSetDoubleArrayRegion)(this, a, start, len, buf);
+  }
+  void* GetPrimitiveArrayCritical(jarray a, jboolean* is_copy) {
+    return slot<void* (*)(JNIEnv_*, jarray, jboolean*)>(kJniGetPrimitiveArrayCritical)(this, a, is_copy);
+  }
+  void ReleasePrimitiveArrayCritical(jarray a, void* p, jint mode) {
+    slot<void (*)(JNIEnv_*, jarray, void*, jint)>(kJniReleasePrimitiveArrayCritical)(this, a, p, mode);
   }
   void GetByteArrayRegion(jbyteArray a, jsize start, jsize len, jbyte* buf) {
     slot<void (*)(JNIEnv_*, jbyteArray, jsize, jsize, jbyte*)>(kJniGetByteArrayRegion)(this, a, start, len, buf);

@@ -37,3 +37,19 @@ def pairhmm(lib_path, b, use_double=False, fault=0):
                            p(b.ins_gop), p(b.del_gop), p(b.gcp), p(b.hap_off), p(b.hap_bases), int(use_double),
                            int(fault), p(out), ec, em, leaks)
     return rc, out[:b.n_reads * b.n_haps], ec.value.decode(), em.value.decode(), (leaks[0], leaks[1])
+
+
+def pdhmm(lib_path, b, object_api=False, n_reads=0, n_haps=0, fault=0):
+    """b: gkl_b200.pdhmm_batch.PdhmmBatch -- the flat batch (object_api False) or strided operands
+    (object_api True: n_reads reads, n_haps haplotypes).  Returns (rc, out, exception class, message, leaks)."""
+    l = _lib()
+    n = n_reads * n_haps if object_api else b.n
+    out = np.zeros(max(1, n), dtype=np.float64)
+    ec, em = C.create_string_buffer(256), C.create_string_buffer(256)
+    leaks = (C.c_long * 2)()
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = l.fakejvm_pdhmm(str(lib_path).encode(), int(object_api), C.c_longlong(b.n), n_reads, n_haps, int(b.max_hap),
+                         int(b.max_read), p(b.hap_bases), p(b.hap_pdbases), p(b.read_bases), p(b.read_qual),
+                         p(b.read_ins_qual), p(b.read_del_qual), p(b.gcp), p(b.hap_lengths), p(b.read_lengths), int(fault),
+                         p(out), ec, em, leaks)
+    return rc, out[:n], ec.value.decode(), em.value.decode(), (leaks[0], leaks[1])

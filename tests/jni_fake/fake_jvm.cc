@@ -14,11 +14,12 @@
 
 namespace {
 
-enum Kind { K_PLAIN, K_CLASS, K_BYTES, K_DOUBLES, K_HOLDER, K_OBJARR };
+enum Kind { K_PLAIN, K_CLASS, K_BYTES, K_DOUBLES, K_HOLDER, K_OBJARR, K_LONGS };
 struct Obj : _jobject { Kind kind = K_PLAIN; };
 struct ClassObj : Obj { ClassObj() { kind = K_CLASS; } std::string name; std::vector<std::string> fields; };
 struct ByteArr : Obj { ByteArr() { kind = K_BYTES; } std::vector<int8_t> data; };
 struct DblArr : Obj { DblArr() { kind = K_DOUBLES; } std::vector<double> data; };
+struct LongArr : Obj { LongArr() { kind = K_LONGS; } std::vector<int64_t> data; };
 struct Holder : Obj { Holder() { kind = K_HOLDER; } ClassObj* cls; std::vector<ByteArr*> vals; };
 struct ObjArr : Obj { ObjArr() { kind = K_OBJARR; } std::vector<_jobject*> elems; };
 
@@ -27,7 +28,7 @@ struct Vm {
   JNINativeInterface_ table;
   std::string exc_class, exc_msg;
   bool exc = false;
-  long locals = 0, pins = 0;
+  long locals = 0, pins = 0, criticals = 0;
   bool fail_double_pin = false;
   std::vector<ClassObj*> found;
   std::vector<std::pair<double*, DblArr*>> dbl_copies;
@@ -69,6 +70,7 @@ jsize fGetArrayLength(JNIEnv*, jarray a) {
   if (o->kind == K_OBJARR) return (jsize)static_cast<ObjArr*>(o)->elems.size();
   if (o->kind == K_BYTES) return (jsize)static_cast<ByteArr*>(o)->data.size();
   if (o->kind == K_DOUBLES) return (jsize)static_cast<DblArr*>(o)->data.size();
+  if (o->kind == K_LONGS) return (jsize)static_cast<LongArr*>(o)->data.size();
   return 0;
 }
 jobject fGetObjectArrayElement(JNIEnv*, jobjectArray a, jsize i) {
@@ -102,6 +104,29 @@ void fGetByteArrayRegion(JNIEnv*, jbyteArray a, jsize start, jsize len, jbyte* b
   memcpy(buf, static_cast<ByteArr*>(a)->data.data() + start, (size_t)len);
 }
 
+jdoubleArray fNewDoubleArray(JNIEnv*, jsize n) {
+  DblArr* d = new DblArr;
+  d->data.assign((size_t)n, 0.0);
+  g_vm->locals++;
+  return d;
+}
+void fSetDoubleArrayRegion(JNIEnv*, jdoubleArray a, jsize start, jsize len, const jdouble* buf) {
+  memcpy(static_cast<DblArr*>(a)->data.data() + start, buf, sizeof(double) * (size_t)len);
+}
+void* fGetPrimitiveArrayCritical(JNIEnv*, jarray a, jboolean* is_copy) {
+  if (is_copy) *is_copy = JNI_FALSE;
+  g_vm->pins++;
+  g_vm->criticals++;
+  Obj* o = static_cast<Obj*>(a);
+  if (o->kind == K_BYTES) return static_cast<ByteArr*>(o)->data.data();
+  if (o->kind == K_LONGS) return static_cast<LongArr*>(o)->data.data();
+  return static_cast<DblArr*>(o)->data.data();
+}
+void fReleasePrimitiveArrayCritical(JNIEnv*, jarray, void*, jint) {
+  g_vm->pins--;
+  g_vm->criticals--;
+}
+
 void unimplemented() {
   fprintf(stderr, "fake_jvm: the library called a JNI slot this stand-in does not implement\n");
   abort();
@@ -125,6 +150,10 @@ void init_vm(Vm* vm) {
   vm->table.fn[kJniGetDoubleArrayElements] = (void*)&fGetDoubleArrayElements;
   vm->table.fn[kJniReleaseDoubleArrayElements] = (void*)&fReleaseDoubleArrayElements;
   vm->table.fn[kJniGetByteArrayRegion] = (void*)&fGetByteArrayRegion;
+  vm->table.fn[kJniNewDoubleArray] = (void*)&fNewDoubleArray;
+  vm->table.fn[kJniSetDoubleArrayRegion] = (void*)&fSetDoubleArrayRegion;
+  vm->table.fn[kJniGetPrimitiveArrayCritical] = (void*)&fGetPrimitiveArrayCritical;
+  vm->table.fn[kJniReleasePrimitiveArrayCritical] = (void*)&fReleasePrimitiveArrayCritical;
   vm->env.functions = &vm->table;
 }
 
@@ -213,6 +242,85 @@ int fakejvm_pairhmm(const char* lib_path, int n_reads, int n_haps, const int64_t
     memcpy(out, result.data.data(), sizeof(double) * result.data.size());
   }
   done(&vm.env, &self);
+  leaks[0] = vm.locals;
+  leaks[1] = vm.pins;
+  g_vm = nullptr;
+  return exc ? 1 : 0;
+}
+
+
+// PDHMM binding (com.intel.gkl.pdhmm.IntelPDHMM).  object_api = 0: computePDHMMNative on the flat arrays
+// (n pairs).  object_api = 1: computeLikelihoodsNative on n_reads ReadDataHolders x n_haps HaplotypeDataHolders
+// built from the strided operands (read r at r * max_read, haplotype h at h * max_hap).
+// fault: 0 none, 1 HaplotypeDataHolder lacks haplotypePDBases, 2 flat array of the wrong size
+int fakejvm_pdhmm(const char* lib_path, int object_api, long long n, int n_reads, int n_haps, int max_hap, int max_read,
+                  const int8_t* hap, const int8_t* pd, const int8_t* rb, const int8_t* rq, const int8_t* ri,
+                  const int8_t* rd, const int8_t* rg, const int64_t* hap_len, const int64_t* read_len, int fault,
+                  double* out, char* exc_class, char* exc_msg, long* leaks) {
+  void* h = dlopen(lib_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) { snprintf(exc_msg, 255, "%s", dlerror()); return -2; }
+  typedef void (*PInit)(JNIEnv*, jclass, jclass, jclass, jint, jint, jint, jint);
+  typedef void (*PLik)(JNIEnv*, jobject, jobjectArray, jobjectArray, jdoubleArray);
+  typedef jdoubleArray (*PFlat)(JNIEnv*, jobject, jbyteArray, jbyteArray, jbyteArray, jbyteArray, jbyteArray, jbyteArray,
+                                jbyteArray, jlongArray, jlongArray, jint, jint, jint);
+  typedef void (*PDone)(JNIEnv*, jclass);
+  PInit init = (PInit)dlsym(h, "Java_com_intel_gkl_pdhmm_IntelPDHMM_initNative");
+  PLik lik = (PLik)dlsym(h, "Java_com_intel_gkl_pdhmm_IntelPDHMM_computeLikelihoodsNative");
+  PFlat flat = (PFlat)dlsym(h, "Java_com_intel_gkl_pdhmm_IntelPDHMM_computePDHMMNative");
+  PDone done = (PDone)dlsym(h, "Java_com_intel_gkl_pdhmm_IntelPDHMM_doneNative");
+  if (!init || !lik || !flat || !done) return -3;
+  Vm vm;
+  init_vm(&vm);
+  g_vm = &vm;
+  ClassObj read_cls, hap_cls, self_cls;
+  read_cls.fields = {"readBases", "readQuals", "insertionGOP", "deletionGOP", "overallGCP"};
+  hap_cls.fields = {"haplotypeBases", "haplotypePDBases"};
+  if (fault == 1) hap_cls.fields.pop_back();
+  Obj self;
+  init(&vm.env, &self_cls, &read_cls, &hap_cls, 0, 2, 0, 10);
+  long long n_out = 0;
+  if (!vm.exc && object_api) {
+    ObjArr reads, haps;
+    for (int r = 0; r < n_reads; r++) {
+      Holder* o = new Holder;
+      const int64_t a = (int64_t)r * max_read, b = a + read_len[r];
+      o->vals = {make_bytes((const uint8_t*)rb, a, b), make_bytes((const uint8_t*)rq, a, b), make_bytes((const uint8_t*)ri, a, b),
+                 make_bytes((const uint8_t*)rd, a, b), make_bytes((const uint8_t*)rg, a, b)};
+      reads.elems.push_back(o);
+    }
+    for (int i = 0; i < n_haps; i++) {
+      Holder* o = new Holder;
+      const int64_t a = (int64_t)i * max_hap, b = a + hap_len[i];
+      o->vals = {make_bytes((const uint8_t*)hap, a, b), make_bytes((const uint8_t*)pd, a, b)};
+      haps.elems.push_back(o);
+    }
+    DblArr result;
+    n_out = (long long)n_reads * n_haps;
+    result.data.assign((size_t)n_out, -12345.0);
+    lik(&vm.env, &self, &reads, &haps, &result);
+    if (!vm.exc) memcpy(out, result.data.data(), sizeof(double) * (size_t)n_out);
+  } else if (!vm.exc) {
+    ByteArr* a[7];
+    const int8_t* src[7] = {hap, pd, rb, rq, ri, rd, rg};
+    for (int i = 0; i < 7; i++) {
+      const long long len = n * (i < 2 ? max_hap : max_read) - ((fault == 2 && i == 3) ? 1 : 0);
+      a[i] = make_bytes((const uint8_t*)src[i], 0, len);
+    }
+    LongArr hl, rl;
+    hl.data.assign(hap_len, hap_len + n);
+    rl.data.assign(read_len, read_len + n);
+    jdoubleArray r = flat(&vm.env, &self, a[0], a[1], a[2], a[3], a[4], a[5], a[6], &hl, &rl, (jint)n, max_hap, max_read);
+    if (!vm.exc && r) {
+      memcpy(out, static_cast<DblArr*>(r)->data.data(), sizeof(double) * (size_t)n);
+      vm.locals--;  // the returned array is handed to the caller
+    }
+  }
+  const bool exc = vm.exc;
+  if (exc) {
+    snprintf(exc_class, 255, "%s", vm.exc_class.c_str());
+    snprintf(exc_msg, 255, "%s", vm.exc_msg.c_str());
+  }
+  done(&vm.env, &self_cls);
   leaks[0] = vm.locals;
   leaks[1] = vm.pins;
   g_vm = nullptr;

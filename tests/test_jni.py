@@ -25,7 +25,10 @@ def test_exports_exactly_the_symbols_intelpairhmm_binds():
               "Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihoodsNative",
               "Java_com_intel_gkl_pairhmm_IntelPairHmm_doneNative", "JNI_OnLoad"):
         assert s in syms
-    assert not [s for s in syms if s.startswith("Java_") and "IntelPairHmm" not in s]
+    # IntelPDHMM.java:206-216 (the same binary is installed as libgkl_pdhmm.so)
+    for s in ("initNative", "computeLikelihoodsNative", "computePDHMMNative", "doneNative"):
+        assert "Java_com_intel_gkl_pdhmm_IntelPDHMM_" + s in syms
+    assert not [s for s in syms if s.startswith("Java_") and "IntelPairHmm" not in s and "IntelPDHMM" not in s]
 
 
 def test_library_refuses_to_load_into_a_jvm_without_a_gpu():
@@ -81,3 +84,36 @@ def test_done_is_idempotent_and_reinitialise_works():
     rc, out, cls, msg, leaks = jni_fake.pairhmm(LIB, b, fault=7)
     assert rc == 0 and leaks == (0, 0), (cls, msg)
     assert (np.abs(out - oracle.port_pairhmm(b)[0]) / np.abs(out)).max() <= 1e-5
+
+
+PD_LIB = native.LIB_PATH.with_name("libgkl_pdhmm.so")
+
+
+def test_pdhmm_missing_field_is_illegal_argument_exception():
+    from gkl_b200 import pdhmm_batch as pb
+    from tests.conftest import GOLDEN
+    b, _ = pb.load_pdhmm_pairs_file(GOLDEN / "pdhmm_syn_990_1_2.txt", limit=4)
+    rc, _, cls, msg, leaks = jni_fake.pdhmm(PD_LIB, b, fault=1)
+    assert rc == 1 and cls == "java/lang/IllegalArgumentException" and msg == "Unable to get field ID" and leaks == (0, 0)
+
+
+@pytest.mark.gpu
+def test_pdhmm_flat_and_object_api_through_jni():
+    from gkl_b200 import pdhmm_batch as pb
+    from tests.conftest import GOLDEN
+    b, expected = pb.load_pdhmm_pairs_file(GOLDEN / "pdhmm_syn_199_68_51.txt")
+    rc, out, cls, msg, leaks = jni_fake.pdhmm(PD_LIB, b)
+    assert rc == 0 and leaks == (0, 0), (cls, msg)
+    assert np.abs(out - expected).max() <= 1e-4  # IntelPDHMMUnitTest.java:33
+    rc, _, cls, _, leaks = jni_fake.pdhmm(PD_LIB, b, fault=2)
+    assert rc == 1 and cls == "java/lang/IllegalArgumentException" and leaks == (0, 0)
+    reads, haps, exp = pb.load_pdhmm_new(GOLDEN / "pdhmm_new.txt")
+    reads, haps = reads[:40], haps[:12]
+    ops = pb.PdhmmBatch.from_pairs([(h[0], h[1], b"", b"", b"", b"", b"") for h in haps])
+    rds = pb.PdhmmBatch.from_pairs([(b"", b"", *r) for r in reads])
+    operands = pb.PdhmmBatch(ops.hap_bases, ops.hap_pdbases, rds.read_bases, rds.read_qual, rds.read_ins_qual,
+                             rds.read_del_qual, rds.gcp, ops.hap_lengths, rds.read_lengths, ops.max_hap, rds.max_read)
+    rc, out, cls, msg, leaks = jni_fake.pdhmm(PD_LIB, operands, object_api=True, n_reads=40, n_haps=12)
+    assert rc == 0 and leaks == (0, 0), (cls, msg)
+    want = exp.reshape(276, 48)[:40, :12].ravel()
+    assert np.abs(out - want).max() <= 1e-4
