@@ -1,0 +1,64 @@
+"""Config 3 (HaplotypeCaller-shaped: 32 active regions, ~300 reads x ~64 haplotypes, read lengths 35-250):
+32 sequential synchronous computeLikelihoods calls, as GATK issues them.
+
+    python bench/config3_bench.py [--out gpurun_out/config3.json]
+"""
+import argparse
+import json
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
+import oracle  # noqa: E402  (CPU baseline / checker only)
+from gkl_b200 import native, synth  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/config3.json")
+    ap.add_argument("--reps", type=int, default=5)
+    a = ap.parse_args()
+    regions = synth.config3(32)
+    cells = sum(r.cells() for r in regions)
+    eng = native.Engine(0, False)
+    outs = [eng.compute(r) for r in regions]  # warm-up (allocations, module load)
+    best = 1e9
+    for _ in range(a.reps):
+        t0 = time.perf_counter()
+        for r in regions:
+            eng.compute(r)
+        best = min(best, time.perf_counter() - t0)
+    kern = 0.0
+    launches = 0
+    classes = []
+    for r in regions:
+        eng.stage(r)
+        eng.run()
+        eng.synchronize()
+        kern += eng.time_runs(3)
+        st = eng.stats()
+        launches += st.kernel_launches
+        classes.append(st.n_classes)
+    threads = oracle.host_threads()
+    fn = oracle.ref_pairhmm if oracle.ref_available() else oracle.port_pairhmm
+    fn(regions[0], threads=threads)
+    cpu_s, err = 0.0, 0.0
+    for r, o in zip(regions, outs):
+        ref = fn(r, threads=threads)
+        cpu_s += ref[2]
+        err = max(err, float(np.max(np.abs(o - ref[0]) / np.abs(ref[0]))))
+    res = {"workload": "config3: 32 sequential calls", "cells": cells, "pairs": int(sum(r.n_reads * r.n_haps for r in regions)),
+           "e2e_ms_total": best * 1e3, "e2e_gcups": cells / best / 1e9, "e2e_ms_per_call": best * 1e3 / 32,
+           "kernels_only_ms_total": kern, "kernels_only_gcups": cells / kern / 1e6, "kernel_launches_total": launches,
+           "classes_per_call_mean": float(np.mean(classes)), "cpu_gcups": cells / cpu_s / 1e9, "cpu_threads": threads,
+           "max_rel_err": err}
+    print(json.dumps(res))
+    Path(a.out).parent.mkdir(parents=True, exist_ok=True)
+    Path(a.out).write_text(json.dumps(res) + "\n")
+
+
+if __name__ == "__main__":
+    main()

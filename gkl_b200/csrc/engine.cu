@@ -159,6 +159,8 @@ struct gklb_engine {
   HostBuf h_meta, h_counters;
   size_t arena_pitch = 0;
   int n_counters = 0;
+  int mega_counter0 = 0;   // first of the per-tile unified queue counters
+  bool use_mega = false;   // one multi-class launch per tile instead of one launch per class
   gklb_pairhmm_stats stats{};
   // forced kernel (measurement): policy,G,K,warps,var
   bool forced = false;
@@ -171,6 +173,7 @@ std::mutex g_mu;
 gklb_engine* g_engine = nullptr;
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+int class_cfg(const ClassInst& c);
 
 int upload_tables(gklb_engine* e) {
   const HostTables& t = host_tables();
@@ -214,6 +217,11 @@ int set_kernel_attrs() {
     CU(cudaFuncSetAttribute(t[i].fn_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     if (t[i].fn_list) CU(cudaFuncSetAttribute(t[i].fn_list, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   }
+  for (int pol : {POL_F2, POL_D1})
+    for (int lm = 0; lm < 2; lm++) {
+      const void* fn = mega_kernel(pol, lm);
+      if (fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    }
   return GKLB_OK;
 }
 
@@ -406,7 +414,15 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
       carry_bytes += c.carry_stride * warps * e->num_sms;
     }
   }
+  e->mega_counter0 = counters;
+  counters += 2 * (int)e->tiles.size();
   e->n_counters = counters;
+  {
+    const char* mg = getenv("GKLB_MEGA");
+    const bool all_cfg = std::all_of(e->classes.begin(), e->classes.end(), [](const ClassInst& c) { return class_cfg(c) >= 0; });
+    e->use_mega = !e->forced && all_cfg && (int)e->classes.size() <= kMaxMegaClasses &&
+                  (mg ? atoi(mg) != 0 : e->classes.size() > 1);
+  }
 
   CU(e->h_meta.ensure(meta_bytes));
   CU(e->d_meta.ensure(meta_bytes));
@@ -456,10 +472,12 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
   return GKLB_OK;
 }
 
-int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index) {
+// Fill the per-class kernel parameters for one (class, tile, kernel) combination.
+void fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index,
+                 SweepParams* out, int* grid_out, size_t* smem_out, uint32_t* slot_bytes_out) {
   const bool dbl = (k->policy == POL_D1);
   const HostTables& ht = host_tables();
-  SweepParams p;
+  SweepParams& p = *out;
   memset(&p, 0, sizeof(p));
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
   p.panel.image = dm + t.meta_off;
@@ -490,8 +508,6 @@ int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEn
   const int gpw = 32 / c.G;
   const int rpw = gpw * k->nr;
   const int slots = e->num_sms * k->warps;
-  int grid;
-  size_t smem;
   if (!list_mode) {
     const int n_blocks = c.n_rec / rpw;
     long long chunk = ((long long)n_blocks * t.n) / (12LL * slots);
@@ -501,14 +517,24 @@ int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEn
     p.hap_chunk = (int)chunk;
     p.n_chunks = (t.n + p.hap_chunk - 1) / p.hap_chunk;
     p.n_tasks = n_blocks * p.n_chunks;
-    grid = std::min(e->num_sms, (p.n_tasks + k->warps - 1) / k->warps);
-    smem = smem_layout(k->warps, t.bytes, (uint32_t)(rpw * 5 * c.stride), dbl ? 8 : 4).total;
+    *grid_out = std::min(e->num_sms, (p.n_tasks + k->warps - 1) / k->warps);
+    *slot_bytes_out = (uint32_t)(rpw * 5 * c.stride);
+    *smem_out = smem_layout(k->warps, t.bytes, *slot_bytes_out, dbl ? 8 : 4).total;
   } else {
     p.list_items = p.fb_items;
     p.list_count = p.fb_count;
-    grid = e->num_sms;
-    smem = smem_layout(k->warps, t.bytes, 0, 8).total;
+    *grid_out = e->num_sms;
+    *slot_bytes_out = 0;
+    *smem_out = smem_layout(k->warps, t.bytes, 0, 8).total;
   }
+}
+
+int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index) {
+  SweepParams p;
+  int grid;
+  size_t smem;
+  uint32_t slot_bytes;
+  fill_params(e, c, t, k, list_mode, tile_index, &p, &grid, &smem, &slot_bytes);
   if (smem > (size_t)kSmemMax) return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu)", smem);
   if (grid <= 0) return GKLB_OK;
   if (!list_mode) {
@@ -528,6 +554,60 @@ int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEn
   return GKLB_OK;
 }
 
+int class_cfg(const ClassInst& c) {
+  if (c.multi) return kCfgMulti;
+  for (int i = 0; i < kNumClasses; i++)
+    if (kClasses[i].G == c.G && kClasses[i].K == c.K) return i;
+  return -1;
+}
+
+// One launch for all classes of a tile (see k_mega_tasks).  policy: POL_F2 or POL_D1.
+int launch_mega_tile(gklb_engine* e, const Tile& t, int tile_index, int policy, bool list_mode) {
+  MegaParams mp;
+  memset(&mp, 0, sizeof(mp));
+  // longest classes first: their tasks are the most expensive, schedule them early
+  std::vector<const ClassInst*> order;
+  for (auto& c : e->classes) order.push_back(&c);
+  std::sort(order.begin(), order.end(), [](const ClassInst* a, const ClassInst* b) { return a->rows > b->rows; });
+  size_t smem = 0;
+  uint32_t slot_bytes = 0;
+  int tasks = 0;
+  for (const ClassInst* c : order) {
+    const KernelEntry* k = (policy == POL_D1) ? c->kd : c->kf;
+    const int i = mp.n_classes++;
+    int grid;
+    size_t sm;
+    uint32_t sb;
+    fill_params(e, *c, t, k, list_mode, tile_index, &mp.cls[i], &grid, &sm, &sb);
+    mp.cfg[i] = class_cfg(*c);
+    if (mp.cfg[i] < 0) return fail(GKLB_ERR_STATE, "class G=%d K=%d has no multi-class configuration", c->G, c->K);
+    tasks += mp.cls[i].n_tasks;
+    mp.task_end[i] = tasks;
+    slot_bytes = std::max(slot_bytes, sb);
+  }
+  unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
+  mp.queue = counters + e->mega_counter0 + 2 * tile_index + (list_mode ? 1 : 0);
+  smem = smem_layout(8, t.bytes, slot_bytes, policy == POL_D1 ? 8 : 4).total;
+  if (smem > (size_t)kSmemMax) return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu)", smem);
+  const int grid = list_mode ? e->num_sms : std::min(e->num_sms, (tasks + 7) / 8);
+  if (grid <= 0) return GKLB_OK;
+  if (!list_mode) {
+    while ((int)e->kev.size() < e->kev_used + 2) {
+      cudaEvent_t ev;
+      CU(cudaEventCreate(&ev));
+      e->kev.push_back(ev);
+    }
+    CU(cudaEventRecord(e->kev[e->kev_used], e->stream));
+  }
+  CU(launch_mega(mega_kernel(policy, list_mode ? 1 : 0), mp, slot_bytes, list_mode ? 1 : 0, grid, 8 * 32, smem, e->stream));
+  if (!list_mode) {
+    CU(cudaEventRecord(e->kev[e->kev_used + 1], e->stream));
+    e->kev_used += 2;
+  }
+  e->stats.kernel_launches++;
+  return GKLB_OK;
+}
+
 int do_run(gklb_engine* e) {
   if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
   CU(cudaSetDevice(e->device));
@@ -537,6 +617,16 @@ int do_run(gklb_engine* e) {
   if (e->classes.empty()) return GKLB_OK;
   CU(cudaMemsetAsync(e->d_counters.p, 0, sizeof(unsigned int) * (size_t)e->n_counters, e->stream));
   for (size_t ti = 0; ti < e->tiles.size(); ti++) {
+    if (e->use_mega) {
+      int rc;
+      if (e->use_double) {
+        if ((rc = launch_mega_tile(e, e->tiles[ti], (int)ti, POL_D1, false))) return rc;
+      } else {
+        if ((rc = launch_mega_tile(e, e->tiles[ti], (int)ti, POL_F2, false))) return rc;
+        if ((rc = launch_mega_tile(e, e->tiles[ti], (int)ti, POL_D1, true))) return rc;
+      }
+      continue;
+    }
     for (auto& c : e->classes) {
       int rc;
       if (e->use_double) {

@@ -480,111 +480,129 @@ __host__ __device__ inline SmemLayout smem_layout(int warps, uint32_t panel_byte
 }
 
 // ------------------------------------------------------------------------------------------
-// Task kernel: persistent CTAs; a task = (block of RPW records) x (chunk of haplotypes).
+// Per-CTA setup shared by all sweep kernels: mbarriers, ph2pr table, panel image (one TMA bulk copy).
 // ------------------------------------------------------------------------------------------
-template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams p) {
+template <class S>
+struct WarpCtx {
+  uint64_t* slot_bar;      // this warp's record-slot mbarrier
+  uint32_t slot_parity;
+  uint8_t* slot;           // this warp's record slot
+  const S* ph2pr_s;
+  const uint8_t* panel_s;
+  const int32_t* hpos;
+  const int32_t* hlen;
+  int warp, lane;
+  size_t warp_global;      // index of this warp in the grid
+};
+
+template <class S>
+__device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const PanelRef& panel, const void* ph2pr, int warps,
+                                                uint32_t slot_bytes) {
+  const SmemLayout lay = smem_layout(warps, panel.bytes, slot_bytes, sizeof(S));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
+  S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 1 + warps; i++) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = reinterpret_cast<const S*>(ph2pr)[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], panel.bytes);
+    tma_bulk_g2s(smem + lay.panel, panel.image, panel.bytes, &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  WarpCtx<S> c;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  c.slot_bar = &bars[1 + c.warp];
+  c.slot_parity = 0;
+  c.slot = smem + lay.slots + (size_t)c.warp * lay.slot_bytes;
+  c.ph2pr_s = ph2pr_s;
+  c.panel_s = smem + lay.panel;
+  c.hpos = reinterpret_cast<const int32_t*>(c.panel_s);
+  c.hlen = c.hpos + panel.n_haps;
+  c.warp_global = (size_t)blockIdx.x * warps + c.warp;
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// One task = (block of RPW records) x (chunk of haplotypes), executed by one warp.
+// ------------------------------------------------------------------------------------------
+template <class P, int G, int K, bool MULTI, int VAR>
+__device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
   typedef typename P::V V;
   typedef typename P::S S;
   constexpr int GPW = 32 / G;           // groups per warp
   constexpr int RPW = GPW * P::NR;      // records per warp-task
-  extern __shared__ __align__(128) uint8_t smem[];
-  const SmemLayout lay = smem_layout(WARPS, p.panel.bytes, (uint32_t)(RPW * 5 * p.cls.stride), sizeof(S));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
-  S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
-  const uint8_t* panel_s = smem + lay.panel;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = ctx.lane;
   const int t = lane % G, g = lane / G;
-  uint8_t* slot = smem + lay.slots + (size_t)warp * lay.slot_bytes;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 1 + WARPS; i++) mbar_init(&bars[i], 1);
-    fence_mbar_init();
-  }
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = reinterpret_cast<const S*>(p.ph2pr)[i];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], p.panel.bytes);
-    tma_bulk_g2s(smem + lay.panel, p.panel.image, p.panel.bytes, &bars[0]);
-  }
-  mbar_wait(&bars[0], 0);
-  const int32_t* hpos = reinterpret_cast<const int32_t*>(panel_s);
-  const int32_t* hlen = hpos + p.panel.n_haps;
-
   const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
-  uint32_t slot_parity = 0;
   const int cap = G * K;
-  V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) +
-                                          ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride_bytes)
-                   : nullptr;
   const int carry_pitch = p.panel.max_hap_len + 2;
+  V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) + ctx.warp_global * p.carry_stride_bytes)
+                   : nullptr;
+  const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
+  const int rec0 = blk * RPW;
+  // stage the block's packed records into this warp's slot
+  __syncwarp();
+  if (lane == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(ctx.slot_bar, RPW * rec_bytes);
+    tma_bulk_g2s(ctx.slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, ctx.slot_bar);
+  }
+  mbar_wait(ctx.slot_bar, ctx.slot_parity);
+  ctx.slot_parity ^= 1;
 
-  for (;;) {
-    unsigned int task = 0;
-    if (lane == 0) task = atomicAdd(p.task_counter, 1u);
-    task = __shfl_sync(0xffffffffu, task, 0);
-    if (task >= (unsigned)p.n_tasks) break;
-    const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
-    const int rec0 = blk * RPW;
-    // stage the block's packed records into this warp's slot
-    __syncwarp();
-    if (lane == 0) {
-      fence_proxy_async();
-      mbar_expect_tx(&bars[1 + warp], RPW * rec_bytes);
-      tma_bulk_g2s(slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, &bars[1 + warp]);
-    }
-    mbar_wait(&bars[1 + warp], slot_parity);
-    slot_parity ^= 1;
-
-    int rid[P::NR], npad[P::NR];
+  int rid[P::NR], npad[P::NR];
 #pragma unroll
-    for (int x = 0; x < P::NR; x++) {
-      const int rec = rec0 + g * P::NR + x;
-      rid[x] = p.cls.rec_rid[rec];
-      npad[x] = p.cls.rows - p.cls.rec_len[rec];
-    }
-    const int h_begin = chunk * p.hap_chunk, h_end = min(p.panel.n_haps, h_begin + p.hap_chunk);
+  for (int x = 0; x < P::NR; x++) {
+    const int rec = rec0 + g * P::NR + x;
+    rid[x] = p.cls.rec_rid[rec];
+    npad[x] = p.cls.rows - p.cls.rec_len[rec];
+  }
+  const int h_begin = chunk * p.hap_chunk, h_end = min(p.panel.n_haps, h_begin + p.hap_chunk);
 
-    LaneRows<P, K> L;
+  LaneRows<P, K> L;
+  if (!MULTI) {
+#pragma unroll
+    for (int x = 0; x < P::NR; x++)
+      load_lane_rows<P, K, VAR>(L, x, ctx.slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K,
+                                npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm));
+  }
+  for (int h = h_begin; h < h_end; h++) {
+    const int haplen = ctx.hlen[h];
+    const uint8_t* hap = ctx.panel_s + ctx.hpos[h];
+    const S initY = (S)p.init_const / (S)haplen;
+    const int n_steps = haplen + G - 1;
+    const int steady_end = haplen;
+    V sum = P::splat(0);
     if (!MULTI) {
+      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
+    } else {
+      V* cg = carry + (size_t)g * 6 * carry_pitch;  // two buffers of 3 lines, ping-pong
+      for (int pass = 0; pass < p.cls.n_pass; pass++) {
 #pragma unroll
-      for (int x = 0; x < P::NR; x++)
-        load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K, npad[x], t == 0,
-                             ph2pr_s, reinterpret_cast<const S*>(p.mm));
-    }
-    for (int h = h_begin; h < h_end; h++) {
-      const int haplen = hlen[h];
-      const uint8_t* hap = panel_s + hpos[h];
-      const S initY = (S)p.init_const / (S)haplen;
-      const int n_steps = haplen + G - 1;
-      const int steady_end = haplen;
-      V sum = P::splat(0);
-      if (!MULTI) {
-        sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
-      } else {
-        V* cg = carry + (size_t)g * 6 * carry_pitch;  // two buffers of 3 lines, ping-pong
-        for (int pass = 0; pass < p.cls.n_pass; pass++) {
-#pragma unroll
-          for (int x = 0; x < P::NR; x++)
-            load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, pass * cap + t * K,
-                                 npad[x], t == 0 && pass == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
-          V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
-          V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
-          sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
-                                     pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
-          __syncwarp();  // carry written by lane G-1 is read by lane 0 of the next pass
-        }
+        for (int x = 0; x < P::NR; x++)
+          load_lane_rows<P, K, VAR>(L, x, ctx.slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows,
+                                    pass * cap + t * K, npad[x], t == 0 && pass == 0, ctx.ph2pr_s,
+                                    reinterpret_cast<const S*>(p.mm));
+        V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
+        V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
+        sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
+                                        pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
+        __syncwarp();  // carry written by lane G-1 is read by lane 0 of the next pass
       }
-      if (t == G - 1) {
+    }
+    if (t == G - 1) {
 #pragma unroll
-        for (int x = 0; x < P::NR; x++) {
-          if (rid[x] >= 0) {
-            double* o = p.out + (size_t)rid[x] * p.panel.n_haps_total + (p.panel.hap0 + h);
-            if (!finish_pair<P>(P::get(sum, x), p.log10_init, o)) {
-              *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the fp64 rerun
-              const unsigned int k = atomicAdd(p.fb_count, 1u);
-              p.fb_items[k] = make_uint2((unsigned)(rec0 + g * P::NR + x), (unsigned)(p.panel.hap0 + h));
-            }
+      for (int x = 0; x < P::NR; x++) {
+        if (rid[x] >= 0) {
+          double* o = p.out + (size_t)rid[x] * p.panel.n_haps_total + (p.panel.hap0 + h);
+          if (!finish_pair<P>(P::get(sum, x), p.log10_init, o)) {
+            *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the fp64 rerun
+            const unsigned int k = atomicAdd(p.fb_count, 1u);
+            p.fb_items[k] = make_uint2((unsigned)(rec0 + g * P::NR + x), (unsigned)(p.panel.hap0 + h));
           }
         }
       }
@@ -593,95 +611,193 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams
 }
 
 // ------------------------------------------------------------------------------------------
-// List kernel: every group takes one (record, haplotype) item at a time -- the fp64 rerun of the
-// pairs the fp32 kernel flagged.  NR must be 1.
+// One warp-item of the rerun list: every group takes one (record, haplotype) pair.  NR must be 1.
 // ------------------------------------------------------------------------------------------
-template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams p) {
+template <class P, int G, int K, bool MULTI, int VAR>
+__device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
+                                              WarpCtx<typename P::S>& ctx) {
   typedef typename P::V V;
   typedef typename P::S S;
-  static_assert(P::NR == 1, "list kernel carries one read per lane");
+  static_assert(P::NR == 1, "list items carry one read per lane");
   constexpr int GPW = 32 / G;
-  extern __shared__ __align__(128) uint8_t smem[];
-  const unsigned int n_items = *p.list_count;
-  if (n_items == 0) return;
-  const SmemLayout lay = smem_layout(WARPS, p.panel.bytes, 0, sizeof(S));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
-  S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
-  const uint8_t* panel_s = smem + lay.panel;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int lane = ctx.lane;
   const int t = lane % G, g = lane / G;
-  if (threadIdx.x == 0) {
-    mbar_init(&bars[0], 1);
-    fence_mbar_init();
-  }
-  for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = reinterpret_cast<const S*>(p.ph2pr)[i];
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], p.panel.bytes);
-    tma_bulk_g2s(smem + lay.panel, p.panel.image, p.panel.bytes, &bars[0]);
-  }
-  mbar_wait(&bars[0], 0);
-  const int32_t* hpos = reinterpret_cast<const int32_t*>(panel_s);
-  const int32_t* hlen = hpos + p.panel.n_haps;
   const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
   const int cap = G * K;
-  V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) +
-                                          ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride_bytes)
-                   : nullptr;
   const int carry_pitch = p.panel.max_hap_len + 2;
-  const unsigned int n_warp_items = (n_items + GPW - 1) / GPW;
-
-  for (;;) {
-    unsigned int wi = 0;
-    if (lane == 0) wi = atomicAdd(p.task_counter, 1u);
-    wi = __shfl_sync(0xffffffffu, wi, 0);
-    if (wi >= n_warp_items) break;
-    const unsigned int item = wi * GPW + g;
-    const bool valid = item < n_items;
-    const uint2 it = valid ? p.list_items[item] : make_uint2(0u, 0u);
-    const int h = (int)it.y - p.panel.hap0;
-    const bool mine = valid && h >= 0 && h < p.panel.n_haps;  // items of other tiles are skipped
-    const int rec = (int)it.x;
-    const int haplen = mine ? hlen[h] : 0;
-    const uint8_t* hap = panel_s + (mine ? hpos[h] : hpos[0]);
-    const int rid = mine ? p.cls.rec_rid[rec] : -1;
-    const int npad = mine ? p.cls.rows - p.cls.rec_len[rec] : 0;
-    const S initY = (S)p.init_const / (S)max(haplen, 1);
-    int n_steps = mine ? haplen + G - 1 : 0;
+  V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) + ctx.warp_global * p.carry_stride_bytes)
+                   : nullptr;
+  const unsigned int item = wi * GPW + g;
+  const bool valid = item < n_items;
+  const uint2 it = valid ? p.list_items[item] : make_uint2(0u, 0u);
+  const int h = (int)it.y - p.panel.hap0;
+  const bool mine = valid && h >= 0 && h < p.panel.n_haps;  // items of other tiles are skipped
+  const int rec = (int)it.x;
+  const int haplen = mine ? ctx.hlen[h] : 0;
+  const uint8_t* hap = ctx.panel_s + (mine ? ctx.hpos[h] : ctx.hpos[0]);
+  const int rid = mine ? p.cls.rec_rid[rec] : -1;
+  const int npad = mine ? p.cls.rows - p.cls.rec_len[rec] : 0;
+  const S initY = (S)p.init_const / (S)max(haplen, 1);
+  int n_steps = mine ? haplen + G - 1 : 0;
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) n_steps = max(n_steps, __shfl_xor_sync(0xffffffffu, n_steps, o));
-    int steady_end = haplen;  // steps G..min(haplen) are unguarded; a warp with an idle group has none
+  for (int o = 16; o >= 1; o >>= 1) n_steps = max(n_steps, __shfl_xor_sync(0xffffffffu, n_steps, o));
+  int steady_end = haplen;  // steps G..min(haplen) are unguarded; a warp with an idle group has none
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) steady_end = min(steady_end, __shfl_xor_sync(0xffffffffu, steady_end, o));
-    const uint8_t* recp = p.cls.records + (size_t)rec * rec_bytes;
-    LaneRows<P, K> L;
-    V sum = P::splat(0);
-    if (!MULTI) {
-      load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm));
-      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
-    } else {
-      V* cg = carry + (size_t)g * 6 * carry_pitch;
-      for (int pass = 0; pass < p.cls.n_pass; pass++) {
-        load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, pass * cap + t * K, npad, t == 0 && pass == 0, ph2pr_s,
-                             reinterpret_cast<const S*>(p.mm));
-        V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
-        V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
-        sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
-                                   pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
-        __syncwarp();
-      }
+  for (int o = 16; o >= 1; o >>= 1) steady_end = min(steady_end, __shfl_xor_sync(0xffffffffu, steady_end, o));
+  if (n_steps == 0) return;
+  const uint8_t* recp = p.cls.records + (size_t)rec * rec_bytes;
+  LaneRows<P, K> L;
+  V sum = P::splat(0);
+  if (!MULTI) {
+    load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
+                              reinterpret_cast<const S*>(p.mm));
+    sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
+  } else {
+    V* cg = carry + (size_t)g * 6 * carry_pitch;
+    for (int pass = 0; pass < p.cls.n_pass; pass++) {
+      load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, pass * cap + t * K, npad, t == 0 && pass == 0,
+                                ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm));
+      V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
+      V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
+      sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
+                                      pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
+      __syncwarp();
     }
-    if (t == G - 1 && mine && rid >= 0) {
-      double* o = p.out + (size_t)rid * p.panel.n_haps_total + (p.panel.hap0 + h);
-      finish_pair<P>(P::get(sum, 0), p.log10_init, o);
-    }
+  }
+  if (t == G - 1 && mine && rid >= 0) {
+    double* o = p.out + (size_t)rid * p.panel.n_haps_total + (p.panel.hap0 + h);
+    finish_pair<P>(P::get(sum, 0), p.log10_init, o);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// Packing kernel: raw batch arenas -> class records (top-padded, planes of `stride` bytes).
-// One warp per record.
+// Single-class kernels: persistent CTAs, tasks / list items pulled from an atomic counter.
+// ------------------------------------------------------------------------------------------
+template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams p) {
+  typedef typename P::S S;
+  constexpr int RPW = (32 / G) * P::NR;
+  extern __shared__ __align__(128) uint8_t smem[];
+  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, (uint32_t)(RPW * 5 * p.cls.stride));
+  for (;;) {
+    unsigned int task = 0;
+    if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= (unsigned)p.n_tasks) break;
+    run_task<P, G, K, MULTI, VAR>(p, task, ctx);
+  }
+}
+
+template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams p) {
+  typedef typename P::S S;
+  constexpr int GPW = 32 / G;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const unsigned int n_items = *p.list_count;
+  if (n_items == 0) return;
+  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, 0);
+  const unsigned int n_warp_items = (n_items + GPW - 1) / GPW;
+  for (;;) {
+    unsigned int wi = 0;
+    if (ctx.lane == 0) wi = atomicAdd(p.task_counter, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= n_warp_items) break;
+    run_list_item<P, G, K, MULTI, VAR>(p, wi, n_items, ctx);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Multi-class ("mega") kernels: one launch covers every length class of a batch.  Each warp pulls from
+// ONE queue that concatenates the classes' tasks (longest class first) and dispatches on the class
+// configuration, so a HaplotypeCaller-shaped batch with a dozen length classes of ~25 reads each
+// fills the GPU with a single launch instead of a dozen serialised under-filled ones.
+// ------------------------------------------------------------------------------------------
+constexpr int kMaxMegaClasses = 14;
+constexpr int kCfgMulti = 13;  // configuration index of the multi-pass class (32 x 8 rows per pass)
+
+struct MegaParams {
+  int n_classes;
+  int cfg[kMaxMegaClasses];        // index into the class table (G, K), kCfgMulti for multi-pass
+  int task_end[kMaxMegaClasses];   // exclusive prefix of tasks in the unified queue (task mode)
+  unsigned int* queue;             // the unified work counter
+  SweepParams cls[kMaxMegaClasses];
+};
+
+template <class P, int G, int K, bool MULTI>
+__device__ __noinline__ void mega_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
+  run_task<P, G, K, MULTI, 2>(p, task, ctx);
+}
+template <class P, int G, int K, bool MULTI>
+__device__ __noinline__ void mega_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
+                                       WarpCtx<typename P::S>& ctx) {
+  run_list_item<P, G, K, MULTI, 2>(p, wi, n_items, ctx);
+}
+
+#define GKLB_MEGA_DISPATCH(FN, ...)                                   \
+  switch (cfg) {                                                      \
+    case 0: FN<P, 8, 4, false>(__VA_ARGS__); break;                   \
+    case 1: FN<P, 8, 5, false>(__VA_ARGS__); break;                   \
+    case 2: FN<P, 8, 6, false>(__VA_ARGS__); break;                   \
+    case 3: FN<P, 8, 7, false>(__VA_ARGS__); break;                   \
+    case 4: FN<P, 8, 8, false>(__VA_ARGS__); break;                   \
+    case 5: FN<P, 16, 5, false>(__VA_ARGS__); break;                  \
+    case 6: FN<P, 16, 6, false>(__VA_ARGS__); break;                  \
+    case 7: FN<P, 16, 7, false>(__VA_ARGS__); break;                  \
+    case 8: FN<P, 16, 8, false>(__VA_ARGS__); break;                  \
+    case 9: FN<P, 32, 5, false>(__VA_ARGS__); break;                  \
+    case 10: FN<P, 32, 6, false>(__VA_ARGS__); break;                 \
+    case 11: FN<P, 32, 7, false>(__VA_ARGS__); break;                 \
+    case 12: FN<P, 32, 8, false>(__VA_ARGS__); break;                 \
+    default: FN<P, 32, 8, true>(__VA_ARGS__); break;                  \
+  }
+
+template <class P, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_mega_tasks(const __grid_constant__ MegaParams m, uint32_t slot_bytes) {
+  typedef typename P::S S;
+  extern __shared__ __align__(128) uint8_t smem[];
+  WarpCtx<S> ctx = setup_cta<S>(smem, m.cls[0].panel, m.cls[0].ph2pr, WARPS, slot_bytes);
+  const unsigned int total = (unsigned)m.task_end[m.n_classes - 1];
+  for (;;) {
+    unsigned int task = 0;
+    if (ctx.lane == 0) task = atomicAdd(m.queue, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= total) break;
+    int c = 0;
+    while (task >= (unsigned)m.task_end[c]) c++;
+    const unsigned int local = task - (c ? (unsigned)m.task_end[c - 1] : 0u);
+    const int cfg = m.cfg[c];
+    GKLB_MEGA_DISPATCH(mega_task, m.cls[c], local, ctx)
+  }
+}
+
+template <class P, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_constant__ MegaParams m) {
+  typedef typename P::S S;
+  extern __shared__ __align__(128) uint8_t smem[];
+  // warp-items per class follow from the list lengths the fp32 kernel left in device memory
+  unsigned int end[kMaxMegaClasses];
+  unsigned int total = 0;
+  for (int c = 0; c < m.n_classes; c++) {
+    const unsigned int gpw = (m.cfg[c] <= 4) ? 4u : (m.cfg[c] <= 8) ? 2u : 1u;
+    total += (*m.cls[c].list_count + gpw - 1) / gpw;
+    end[c] = total;
+  }
+  if (total == 0) return;
+  WarpCtx<S> ctx = setup_cta<S>(smem, m.cls[0].panel, m.cls[0].ph2pr, WARPS, 0);
+  for (;;) {
+    unsigned int wi = 0;
+    if (ctx.lane == 0) wi = atomicAdd(m.queue, 1u);
+    wi = __shfl_sync(0xffffffffu, wi, 0);
+    if (wi >= total) break;
+    int c = 0;
+    while (wi >= end[c]) c++;
+    const unsigned int local = wi - (c ? end[c - 1] : 0u);
+    const int cfg = m.cfg[c];
+    const unsigned int n_items = *m.cls[c].list_count;
+    GKLB_MEGA_DISPATCH(mega_item, m.cls[c], local, n_items, ctx)
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 struct PackParams {
   const int64_t* read_off;

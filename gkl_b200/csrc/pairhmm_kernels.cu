@@ -102,6 +102,20 @@ const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, i
   return nullptr;
 }
 
+const void* mega_kernel(int policy, int list_mode) {
+  if (policy == POL_F2 && !list_mode) return reinterpret_cast<const void*>(&k_mega_tasks<VF2, 8>);
+  if (policy == POL_D1 && !list_mode) return reinterpret_cast<const void*>(&k_mega_tasks<VD1, 8>);
+  if (policy == POL_D1 && list_mode) return reinterpret_cast<const void*>(&k_mega_list<VD1, 8>);
+  return nullptr;
+}
+
+cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes, int list_mode, int grid, int threads,
+                        size_t smem, cudaStream_t s) {
+  void* args_tasks[] = {const_cast<MegaParams*>(&m), &slot_bytes};
+  void* args_list[] = {const_cast<MegaParams*>(&m)};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(threads), list_mode ? args_list : args_tasks, smem, s);
+}
+
 cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
   void* args[] = {const_cast<SweepParams*>(&p)};
   return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, s);
