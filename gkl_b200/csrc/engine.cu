@@ -158,6 +158,9 @@ struct gklb_engine {
   DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
   HostBuf h_meta, h_counters;
   size_t arena_pitch = 0;
+  const int64_t* p_read_off = nullptr;   // where the staged offsets / arenas live on the device
+  const int64_t* p_hap_off = nullptr;
+  const uint8_t* p_arenas = nullptr;
   int n_counters = 0;
   int mega_counter0 = 0;   // first of the per-tile unified queue counters
   bool use_mega = false;   // one multi-class launch per tile instead of one launch per class
@@ -424,13 +427,24 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
                   (mg ? atoi(mg) != 0 : e->classes.size() > 1);
   }
 
-  CU(e->h_meta.ensure(meta_bytes));
-  CU(e->d_meta.ensure(meta_bytes));
+  // small host-resident batches: offsets + arenas are staged behind the meta block (see below)
+  e->arena_pitch = align_up((size_t)total_read, 256);
+  const bool consolidate = !hap_on_device && (size_t)total_read * 5 <= (4u << 20);
+  size_t st_read_off = 0, st_hap_off = 0, st_arena = 0, staged_bytes = meta_bytes;
+  if (consolidate) {
+    st_read_off = staged_bytes;
+    staged_bytes += align_up(sizeof(int64_t) * ((size_t)b->n_reads + 1), 256);
+    st_hap_off = staged_bytes;
+    staged_bytes += align_up(sizeof(int64_t) * ((size_t)b->n_haps + 1), 256);
+    st_arena = staged_bytes;
+    staged_bytes += 5 * e->arena_pitch;
+  }
+  CU(e->h_meta.ensure(staged_bytes));
+  CU(e->d_meta.ensure(staged_bytes));
   CU(e->d_records.ensure(rec_bytes));
   CU(e->d_read_off.ensure(sizeof(int64_t) * ((size_t)b->n_reads + 1)));
   CU(e->d_hap_off.ensure(sizeof(int64_t) * ((size_t)b->n_haps + 1)));
-  e->arena_pitch = align_up((size_t)total_read, 256);
-  CU(e->d_arenas.ensure(e->arena_pitch * 5));
+  if (!consolidate) CU(e->d_arenas.ensure(e->arena_pitch * 5));
   CU(e->d_out.ensure(sizeof(double) * (size_t)e->stats.pairs));
   if (fb_items) CU(e->d_fb.ensure(sizeof(uint2) * fb_items));
   CU(e->d_counters.ensure(sizeof(unsigned int) * (size_t)counters));
@@ -444,28 +458,52 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
     memcpy(hm + c.meta_len, c.len.data(), sizeof(int32_t) * c.n_rec);
   }
   cudaStream_t s = e->stream;
-  CU(cudaMemcpyAsync(e->d_meta.p, hm, meta_bytes, cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(e->d_read_off.p, b->read_off, sizeof(int64_t) * ((size_t)b->n_reads + 1), cudaMemcpyHostToDevice, s));
-  CU(cudaMemcpyAsync(e->d_hap_off.p, b->hap_off, sizeof(int64_t) * ((size_t)b->n_haps + 1), cudaMemcpyHostToDevice, s));
-  uint8_t* da = static_cast<uint8_t*>(e->d_arenas.p);
+  const size_t off_bytes_r = sizeof(int64_t) * ((size_t)b->n_reads + 1), off_bytes_h = sizeof(int64_t) * ((size_t)b->n_haps + 1);
   const uint8_t* src[5] = {b->read_bases, b->read_quals, b->ins_gop, b->del_gop, b->gcp};
-  for (int i = 0; i < 5; i++)
-    CU(cudaMemcpyAsync(da + i * e->arena_pitch, src[i], (size_t)total_read, cudaMemcpyDefault, s));
+  uint8_t* dmw = static_cast<uint8_t*>(e->d_meta.p);
+  if (consolidate) {
+    // small batch: offsets and arenas ride in the same pinned staging buffer -> one host->device copy
+    memcpy(hm + st_read_off, b->read_off, off_bytes_r);
+    memcpy(hm + st_hap_off, b->hap_off, off_bytes_h);
+    for (int i = 0; i < 5; i++) memcpy(hm + st_arena + i * e->arena_pitch, src[i], (size_t)total_read);
+    CU(cudaMemcpyAsync(dmw, hm, staged_bytes, cudaMemcpyHostToDevice, s));
+    e->p_read_off = reinterpret_cast<const int64_t*>(dmw + st_read_off);
+    e->p_hap_off = reinterpret_cast<const int64_t*>(dmw + st_hap_off);
+    e->p_arenas = dmw + st_arena;
+  } else {
+    CU(cudaMemcpyAsync(dmw, hm, meta_bytes, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->d_read_off.p, b->read_off, off_bytes_r, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->d_hap_off.p, b->hap_off, off_bytes_h, cudaMemcpyHostToDevice, s));
+    uint8_t* da = static_cast<uint8_t*>(e->d_arenas.p);
+    for (int i = 0; i < 5; i++)
+      CU(cudaMemcpyAsync(da + i * e->arena_pitch, src[i], (size_t)total_read, cudaMemcpyDefault, s));
+    e->p_read_off = static_cast<const int64_t*>(e->d_read_off.p);
+    e->p_hap_off = static_cast<const int64_t*>(e->d_hap_off.p);
+    e->p_arenas = da;
+  }
 
-  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
-  for (auto& c : e->classes) {
+  // one packing launch for all classes (32 classes per launch)
+  const uint8_t* dm = dmw;
+  for (size_t c0 = 0; c0 < e->classes.size(); c0 += 32) {
     PackParams pp;
-    pp.read_off = static_cast<const int64_t*>(e->d_read_off.p);
-    pp.bases = da;
-    pp.quals = da + e->arena_pitch;
-    pp.ins = da + 2 * e->arena_pitch;
-    pp.del = da + 3 * e->arena_pitch;
-    pp.gcp = da + 4 * e->arena_pitch;
-    pp.records = static_cast<uint8_t*>(e->d_records.p) + c.rec_off;
-    pp.rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
-    pp.n_rec = c.n_rec;
-    pp.rows = c.rows;
-    pp.stride = c.stride;
+    memset(&pp, 0, sizeof(pp));
+    pp.read_off = e->p_read_off;
+    pp.bases = e->p_arenas;
+    pp.quals = e->p_arenas + e->arena_pitch;
+    pp.ins = e->p_arenas + 2 * e->arena_pitch;
+    pp.del = e->p_arenas + 3 * e->arena_pitch;
+    pp.gcp = e->p_arenas + 4 * e->arena_pitch;
+    for (size_t ci = c0; ci < std::min(e->classes.size(), c0 + 32); ci++) {
+      const ClassInst& c = e->classes[ci];
+      PackClass& pc = pp.cls[pp.n_classes++];
+      pc.records = static_cast<uint8_t*>(e->d_records.p) + c.rec_off;
+      pc.rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
+      pc.rec_begin = pp.n_rec_total;
+      pc.n_rec = c.n_rec;
+      pc.rows = c.rows;
+      pc.stride = c.stride;
+      pp.n_rec_total += c.n_rec;
+    }
     CU(launch_pack(pp, s));
   }
   e->staged = true;
@@ -783,7 +821,7 @@ int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_bases_dev) {
   CU(cudaSetDevice(e->device));
   uint8_t* dm = static_cast<uint8_t*>(e->d_meta.p);
   for (auto& t : e->tiles)
-    CU(launch_fill_panel(dm + t.meta_off, t.n, t.hap0, static_cast<const int64_t*>(e->d_hap_off.p),
+    CU(launch_fill_panel(dm + t.meta_off, t.n, t.hap0, e->p_hap_off,
                          static_cast<const uint8_t*>(hap_bases_dev), e->stream));
   return GKLB_OK;
 }

@@ -799,18 +799,25 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------
-struct PackParams {
+struct PackClass {
+  uint8_t* records;         // [n_rec][5][stride]
+  const int32_t* rec_rid;   // [n_rec]
+  int rec_begin;            // index of the class's first record in the launch's flat record numbering
+  int n_rec;
+  int rows;
+  int stride;
+};
+
+struct PackParams {         // one launch packs the records of every class of a batch
   const int64_t* read_off;
   const uint8_t* bases;
   const uint8_t* quals;
   const uint8_t* ins;
   const uint8_t* del;
   const uint8_t* gcp;
-  uint8_t* records;
-  const int32_t* rec_rid;
-  int n_rec;
-  int rows;
-  int stride;
+  int n_classes;
+  int n_rec_total;
+  PackClass cls[32];
 };
 
 }  // namespace gklb

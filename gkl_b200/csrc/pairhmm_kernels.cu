@@ -10,34 +10,38 @@
 namespace gklb {
 
 // One warp per record: raw batch arenas -> top-padded class records.
-__global__ void k_pack_reads(const PackParams p) {
-  const int rec = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
+__global__ void k_pack_reads(const __grid_constant__ PackParams p) {
+  const int g = (int)((blockIdx.x * (size_t)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (rec >= p.n_rec) return;
-  const int rid = p.rec_rid[rec];
+  if (g >= p.n_rec_total) return;
+  int ci = 0;
+  while (ci + 1 < p.n_classes && g >= p.cls[ci + 1].rec_begin) ci++;
+  const PackClass& c = p.cls[ci];
+  const int rec = g - c.rec_begin;
+  const int rid = c.rec_rid[rec];
   int64_t off = 0;
   int len = 0;
   if (rid >= 0) {
     off = p.read_off[rid];
     len = (int)(p.read_off[rid + 1] - off);
   }
-  const int npad = p.rows - len;
-  uint8_t* r = p.records + (size_t)rec * 5 * p.stride;
-  for (int row = lane; row < p.stride; row += 32) {
-    uint8_t b = 0, q = 0, i = 0, d = 0, c = 0;
-    if (row >= npad && row < p.rows) {
+  const int npad = c.rows - len;
+  uint8_t* r = c.records + (size_t)rec * 5 * c.stride;
+  for (int row = lane; row < c.stride; row += 32) {
+    uint8_t b = 0, q = 0, i = 0, d = 0, cg = 0;
+    if (row >= npad && row < c.rows) {
       const int64_t s = off + (row - npad);
       b = base_nibble(p.bases[s]);
       q = p.quals[s] & 127;  // avx-pairhmm-template.h:134-136,149
       i = p.ins[s] & 127;
       d = p.del[s] & 127;
-      c = p.gcp[s] & 127;
+      cg = p.gcp[s] & 127;
     }
     r[row] = b;
-    r[p.stride + row] = q;
-    r[2 * p.stride + row] = i;
-    r[3 * p.stride + row] = d;
-    r[4 * p.stride + row] = c;
+    r[c.stride + row] = q;
+    r[2 * c.stride + row] = i;
+    r[3 * c.stride + row] = d;
+    r[4 * c.stride + row] = cg;
   }
 }
 
@@ -123,7 +127,7 @@ cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int thr
 
 cudaError_t launch_pack(const PackParams& p, cudaStream_t s) {
   const int threads = 256;
-  const long long total = (long long)p.n_rec * 32;
+  const long long total = (long long)p.n_rec_total * 32;
   const int grid = (int)((total + threads - 1) / threads);
   if (grid == 0) return cudaSuccess;
   k_pack_reads<<<grid, threads, 0, s>>>(p);
