@@ -305,9 +305,16 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
   return GKLB_OK;
 }
 
-uint32_t slot_bytes_total(const ClassInst& c, const KernelEntry* k) {
+// Per-warp slot: the task's packed records, then (VAR 3) the prior table of 5 symbols x K rows x 32 lanes.
+uint32_t warp_slot_bytes(const ClassInst& c, const KernelEntry* k, bool list_mode) {
   const uint32_t rpw = (uint32_t)((32 / c.G) * k->nr);
-  return (uint32_t)k->warps * (uint32_t)align_up((size_t)rpw * 5 * c.stride, 128);
+  const uint32_t rec = list_mode ? 0u : (uint32_t)align_up((size_t)rpw * 5 * c.stride, 128);
+  const uint32_t tbl = (k->var == 3) ? (uint32_t)(kPriorSyms * c.K * 32 * 8) : 0u;
+  return rec + tbl;
+}
+
+uint32_t slot_bytes_total(const ClassInst& c, const KernelEntry* k) {
+  return (uint32_t)k->warps * (uint32_t)align_up((size_t)warp_slot_bytes(c, k, false), 128);
 }
 
 // Split the haplotypes into tiles whose panel image fits beside the largest slot area.
@@ -356,7 +363,7 @@ void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) 
     hpos[i] = (int32_t)(off + kHapLeftMargin - 1);  // column 0; column c is at hpos + c
     hlen[i] = len;
     uint8_t* dst = img + off + kHapLeftMargin;
-    for (int c = 0; c < len; c++) dst[c] = base_nibble(b->hap_bases[o + c]);
+    for (int c = 0; c < len; c++) dst[c] = panel_byte(b->hap_bases[o + c]);
     off += kHapLeftMargin + len + kHapRightMargin;
   }
 }
@@ -556,15 +563,16 @@ void fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kernel
     p.n_chunks = (t.n + p.hap_chunk - 1) / p.hap_chunk;
     p.n_tasks = n_blocks * p.n_chunks;
     *grid_out = std::min(e->num_sms, (p.n_tasks + k->warps - 1) / k->warps);
-    *slot_bytes_out = (uint32_t)(rpw * 5 * c.stride);
+    *slot_bytes_out = warp_slot_bytes(c, k, false);
     *smem_out = smem_layout(k->warps, t.bytes, *slot_bytes_out, dbl ? 8 : 4).total;
   } else {
     p.list_items = p.fb_items;
     p.list_count = p.fb_count;
     *grid_out = e->num_sms;
-    *slot_bytes_out = 0;
-    *smem_out = smem_layout(k->warps, t.bytes, 0, 8).total;
+    *slot_bytes_out = warp_slot_bytes(c, k, true);
+    *smem_out = smem_layout(k->warps, t.bytes, *slot_bytes_out, 8).total;
   }
+  p.slot_bytes = *slot_bytes_out;
 }
 
 int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index) {

@@ -57,6 +57,20 @@ __host__ __device__ inline uint8_t base_nibble(uint8_t ch) {
   }
 }
 
+// Symbol index of a haplotype base (ConvertChar order: A C T G N) and its byte in the panel image:
+// low 3 bits = index (VAR 3 prior-table lookup), high nibble = one-hot code (VAR 0-2 match test).
+__host__ __device__ inline uint8_t base_index(uint8_t ch) {
+  switch (ch) {
+    case 'C': return 1;
+    case 'T': return 2;
+    case 'G': return 3;
+    case 'N': return 4;
+    default: return 0;
+  }
+}
+__host__ __device__ inline uint8_t panel_byte(uint8_t ch) { return (uint8_t)(base_index(ch) | (base_nibble(ch) << 4)); }
+constexpr int kPriorSyms = 5;
+
 // ------------------------------------------------------------------------------------------
 // Lane arithmetic policies.  V is what one lane holds per matrix cell slot (64 bits for the
 // two product policies), S the scalar type, NR the number of reads carried per lane.
@@ -161,6 +175,7 @@ struct SweepParams {
   size_t carry_stride_bytes;    // bytes per warp
   double init_const;            // 2^120 (fp32) or 2^1020 (fp64)   Context.h:142,183
   double log10_init;            // log10f(2^120) widened, or log10(2^1020)
+  uint32_t slot_bytes;          // per-warp shared-memory slot: packed records (task mode) + prior table (VAR 3)
 };
 
 // ------------------------------------------------------------------------------------------
@@ -208,6 +223,8 @@ struct LaneRows {
   // VAR 2 (folded):        Am=pMM, Ax=pGAPM(next row), Gm=1-e, Gx=e/3, pMY holds pMY*pGAPM(next row):
   //                        the Y state is Y/pMY and the diagonal state is pGAPM(next row)*(X+Y), which
   //                        takes one multiply out of the Y update and one out of the M update
+  // VAR 3 (table):         as VAR 2, but the prior (1-e | e/3) of every (row, haplotype symbol) sits in a per-warp
+  //                        shared-memory table and arrives by LDS: no LOP3/FSEL and no Gm/Gx registers
   typename P::V Am[K], Ax[K], Gm[K], Gx[K];
   typename P::V pMX[K], pXX[K], pMY[K];      // pYY == pXX (both ph2pr[gcp], avx-pairhmm-template.h:142-146)
   typename P::V pXXtop;                      // pXX[0] as used by the X update (zeroed on the first lane of pass 0)
@@ -226,7 +243,7 @@ __device__ __forceinline__ int mm_index(int ins_q, int del_q) {  // Context.h:15
 template <class P, int K, int VAR>
 __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const uint8_t* rec, int stride, int n_rows,
                                                int row0, int n_pad, bool top_is_row0, const typename P::S* __restrict__ ph2pr,
-                                               const typename P::S* __restrict__ mm) {
+                                               const typename P::S* __restrict__ mm, typename P::S* tbl = nullptr) {
   typedef typename P::S S;
   uint32_t pm = 0;
 #pragma unroll
@@ -248,7 +265,14 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
     else { am = pmm; ax = pgap; gm = om; gx = th; }
     S mx = ph2pr[ig], my = ph2pr[dg], xx = pc;
     if (pad) { am = ax = gm = gx = (S)0; mx = my = (S)0; xx = (S)1; pm |= 1u << j; }
-    if (VAR == 2) {
+    if (VAR == 3) {
+      // prior table: tbl is this lane's column; entry (symbol, row j) of read x at ((symbol * K + j) * 32) * NR + x
+      const uint32_t symnib[kPriorSyms] = {1u, 2u, 4u, 8u, 15u};
+#pragma unroll
+      for (int sy = 0; sy < kPriorSyms; sy++)
+        tbl[(size_t)((sy * K + j) * 32) * P::NR + x] = pad ? (S)0 : ((nib & symnib[sy]) ? om : th);
+    }
+    if (VAR >= 2) {
       // pGAPM of the row below (0 past the last row and for padding rows, whose M must stay 0)
       S gnext = (S)0;
       if (row + 1 < n_rows && row + 1 >= n_pad) gnext = (S)1 - ph2pr[rec[4 * stride + row + 1]];
@@ -295,7 +319,9 @@ struct Sweeper {
   V inj;                  // what row 0 feeds the first row's M update
   const uint8_t* hap;
   int haplen, c;
-  uint32_t hb;
+  uint32_t hb;            // VAR 0-2: symbol byte of column c;  VAR 3: symbol byte of column c + 1
+  const V* tb;            // VAR 3: this lane's column of the warp's prior table
+  V pr[K];                // VAR 3: priors of column c
   bool first, row0_above, last;
   const V* carry_in;
   V* carry_out;
@@ -323,7 +349,7 @@ struct Sweeper {
 #pragma unroll
     for (int x = 0; x < P::NR; x++)
 #pragma unroll
-      for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = L.rbm[x][w] & hrep;
+      for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = (VAR == 3) ? 0u : (L.rbm[x][w] & hrep);
     V dM = dMp, dZ = dZp, upM = uM, upX = uX;
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -333,7 +359,11 @@ struct Sweeper {
       const uint32_t bit = 0xFu << (4 * (j % 8));
       V Mn, Yn, Zn;
       const V Xn = P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
-      if (VAR == 0) {
+      if (VAR == 3) {
+        Mn = P::mul(pr[j], P::fma(L.Am[j], dM, dZ));
+        Yn = P::fma(L.pXX[j], Yl[j], Ml[j]);
+        Zn = P::fma(L.pMY[j], Yn, P::mul(L.Ax[j], Xn));
+      } else if (VAR == 0) {
         const V A = P::sel(m2, bit, L.Am[j], L.Ax[j]);
         const V Gs = P::sel(m2, bit, L.Gm[j], L.Gx[j]);
         Mn = P::fma(A, dM, P::mul(Gs, dZ));
@@ -371,9 +401,20 @@ struct Sweeper {
 
   template <bool GUARD>
   __device__ __forceinline__ void step() {
-    const uint32_t hrep = hb * 0x11111111u;
-    hb = hap[min(c + 1, haplen + 1)];  // prefetch the next column's symbol
-    if (!GUARD || (unsigned)(c - 1) < (unsigned)haplen) cells(hrep);
+    if (VAR == 3) {
+      V prn[K];  // priors of column c + 1, in flight while column c is computed
+      const V* tn = tb + (size_t)(hb & 7u) * (K * 32);
+#pragma unroll
+      for (int j = 0; j < K; j++) prn[j] = tn[j * 32];
+      hb = hap[min(c + 2, haplen + 1)];
+      if (!GUARD || (unsigned)(c - 1) < (unsigned)haplen) cells(0u);
+#pragma unroll
+      for (int j = 0; j < K; j++) pr[j] = prn[j];
+    } else {
+      const uint32_t hrep = (hb >> 4) * 0x11111111u;
+      hb = hap[min(c + 1, haplen + 1)];  // prefetch the next column's symbol
+      if (!GUARD || (unsigned)(c - 1) < (unsigned)haplen) cells(hrep);
+    }
     dMp = uM;
     dZp = uZ;
     c++;
@@ -382,7 +423,8 @@ struct Sweeper {
 
   __device__ __forceinline__ V run(const uint8_t* hap_, int haplen_, int steady_end, int n_steps, int t,
                                    typename P::S initY, bool pass0, const V* carry_in_, V* carry_out_,
-                                   int carry_pitch_) {
+                                   int carry_pitch_, const V* tb_) {
+    tb = tb_;
     const V zero = P::splat(0);
     hap = hap_;
     haplen = haplen_;
@@ -393,7 +435,7 @@ struct Sweeper {
     carry_out = carry_out_;
     carry_pitch = carry_pitch_;
     const V initYv = P::splat(initY);
-    inj = (VAR == 2) ? P::mul(L.gTop, initYv) : initYv;
+    inj = (VAR >= 2) ? P::mul(L.gTop, initYv) : initYv;
 #pragma unroll
     for (int j = 0; j < K; j++) {
       Ml[j] = zero;
@@ -402,7 +444,7 @@ struct Sweeper {
       for (int x = 0; x < P::NR; x++)
         if (L.padmask[x] & (1u << j)) P::set(y0, x, initY);
       Yl[j] = y0;
-      Zl[j] = (VAR == 2) ? P::mul(L.pMY[j], y0) : y0;
+      Zl[j] = (VAR >= 2) ? P::mul(L.pMY[j], y0) : y0;
     }
     botX = zero;
     sum = zero;
@@ -423,6 +465,12 @@ struct Sweeper {
       }
     }
     hb = hap[max(c, -kHapLeftMargin + 1)];
+    if (VAR == 3) {
+      const V* t0 = tb + (size_t)(hb & 7u) * (K * 32);
+#pragma unroll
+      for (int j = 0; j < K; j++) pr[j] = t0[j * 32];
+      hb = hap[min(max(c + 1, -kHapLeftMargin + 1), haplen + 1)];
+    }
     fetch_up();
     int s = 1;
     const int pre_end = min(G - 1, n_steps);
@@ -438,9 +486,9 @@ template <class P, int G, int K, bool MULTI, int VAR>
 __device__ __forceinline__ typename P::V sweep(const LaneRows<P, K>& L, const uint8_t* hap, int haplen,
                                                int steady_end, int n_steps, int t, typename P::S initY, bool pass0,
                                                const typename P::V* carry_in, typename P::V* carry_out,
-                                               int carry_pitch) {
+                                               int carry_pitch, const typename P::V* tb = nullptr) {
   Sweeper<P, G, K, MULTI, VAR> sw(L);
-  return sw.run(hap, haplen, steady_end, n_steps, t, initY, pass0, carry_in, carry_out, carry_pitch);
+  return sw.run(hap, haplen, steady_end, n_steps, t, initY, pass0, carry_in, carry_out, carry_pitch, tb);
 }
 
 // Result of one pair (IntelPairHmm.cc:157-167).  Returns false when the pair must be rerun in fp64.
@@ -544,6 +592,9 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
                    : nullptr;
   const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
   const int rec0 = blk * RPW;
+  // VAR 3: the warp's prior table sits behind the record slot; lane-private column
+  V* tbv = reinterpret_cast<V*>(ctx.slot + ((RPW * rec_bytes + 127u) & ~127u)) + lane;
+  S* tbs = reinterpret_cast<S*>(tbv);
   // stage the block's packed records into this warp's slot
   __syncwarp();
   if (lane == 0) {
@@ -568,7 +619,7 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
 #pragma unroll
     for (int x = 0; x < P::NR; x++)
       load_lane_rows<P, K, VAR>(L, x, ctx.slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K,
-                                npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm));
+                                npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs);
   }
   for (int h = h_begin; h < h_end; h++) {
     const int haplen = ctx.hlen[h];
@@ -578,7 +629,7 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
     const int steady_end = haplen;
     V sum = P::splat(0);
     if (!MULTI) {
-      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
+      sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0, tbv);
     } else {
       V* cg = carry + (size_t)g * 6 * carry_pitch;  // two buffers of 3 lines, ping-pong
       for (int pass = 0; pass < p.cls.n_pass; pass++) {
@@ -586,11 +637,11 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
         for (int x = 0; x < P::NR; x++)
           load_lane_rows<P, K, VAR>(L, x, ctx.slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows,
                                     pass * cap + t * K, npad[x], t == 0 && pass == 0, ctx.ph2pr_s,
-                                    reinterpret_cast<const S*>(p.mm));
+                                    reinterpret_cast<const S*>(p.mm), tbs);
         V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
         V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
         sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
-                                        pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
+                                        pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch, tbv);
         __syncwarp();  // carry written by lane G-1 is read by lane 0 of the next pass
       }
     }
@@ -627,6 +678,8 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   const int carry_pitch = p.panel.max_hap_len + 2;
   V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) + ctx.warp_global * p.carry_stride_bytes)
                    : nullptr;
+  V* tbv = reinterpret_cast<V*>(ctx.slot) + lane;  // VAR 3: the slot holds only the prior table here
+  S* tbs = reinterpret_cast<S*>(tbv);
   const unsigned int item = wi * GPW + g;
   const bool valid = item < n_items;
   const uint2 it = valid ? p.list_items[item] : make_uint2(0u, 0u);
@@ -650,17 +703,17 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   V sum = P::splat(0);
   if (!MULTI) {
     load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
-                              reinterpret_cast<const S*>(p.mm));
-    sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0);
+                              reinterpret_cast<const S*>(p.mm), tbs);
+    sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0, tbv);
   } else {
     V* cg = carry + (size_t)g * 6 * carry_pitch;
     for (int pass = 0; pass < p.cls.n_pass; pass++) {
       load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, pass * cap + t * K, npad, t == 0 && pass == 0,
-                                ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm));
+                                ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs);
       V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
       V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
       sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
-                                      pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch);
+                                      pass + 1 < p.cls.n_pass ? cout : nullptr, carry_pitch, tbv);
       __syncwarp();
     }
   }
@@ -676,9 +729,8 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
 template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams p) {
   typedef typename P::S S;
-  constexpr int RPW = (32 / G) * P::NR;
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, (uint32_t)(RPW * 5 * p.cls.stride));
+  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, p.slot_bytes);
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
@@ -695,7 +747,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
   extern __shared__ __align__(128) uint8_t smem[];
   const unsigned int n_items = *p.list_count;
   if (n_items == 0) return;
-  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, 0);
+  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, p.slot_bytes);
   const unsigned int n_warp_items = (n_items + GPW - 1) / GPW;
   for (;;) {
     unsigned int wi = 0;
@@ -723,14 +775,17 @@ struct MegaParams {
   SweepParams cls[kMaxMegaClasses];
 };
 
+#ifndef GKLB_PRODUCT_VAR
+#define GKLB_PRODUCT_VAR 3
+#endif
 template <class P, int G, int K, bool MULTI>
 __device__ __noinline__ void mega_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
-  run_task<P, G, K, MULTI, 2>(p, task, ctx);
+  run_task<P, G, K, MULTI, GKLB_PRODUCT_VAR>(p, task, ctx);
 }
 template <class P, int G, int K, bool MULTI>
 __device__ __noinline__ void mega_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
                                        WarpCtx<typename P::S>& ctx) {
-  run_list_item<P, G, K, MULTI, 2>(p, wi, n_items, ctx);
+  run_list_item<P, G, K, MULTI, GKLB_PRODUCT_VAR>(p, wi, n_items, ctx);
 }
 
 #define GKLB_MEGA_DISPATCH(FN, ...)                                   \
@@ -771,7 +826,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_tasks(const __grid_const
 }
 
 template <class P, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_constant__ MegaParams m) {
+__global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_constant__ MegaParams m, uint32_t slot_bytes) {
   typedef typename P::S S;
   extern __shared__ __align__(128) uint8_t smem[];
   // warp-items per class follow from the list lengths the fp32 kernel left in device memory
@@ -783,7 +838,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_consta
     end[c] = total;
   }
   if (total == 0) return;
-  WarpCtx<S> ctx = setup_cta<S>(smem, m.cls[0].panel, m.cls[0].ph2pr, WARPS, 0);
+  WarpCtx<S> ctx = setup_cta<S>(smem, m.cls[0].panel, m.cls[0].ph2pr, WARPS, slot_bytes);
   for (;;) {
     unsigned int wi = 0;
     if (ctx.lane == 0) wi = atomicAdd(m.queue, 1u);

@@ -54,7 +54,7 @@ __global__ void k_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t
   const int32_t* hlen = hpos + n_haps;
   const int64_t o = hap_off[hap0 + i];
   uint8_t* dst = image + hpos[i] + 1;
-  for (int c = threadIdx.x; c < hlen[i]; c += blockDim.x) dst[c] = base_nibble(bases[o + c]);
+  for (int c = threadIdx.x; c < hlen[i]; c += blockDim.x) dst[c] = panel_byte(bases[o + c]);
 }
 
 cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,
@@ -71,23 +71,22 @@ cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_
 #define E_D1(G, K, W, M, V) {POL_D1, G, K, W, M, V, 1, GKLB_TASKS(VD1, G, K, W, M, V), GKLB_LIST(VD1, G, K, W, M, V)}
 
 static const KernelEntry g_table[] = {
-    // ---- product: packed fp32, folded form (VAR 2) ----
-    E_F2(8, 4, 8, false, 2),  E_F2(8, 5, 8, false, 2),  E_F2(8, 6, 8, false, 2),  E_F2(8, 7, 8, false, 2),
-    E_F2(8, 8, 8, false, 2),  E_F2(16, 5, 8, false, 2), E_F2(16, 6, 8, false, 2), E_F2(16, 7, 8, false, 2),
-    E_F2(16, 8, 8, false, 2), E_F2(32, 5, 8, false, 2), E_F2(32, 6, 8, false, 2), E_F2(32, 7, 8, false, 2),
-    E_F2(32, 8, 8, false, 2), E_F2(32, 8, 8, true, 2),
+    // ---- product: packed fp32, folded recurrence with the shared-memory prior table (VAR 3) ----
+    E_F2(8, 4, 8, false, 3),  E_F2(8, 5, 8, false, 3),  E_F2(8, 6, 8, false, 3),  E_F2(8, 7, 8, false, 3),
+    E_F2(8, 8, 8, false, 3),  E_F2(16, 5, 8, false, 3), E_F2(16, 6, 8, false, 3), E_F2(16, 7, 8, false, 3),
+    E_F2(16, 8, 8, false, 3), E_F2(32, 5, 8, false, 3), E_F2(32, 6, 8, false, 3), E_F2(32, 7, 8, false, 3),
+    E_F2(32, 8, 8, false, 3), E_F2(32, 8, 8, true, 3),
     // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
-    E_D1(8, 4, 8, false, 2),  E_D1(8, 5, 8, false, 2),  E_D1(8, 6, 8, false, 2),  E_D1(8, 7, 8, false, 2),
-    E_D1(8, 8, 8, false, 2),  E_D1(16, 5, 8, false, 2), E_D1(16, 6, 8, false, 2), E_D1(16, 7, 8, false, 2),
-    E_D1(16, 8, 8, false, 2), E_D1(32, 5, 8, false, 2), E_D1(32, 6, 8, false, 2), E_D1(32, 7, 8, false, 2),
-    E_D1(32, 8, 8, false, 2), E_D1(32, 8, 8, true, 2),
+    E_D1(8, 4, 8, false, 3),  E_D1(8, 5, 8, false, 3),  E_D1(8, 6, 8, false, 3),  E_D1(8, 7, 8, false, 3),
+    E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 8, false, 3), E_D1(16, 6, 8, false, 3), E_D1(16, 7, 8, false, 3),
+    E_D1(16, 8, 8, false, 3), E_D1(32, 5, 8, false, 3), E_D1(32, 6, 8, false, 3), E_D1(32, 7, 8, false, 3),
+    E_D1(32, 8, 8, false, 3), E_D1(32, 8, 8, true, 3),
 #ifdef GKLB_EXPERIMENTAL
     // ---- measurement only ----
-    E_F2(16, 7, 8, false, 0), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 12, false, 2), E_F2(16, 7, 10, false, 2),
-    E_F2(32, 4, 8, false, 2), E_F2(32, 4, 12, false, 2), E_F2(32, 4, 16, false, 2),
-    E_F1(8, 13, 8, false, 2), E_F1(8, 13, 8, false, 1), E_F1(8, 13, 12, false, 2), E_F1(16, 7, 12, false, 2),
-    E_F1(16, 7, 16, false, 2), E_F1(16, 7, 16, false, 1), E_F1(32, 4, 16, false, 2),
-    E_D1(8, 13, 8, false, 2), E_D1(32, 4, 8, false, 2),
+    E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0), E_F2(16, 7, 10, false, 3),
+    E_F2(16, 7, 12, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 3), E_F2(32, 4, 16, false, 3),
+    E_F1(8, 13, 8, false, 3), E_F1(8, 13, 8, false, 2), E_F1(8, 13, 12, false, 3), E_F1(16, 7, 16, false, 3),
+    E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3),
 #endif
 };
 
@@ -116,7 +115,7 @@ const void* mega_kernel(int policy, int list_mode) {
 cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes, int list_mode, int grid, int threads,
                         size_t smem, cudaStream_t s) {
   void* args_tasks[] = {const_cast<MegaParams*>(&m), &slot_bytes};
-  void* args_list[] = {const_cast<MegaParams*>(&m)};
+  void* args_list[] = {const_cast<MegaParams*>(&m), &slot_bytes};
   return cudaLaunchKernel(fn, dim3(grid), dim3(threads), list_mode ? args_list : args_tasks, smem, s);
 }
 
