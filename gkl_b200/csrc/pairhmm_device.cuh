@@ -225,10 +225,15 @@ struct LaneRows {
   //                        takes one multiply out of the Y update and one out of the M update
   // VAR 3 (table):         as VAR 2, but the prior (1-e | e/3) of every (row, haplotype symbol) sits in a per-warp
   //                        shared-memory table and arrives by LDS: no LOP3/FSEL and no Gm/Gx registers
+  // VAR 4 (fp32 only):     as VAR 3, and the X state is kept as W = X / pMX(row): W = M(up) + kappa * W(up) with
+  //                        kappa = pXX * pMX(row-1) / pMX(row) in pMX[], Ax = pGAPM(next row) * pMX(row); the final
+  //                        sum is sumM + pMX(last row) * sumW.  One FMUL less per cell.  W can overflow fp32 for
+  //                        adversarial gap-open patterns: a non-finite sum sends the pair to the fp64 rerun.
   typename P::V Am[K], Ax[K], Gm[K], Gx[K];
   typename P::V pMX[K], pXX[K], pMY[K];      // pYY == pXX (both ph2pr[gcp], avx-pairhmm-template.h:142-146)
   typename P::V pXXtop;                      // pXX[0] as used by the X update (zeroed on the first lane of pass 0)
-  typename P::V gTop;                        // VAR 2: pGAPM of the lane's first row (0 if it is padding)
+  typename P::V gTop;                        // VAR >= 2: pGAPM of the lane's first row (0 if it is padding)
+  typename P::V xlast;                       // VAR 4: pMX of the lane's last row (scales sumW on the last lane)
   uint32_t rbm[P::NR][(K + 7) / 8];          // read-base one-hot nibbles, row j at bits 4*(j%8) of word j/8
   uint32_t padmask[P::NR];                   // bit j set: row j is a top-padding row
 };
@@ -265,7 +270,7 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
     else { am = pmm; ax = pgap; gm = om; gx = th; }
     S mx = ph2pr[ig], my = ph2pr[dg], xx = pc;
     if (pad) { am = ax = gm = gx = (S)0; mx = my = (S)0; xx = (S)1; pm |= 1u << j; }
-    if (VAR == 3) {
+    if (VAR >= 3) {
       // prior table: tbl is this lane's column; entry (symbol, row j) of read x at ((symbol * K + j) * 32) * NR + x
       const uint32_t symnib[kPriorSyms] = {1u, 2u, 4u, 8u, 15u};
 #pragma unroll
@@ -279,6 +284,15 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
       ax = gnext;
       my = (pad ? (S)1 : my) * gnext;
       if (j == 0) P::set(L.gTop, x, pad ? (S)0 : pgap);
+    }
+    if (VAR == 4) {
+      // W = X / pMX(row):  W = M(up) + kappa * W(up);  the row above a first real row has X = 0 (kappa = 0)
+      const S pmx = ph2pr[ig];
+      S kappa = (S)0;
+      if (!pad && row - 1 >= n_pad) kappa = pc * ph2pr[rec[2 * stride + row - 1]] / pmx;
+      ax = pad ? (S)0 : ax * pmx;   // pGAPM(next) * pMX(row) multiplies W in the diagonal state
+      mx = kappa;
+      if (j == K - 1) P::set(L.xlast, x, pad ? (S)0 : pmx);
     }
     S xxtop = xx;
     if (j == 0 && top_is_row0) {  // row 0 above: M = X = 0, so the M-diagonal and X inputs are killed
@@ -313,7 +327,7 @@ struct Sweeper {
   typedef typename P::V V;
   const LaneRows<P, K>& L;
   V Ml[K], Yl[K], Zl[K];  // previous column: M, Y (VAR 2: Y / pMY), X+Y (VAR 2: pGAPM_next * (X+Y))
-  V botX, sum;
+  V botX, sum, sumW;
   V uM, uX, uZ;           // bottom row of the lane above at this step's column
   V dMp, dZp;             // ... and at the previous column
   V inj;                  // what row 0 feeds the first row's M update
@@ -333,7 +347,10 @@ struct Sweeper {
     uM = P::shfl_up(Ml[K - 1], G);
     uX = P::shfl_up(botX, G);
     uZ = P::shfl_up(Zl[K - 1], G);
-    if (row0_above) uZ = inj;  // row 0: M = X = 0 (killed by the zeroed top constants), Y = init
+    if (row0_above) {  // row 0: M = X = 0 (killed by the zeroed top constants), Y = init
+      uZ = inj;
+      if (VAR == 4) uM = P::splat(0);  // the W update adds M(up) without a coefficient
+    }
     if (MULTI) {
       if (first && carry_in != nullptr) {
         const int cc = min(max(c, 0), haplen + 1);
@@ -349,7 +366,7 @@ struct Sweeper {
 #pragma unroll
     for (int x = 0; x < P::NR; x++)
 #pragma unroll
-      for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = (VAR == 3) ? 0u : (L.rbm[x][w] & hrep);
+      for (int w = 0; w < (K + 7) / 8; w++) mw[x][w] = (VAR >= 3) ? 0u : (L.rbm[x][w] & hrep);
     V dM = dMp, dZ = dZp, upM = uM, upX = uX;
 #pragma unroll
     for (int j = 0; j < K; j++) {
@@ -358,8 +375,9 @@ struct Sweeper {
       for (int x = 0; x < P::NR; x++) m2[x] = mw[x][j / 8];
       const uint32_t bit = 0xFu << (4 * (j % 8));
       V Mn, Yn, Zn;
-      const V Xn = P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
-      if (VAR == 3) {
+      const V Xn = (VAR == 4) ? P::fma(L.pMX[j], upX, upM)  // W form: kappa * W(up) + M(up)
+                              : P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
+      if (VAR >= 3) {
         Mn = P::mul(pr[j], P::fma(L.Am[j], dM, dZ));
         Yn = P::fma(L.pXX[j], Yl[j], Ml[j]);
         Zn = P::fma(L.pMY[j], Yn, P::mul(L.Ax[j], Xn));
@@ -389,7 +407,12 @@ struct Sweeper {
       upX = Xn;
     }
     botX = upX;
-    sum = P::add(sum, P::add(upM, upX));
+    if (VAR == 4) {
+      sum = P::add(sum, upM);
+      sumW = P::add(sumW, upX);
+    } else {
+      sum = P::add(sum, P::add(upM, upX));
+    }
     if (MULTI) {
       if (carry_out != nullptr && last) {
         carry_out[c] = upM;
@@ -401,7 +424,7 @@ struct Sweeper {
 
   template <bool GUARD>
   __device__ __forceinline__ void step() {
-    if (VAR == 3) {
+    if (VAR >= 3) {
       V prn[K];  // priors of column c + 1, in flight while column c is computed
       const V* tn = tb + (size_t)(hb & 7u) * (K * 32);
 #pragma unroll
@@ -448,6 +471,7 @@ struct Sweeper {
     }
     botX = zero;
     sum = zero;
+    sumW = zero;
     // column 0 of the row above the lane's first row: row 0 (M = 0, Y = init) for the first lane
     // of pass 0, the previous pass's bottom row for the first lane of later passes
     dMp = zero;
@@ -465,7 +489,7 @@ struct Sweeper {
       }
     }
     hb = hap[max(c, -kHapLeftMargin + 1)];
-    if (VAR == 3) {
+    if (VAR >= 3) {
       const V* t0 = tb + (size_t)(hb & 7u) * (K * 32);
 #pragma unroll
       for (int j = 0; j < K; j++) pr[j] = t0[j * 32];
@@ -478,7 +502,7 @@ struct Sweeper {
 #pragma unroll 2
     for (; s <= steady_end; s++) step<false>();
     for (; s <= n_steps; s++) step<true>();
-    return sum;
+    return (VAR == 4) ? P::fma(L.xlast, sumW, sum) : sum;
   }
 };
 
@@ -498,7 +522,8 @@ __device__ __forceinline__ bool finish_pair(typename P::S sum, double log10_init
     *out = log10((double)sum) - log10_init;
     return true;
   } else {
-    if ((float)sum < kMinAccepted) return false;
+    // below GKL's threshold -> fp64 rerun; so does a non-finite sum (the W form of VAR 4 can overflow)
+    if (!((float)sum >= kMinAccepted) || (float)sum > 3.0e38f) return false;
     // log10f(result_float) - log10f(2^120), evaluated in float, widened
     const float lg = (float)log10((double)sum);
     *out = (double)(lg - (float)log10_init);
@@ -775,17 +800,16 @@ struct MegaParams {
   SweepParams cls[kMaxMegaClasses];
 };
 
-#ifndef GKLB_PRODUCT_VAR
-#define GKLB_PRODUCT_VAR 3
-#endif
+// product variants: fp32 uses the W form (VAR 4), fp64 must not (2^1020 leaves no headroom for X / pMX)
+template <class P> struct ProductVar { static constexpr int value = P::kDouble ? 3 : 4; };
 template <class P, int G, int K, bool MULTI>
 __device__ __noinline__ void mega_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
-  run_task<P, G, K, MULTI, GKLB_PRODUCT_VAR>(p, task, ctx);
+  run_task<P, G, K, MULTI, ProductVar<P>::value>(p, task, ctx);
 }
 template <class P, int G, int K, bool MULTI>
 __device__ __noinline__ void mega_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
                                        WarpCtx<typename P::S>& ctx) {
-  run_list_item<P, G, K, MULTI, GKLB_PRODUCT_VAR>(p, wi, n_items, ctx);
+  run_list_item<P, G, K, MULTI, ProductVar<P>::value>(p, wi, n_items, ctx);
 }
 
 #define GKLB_MEGA_DISPATCH(FN, ...)                                   \

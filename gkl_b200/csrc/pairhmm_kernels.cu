@@ -72,10 +72,10 @@ cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_
 
 static const KernelEntry g_table[] = {
     // ---- product: packed fp32, folded recurrence with the shared-memory prior table (VAR 3) ----
-    E_F2(8, 4, 8, false, 3),  E_F2(8, 5, 8, false, 3),  E_F2(8, 6, 8, false, 3),  E_F2(8, 7, 8, false, 3),
-    E_F2(8, 8, 8, false, 3),  E_F2(16, 5, 8, false, 3), E_F2(16, 6, 8, false, 3), E_F2(16, 7, 8, false, 3),
-    E_F2(16, 8, 8, false, 3), E_F2(32, 5, 8, false, 3), E_F2(32, 6, 8, false, 3), E_F2(32, 7, 8, false, 3),
-    E_F2(32, 8, 8, false, 3), E_F2(32, 8, 8, true, 3),
+    E_F2(8, 4, 8, false, 4),  E_F2(8, 5, 8, false, 4),  E_F2(8, 6, 8, false, 4),  E_F2(8, 7, 8, false, 4),
+    E_F2(8, 8, 8, false, 4),  E_F2(16, 5, 8, false, 4), E_F2(16, 6, 8, false, 4), E_F2(16, 7, 8, false, 4),
+    E_F2(16, 8, 8, false, 4), E_F2(32, 5, 8, false, 4), E_F2(32, 6, 8, false, 4), E_F2(32, 7, 8, false, 4),
+    E_F2(32, 8, 8, false, 4), E_F2(32, 8, 8, true, 4),
     // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
     E_D1(8, 4, 8, false, 3),  E_D1(8, 5, 8, false, 3),  E_D1(8, 6, 8, false, 3),  E_D1(8, 7, 8, false, 3),
     E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 8, false, 3), E_D1(16, 6, 8, false, 3), E_D1(16, 7, 8, false, 3),
@@ -83,9 +83,9 @@ static const KernelEntry g_table[] = {
     E_D1(32, 8, 8, false, 3), E_D1(32, 8, 8, true, 3),
 #ifdef GKLB_EXPERIMENTAL
     // ---- measurement only ----
-    E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0), E_F2(16, 7, 10, false, 3),
-    E_F2(16, 7, 12, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 3), E_F2(32, 4, 16, false, 3),
-    E_F1(8, 13, 8, false, 3), E_F1(8, 13, 8, false, 2), E_F1(8, 13, 12, false, 3), E_F1(16, 7, 16, false, 3),
+    E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0),
+    E_F2(16, 7, 10, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 4), E_F2(32, 4, 16, false, 4),
+    E_F1(8, 13, 8, false, 4), E_F1(8, 13, 8, false, 3), E_F1(8, 13, 12, false, 4), E_F1(16, 7, 16, false, 4),
     E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3),
 #endif
 };

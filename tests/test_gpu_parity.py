@@ -121,6 +121,35 @@ def test_every_length_class_boundary(eng):
     assert rel(out, ref).max() <= REL_TOL
 
 
+def test_adversarial_gap_open_patterns_stay_within_tolerance(eng):
+    """The fp32 kernel keeps the insertion state as X / pMX(row); alternating gap-open penalties of 0 and 127 with a
+    zero gap-continuation penalty push that ratio past the fp32 range.  Such pairs must be caught (non-finite sum)
+    and recomputed by the fp64 kernel, so the results still match the reference."""
+    rng = np.random.default_rng(3)
+    hap = synth.ACGT[rng.integers(0, 4, size=260)]
+    reads, quals, ins, dele, gcp = [], [], [], [], []
+    for k in range(24):
+        L = int(rng.integers(60, 200))
+        s = int(rng.integers(0, 260 - 60))
+        r = hap[s:s + L]
+        if len(r) < L:
+            r = np.concatenate([r, synth.ACGT[rng.integers(0, 4, size=L - len(r))]])
+        reads.append(bytes(r))
+        quals.append(bytes(rng.integers(20, 41, size=L).astype(np.uint8)))
+        pat = np.where(np.arange(L) % 2 == (k % 2), 0, 127).astype(np.uint8)
+        if k % 3 == 0:
+            pat = np.where(np.arange(L) < L // 2, 127, 0).astype(np.uint8)
+        ins.append(bytes(pat))
+        dele.append(bytes(rng.integers(0, 128, size=L).astype(np.uint8)))
+        gcp.append(bytes(np.zeros(L, dtype=np.uint8) if k % 2 else rng.integers(0, 12, size=L).astype(np.uint8)))
+    b = fixtures.PairHmmBatch.from_lists(reads, quals, ins, dele, gcp, [bytes(hap), bytes(hap[:130]), bytes(hap[70:])])
+    out = eng.compute(b)
+    ref = checker(b)
+    ok = np.isfinite(ref)
+    assert np.all(np.isfinite(out[ok]))
+    assert rel(out[ok], ref[ok]).max() <= REL_TOL
+
+
 def test_haplotype_panel_larger_than_shared_memory_is_tiled(eng):
     b = synth.random_batch(51, 24, 800, read_len=(60, 120), hap_len=(250, 450))
     assert rel(eng.compute(b), checker(b)).max() <= REL_TOL
