@@ -53,7 +53,8 @@ struct PdhmmParams {
 
 __device__ __forceinline__ double shfl_up_d(double v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
 
-// Smem per group: y[c], info[c], allele[c] for c in [-kPdMargin, max_hap + kPdMargin)
+// Smem per group: y[c], info[c], allele[c] (bytes) and nspec[c] (uint16: first column >= c that needs the state
+// machine) for c in [-kPdMargin, max_hap + kPdMargin): 5 bytes per column
 template <int G, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
   constexpr int GPW = 32 / G;
@@ -61,11 +62,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = lane % G, g = lane / G;
-  const int col_pitch = p.max_hap + 2 * kPdMargin;
-  uint8_t* gs = smem + (size_t)(warp * GPW + g) * 3 * col_pitch;
+  const int col_pitch = (p.max_hap + 2 * kPdMargin + 1) & ~1;  // even: the uint16 prefix array follows three byte arrays
+  uint8_t* gs = smem + (size_t)(warp * GPW + g) * 5 * col_pitch;
   uint8_t* ys = gs + kPdMargin;                  // haplotype byte of column c at ys[c] (c = 1..H)
   uint8_t* infos = gs + col_pitch + kPdMargin;   // state bits + DEL_END
   uint8_t* alleles = gs + 2 * col_pitch + kPdMargin;
+  uint16_t* nspec = reinterpret_cast<uint16_t*>(gs + 3 * col_pitch) + kPdMargin;  // col_pitch is even
   const int carry_pitch = p.max_hap + 2;
   double* carry_g = p.carry + ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride + (size_t)g * 12 * carry_pitch;
   const unsigned long long n_warp_items = ((unsigned long long)p.n + GPW - 1) / GPW;
@@ -116,6 +118,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
         if (f & 4) s0 = s1 = s2 = 2;
       }
       end_state = s0 | (s1 << 2) | (s2 << 4);
+      // which row-start states can occur at all: NORMAL, then the end state of the previous row, ...
+      int reach = 1, st = 0;
+      if (p.carry_state)
+        for (int r = 0; r < 3; r++) { st = (end_state >> (2 * st)) & 3; reach |= 1 << st; }
+      const uint32_t rmask = ((reach & 1) ? 0x03u : 0u) | ((reach & 2) ? 0x0Cu : 0u) | ((reach & 4) ? 0x30u : 0u) | 0x40u;
+      // a column is "plain" when every reachable start state sees it NORMAL and it does not close a deletion;
+      // nspec[c] = the first column >= c that is not plain (0xFFFF if none)
+      uint32_t nxt = 0xFFFFu;
+      for (int c = p.max_hap + kPdMargin - 1; c >= -kPdMargin; c--) {
+        if (c >= 1 && c <= H && (infos[c] & rmask)) nxt = (uint32_t)c;
+        nspec[c] = (uint16_t)nxt;
+      }
     }
     end_state = __shfl_sync(0xffffffffu, end_state, g * G);
     __syncwarp();
@@ -198,10 +212,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
         cout[2 * carry_pitch] = D[K - 1];  // column 0 of a padding bottom row is init, of a real row 0
       }
       int c = 1 - t;
-      for (int s = 1; s <= n_steps; s++, c++) {
-        // bottom row of the lane above at column c (it computed it one step ago)
-        double uM = shfl_up_d(M[K - 1], G), uI = shfl_up_d(I[K - 1], G), uD = shfl_up_d(D[K - 1], G);
-        double ubM = shfl_up_d(bM[K - 1], G), ubI = shfl_up_d(bI[K - 1], G), ubD = shfl_up_d(bD[K - 1], G);
+      // values of the lane above at this step's column (shuffled at the end of the previous step)
+      double uM, uI, uD, ubM = 0.0, ubI = 0.0, ubD = 0.0;
+      auto fetch = [&](bool with_branch) {
+        uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
+        if (with_branch) { ubM = shfl_up_d(bM[K - 1], G); ubI = shfl_up_d(bI[K - 1], G); ubD = shfl_up_d(bD[K - 1], G); }
         if (first) {
           if (pass == 0) { uM = uI = ubM = ubI = ubD = 0.0; uD = init; }  // row 0: D = init, everything else 0
           else if (live) {
@@ -210,10 +225,74 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
             ubM = cin[3 * carry_pitch + cc]; ubI = cin[4 * carry_pitch + cc]; ubD = cin[5 * carry_pitch + cc];
           }
         }
+      };
+      auto finish_step = [&]() {
+        if (pass == n_pass - 1) sum += M[K - 1] + I[K - 1];
+        if (write_carry) {
+          cout[c] = M[K - 1]; cout[carry_pitch + c] = I[K - 1]; cout[2 * carry_pitch + c] = D[K - 1];
+          cout[3 * carry_pitch + c] = bM[K - 1]; cout[4 * carry_pitch + c] = bI[K - 1];
+          cout[5 * carry_pitch + c] = bD[K - 1];
+        }
+      };
+      fetch(true);
+      int s = 1;
+      while (s <= n_steps) {
+        // Lane 0 is at column s, lane G-1 at s-G+1.  Steps are "fast" while none of the columns the warp touches,
+        // nor the one lane 0 reaches next, needs the state machine: the window [s-G, s+1] holds no special column.
+        // (Warp-uniform only when the warp carries one pair, i.e. G = 32.)
+        int n_fast = 0;
+        if (G == 32) {
+          const int first_special = nspec[max(s - G, -kPdMargin)];
+          n_fast = min(first_special - (s + 1), n_steps - s + 1);
+        }
+        if (n_fast > 0) {
+          // ---- fast steps: M/I/D only, the branch twins simply trail by one column ----
+#pragma unroll 2
+          for (int k = 0; k < n_fast; k++) {
+            if (live && (unsigned)(c - 1) < (unsigned)H) {
+              const uint32_t y = ys[c], al = alleles[c];
+              double tM = uM, tI = uI;
+              double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const double lM = M[j], lI = I[j], lD = D[j];
+                const bool match = (xb[j] == y) || (xb[j] == 'N') || (y == 'N') || ((xbit[j] & al) != 0);
+                const double prior = match ? pMa[j] : pMi[j];
+                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+                const double nD = lM * tMD[j] + lD * tII[j];
+                const double nI = tM * tMI[j] + tI * tII[j];
+                dM = lM; dI = lI; dD = lD;
+                bM[j] = lM; bI[j] = lI; bD[j] = lD;
+                M[j] = nM; I[j] = nI; D[j] = nD;
+                tM = nM; tI = nI;
+              }
+              finish_step();
+            }
+            gM = uM; gI = uI; gD = uD;
+            c++;
+            fetch(false);
+          }
+          s += n_fast;
+          // the branch twins of the lane above were not exchanged during the fast steps; the next (slow) step
+          // needs them as its top values -- its diagonal twins are only read on special columns, which by
+          // construction of the window are at least one slow step away
+          ubM = shfl_up_d(bM[K - 1], G); ubI = shfl_up_d(bI[K - 1], G); ubD = shfl_up_d(bD[K - 1], G);
+          if (first) {
+            if (pass == 0) { ubM = ubI = ubD = 0.0; }
+            else if (live) {
+              const int cc = min(max(c, 0), H + 1);
+              ubM = cin[3 * carry_pitch + cc]; ubI = cin[4 * carry_pitch + cc]; ubD = cin[5 * carry_pitch + cc];
+            }
+          }
+          gbM = gbI = gbD = 0.0;
+          continue;
+        }
+        // ---- one slow step: the full state machine ----
         if (live && (unsigned)(c - 1) < (unsigned)H) {
-          const uint32_t y = ys[c], info = infos[c], al = alleles[c];
+          const uint32_t y = ys[c], al = alleles[c];
+          const uint32_t info = infos[c];
           const bool del_end = (info & 0x40) != 0;
-          double tM = uM, tI = uI, tD = uD, tbM = ubM, tbI = ubI, tbD = ubD;          // top of row j
+          double tM = uM, tI = uI, tbM = ubM, tbI = ubI;                               // top of row j
           double dM = gM, dI = gI, dD = gD, dbM = gbM, dbI = gbI, dbD = gbD;          // diagonal of row j
 #pragma unroll
           for (int j = 0; j < K; j++) {
@@ -236,17 +315,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
             // the next row's diagonal is this row's previous column, its top this row's new column
             dM = M[j]; dI = I[j]; dD = D[j]; dbM = lbM; dbI = lbI; dbD = lbD;
             M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
-            tM = nM; tI = nI; tD = nD; tbM = nbM; tbI = nbI; tbD = nbD;
+            tM = nM; tI = nI; tbM = nbM; tbI = nbI;
           }
-          (void)tD; (void)tbD;
-          if (pass == n_pass - 1) sum += M[K - 1] + I[K - 1];
-          if (write_carry) {
-            cout[c] = M[K - 1]; cout[carry_pitch + c] = I[K - 1]; cout[2 * carry_pitch + c] = D[K - 1];
-            cout[3 * carry_pitch + c] = bM[K - 1]; cout[4 * carry_pitch + c] = bI[K - 1];
-            cout[5 * carry_pitch + c] = bD[K - 1];
-          }
+          finish_step();
         }
         gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
+        c++;
+        s++;
+        fetch(true);
       }
       __syncwarp();
     }

@@ -147,8 +147,8 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   else for (long long k = 0; k < n; k++) cells += b->hap_lengths[k] * b->read_lengths[k];
 
   constexpr int gpw = 32 / kG;
-  const size_t col_pitch = (size_t)b->max_hap + 2 * kPdMargin;
-  const size_t smem = (size_t)kWarps * gpw * 3 * col_pitch;
+  const size_t col_pitch = ((size_t)b->max_hap + 2 * kPdMargin + 1) & ~(size_t)1;
+  const size_t smem = (size_t)kWarps * gpw * 5 * col_pitch;
   if (smem > (size_t)kSmemMax)
     return gklb_internal_fail(GKLB_ERR_INVALID, "maxHapLength %d does not fit in shared memory", b->max_hap);
 
