@@ -17,6 +17,7 @@
 
 #include <algorithm>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -173,7 +174,8 @@ struct gklb_engine {
 namespace {
 
 std::mutex g_mu;
-gklb_engine* g_engine = nullptr;
+std::vector<gklb_engine*> g_engines;   // one per device in use (GKLB_DEVICES); [0] serves small batches alone
+gklb_pairhmm_stats g_last_stats{};
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 int class_cfg(const ClassInst& c);
@@ -555,7 +557,13 @@ void fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kernel
   const int slots = e->num_sms * k->warps;
   if (!list_mode) {
     const int n_blocks = c.n_rec / rpw;
-    long long chunk = ((long long)n_blocks * t.n) / (12LL * slots);
+    // aim at ~tasks_per_warp tasks per resident warp: enough for the dynamic queue to balance the tail, few
+    // enough that the per-task constant set-up stays negligible (GKLB_TASKS_PER_WARP overrides, for measurement)
+    static const long long tasks_per_warp = [] {
+      const char* v = getenv("GKLB_TASKS_PER_WARP");
+      return (long long)(v && atoi(v) > 0 ? atoi(v) : 32);
+    }();
+    long long chunk = ((long long)n_blocks * t.n) / (tasks_per_warp * slots);
     chunk = std::max(1LL, std::min(chunk, 32LL));
     if (c.multi) chunk = 1;
     chunk = std::min<long long>(chunk, t.n);
@@ -768,20 +776,140 @@ extern "C" {
 int gklb_pairhmm_init(int use_double, int max_threads) {
   (void)max_threads;  // GKL's non-OpenMP library ignores it as well (IntelPairHmm.cc:85-89)
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_engine) { destroy_engine(g_engine); g_engine = nullptr; }
-  const char* dev = getenv("GKLB_DEVICE");
-  return create_engine(&g_engine, dev ? atoi(dev) : 0, use_double);
+  for (auto* e : g_engines) destroy_engine(e);
+  g_engines.clear();
+  // GKLB_DEVICES = "all" | "0,1,2,..." : shard large batches over several GPUs inside this process
+  // (the JVM is one process); GKLB_DEVICE = n : a single device (default 0)
+  std::vector<int> devices;
+  const char* many = getenv("GKLB_DEVICES");
+  if (many && *many) {
+    if (!strcmp(many, "all")) {
+      int n = 0;
+      cudaGetDeviceCount(&n);
+      for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) devices.push_back(i);
+      }
+    } else {
+      for (const char* q = many; *q;) {
+        devices.push_back(atoi(q));
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+    }
+  }
+  if (devices.empty()) {
+    const char* dev = getenv("GKLB_DEVICE");
+    devices.push_back(dev ? atoi(dev) : 0);
+  }
+  for (int d : devices) {
+    gklb_engine* e = nullptr;
+    const int rc = create_engine(&e, d, use_double);
+    if (rc) {
+      for (auto* x : g_engines) destroy_engine(x);
+      g_engines.clear();
+      return rc;
+    }
+    g_engines.push_back(e);
+  }
+  return GKLB_OK;
 }
+
+// Batches below this many cells are not worth splitting: one GPU finishes them in well under a millisecond.
+static const long long kMinCellsPerDevice = 4000000000LL;
 
 int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_engine) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
-  return do_compute(g_engine, batch, likelihoods);
+  if (g_engines.empty()) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
+  int rc = validate(batch);
+  if (rc) return rc;
+  int n_dev = (int)g_engines.size();
+  if (batch->n_reads > 0 && batch->n_haps > 0) {
+    const long long cells = (long long)batch->read_off[batch->n_reads] * (long long)batch->hap_off[batch->n_haps];
+    n_dev = (int)std::max(1LL, std::min<long long>(n_dev, cells / kMinCellsPerDevice));
+    n_dev = std::min(n_dev, batch->n_reads);
+  } else {
+    n_dev = 1;
+  }
+  if (n_dev <= 1) {
+    rc = do_compute(g_engines[0], batch, likelihoods);
+    g_last_stats = g_engines[0]->stats;
+    return rc;
+  }
+  // Reads are sharded into contiguous ranges balanced by total length (every read meets every haplotype, so
+  // cells are proportional to read length); range g gets a contiguous slab of the read-major output
+  // (JavaData.h:94-105).  Each device copies its shard and the panel over its own PCIe link and writes its slab
+  // straight into the caller's array: the shards never need to meet on one GPU.
+  const int64_t total = batch->read_off[batch->n_reads];
+  std::vector<int> cut(n_dev + 1, 0);
+  {
+    int r = 0;
+    for (int g = 1; g < n_dev; g++) {
+      const int64_t target = total * g / n_dev;
+      while (r < batch->n_reads && batch->read_off[r] < target) r++;
+      cut[g] = std::max(r, cut[g - 1]);
+    }
+    cut[n_dev] = batch->n_reads;
+  }
+  std::vector<std::vector<int64_t>> offs(n_dev);
+  std::vector<gklb_pairhmm_batch> sub(n_dev);
+  std::vector<int> rcs(n_dev, GKLB_OK);
+  std::vector<std::string> errs(n_dev);
+  std::vector<std::thread> th;
+  for (int g = 0; g < n_dev; g++) {
+    const int lo = cut[g], hi = cut[g + 1];
+    const int64_t base = batch->read_off[lo];
+    offs[g].resize((size_t)(hi - lo) + 1);
+    for (int r = lo; r <= hi; r++) offs[g][r - lo] = batch->read_off[r] - base;
+    sub[g] = *batch;
+    sub[g].n_reads = hi - lo;
+    sub[g].read_off = offs[g].data();
+    sub[g].read_bases = batch->read_bases + base;
+    sub[g].read_quals = batch->read_quals + base;
+    sub[g].ins_gop = batch->ins_gop + base;
+    sub[g].del_gop = batch->del_gop + base;
+    sub[g].gcp = batch->gcp + base;
+  }
+  for (int g = 0; g < n_dev; g++) {
+    th.emplace_back([&, g] {
+      if (sub[g].n_reads == 0) return;
+      rcs[g] = do_compute(g_engines[g], &sub[g], likelihoods + (size_t)cut[g] * batch->n_haps);
+      if (rcs[g]) errs[g] = t_last_error;  // last error is thread-local: carry it to the caller's thread
+    });
+  }
+  for (auto& t : th) t.join();
+  g_last_stats = gklb_pairhmm_stats{};
+  for (int g = 0; g < n_dev; g++) {
+    if (rcs[g]) { t_last_error = errs[g]; return rcs[g]; }
+    const gklb_pairhmm_stats& st = g_engines[g]->stats;
+    g_last_stats.pairs += st.pairs;
+    g_last_stats.cells += st.cells;
+    g_last_stats.fallback_pairs += st.fallback_pairs;
+    g_last_stats.kernel_launches += st.kernel_launches;
+    g_last_stats.n_classes = std::max(g_last_stats.n_classes, st.n_classes);
+    g_last_stats.h2d_ms = std::max(g_last_stats.h2d_ms, st.h2d_ms);
+    g_last_stats.kernel_ms = std::max(g_last_stats.kernel_ms, st.kernel_ms);
+    g_last_stats.d2h_ms = std::max(g_last_stats.d2h_ms, st.d2h_ms);
+  }
+  return GKLB_OK;
 }
 
 int gklb_pairhmm_done(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_engine) { destroy_engine(g_engine); g_engine = nullptr; }
+  for (auto* e : g_engines) destroy_engine(e);
+  g_engines.clear();
+  return GKLB_OK;
+}
+
+int gklb_pairhmm_devices_in_use(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return (int)g_engines.size();
+}
+
+int gklb_pairhmm_last_stats(gklb_pairhmm_stats* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out) return fail(GKLB_ERR_INVALID, "out is null");
+  *out = g_last_stats;
   return GKLB_OK;
 }
 

@@ -40,7 +40,8 @@ class Stats(C.Structure):
                 ("sweep_ms", C.c_float), ("sweep_launches", C.c_int32)]
 
 
-EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_engine_create",
+EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_pairhmm_devices_in_use",
+           "gklb_pairhmm_last_stats", "gklb_engine_create",
            "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_stage",
            "gklb_engine_stage_device", "gklb_engine_update_haps_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
            "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
@@ -82,6 +83,7 @@ def lib() -> C.CDLL:
         l.gklb_engine_time_runs.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         l.gklb_pairhmm_init.argtypes = [C.c_int, C.c_int]
         l.gklb_pairhmm_compute.argtypes = [C.POINTER(_Batch), C.c_void_p]
+        l.gklb_pairhmm_last_stats.argtypes = [C.POINTER(Stats)]
         _lib = l
     return _lib
 
@@ -199,3 +201,28 @@ class Engine:
 
 def device_count() -> int:
     return int(lib().gklb_device_count())
+
+
+def global_init(use_double: bool = False, max_threads: int = 1) -> int:
+    """The process-global surface the JNI layer uses (gklb_pairhmm_init); returns the number of devices in use."""
+    _check(lib().gklb_pairhmm_init(int(use_double), int(max_threads)))
+    return int(lib().gklb_pairhmm_devices_in_use())
+
+
+def global_compute(b: PairHmmBatch, out: np.ndarray | None = None) -> np.ndarray:
+    b.validate()
+    if out is None:
+        out = np.empty(b.n_reads * b.n_haps, dtype=np.float64)
+    s = make_batch(b)
+    _check(lib().gklb_pairhmm_compute(C.byref(s), _ptr(out)))
+    return out
+
+
+def global_stats() -> Stats:
+    st = Stats()
+    _check(lib().gklb_pairhmm_last_stats(C.byref(st)))
+    return st
+
+
+def global_done() -> None:
+    _check(lib().gklb_pairhmm_done())

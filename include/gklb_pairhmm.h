@@ -93,8 +93,11 @@ typedef struct gklb_engine gklb_engine;
 
 /* initNative.  use_double mirrors PairHMMNativeArguments.useDoublePrecision; max_threads is
  * accepted for signature compatibility and ignored (GKL's non-OpenMP library ignores it too,
- * IntelPairHmm.cc:85-89).  Device selection: env GKLB_DEVICE (default 0).  May be called again;
- * re-initialises with the new arguments. */
+ * IntelPairHmm.cc:85-89).  Device selection: env GKLB_DEVICE (one device, default 0) or GKLB_DEVICES
+ * ("all" or "0,1,..."): with several devices, batches of more than ~4e9 cells per device are sharded over
+ * reads inside this process (one host thread and one engine per GPU; each GPU copies its shard and the
+ * haplotype panel over its own PCIe link and writes its contiguous slab of the read-major output
+ * directly).  May be called again; re-initialises with the new arguments. */
 GKLB_API int gklb_pairhmm_init(int use_double, int max_threads);
 
 /* computeLikelihoodsNative.  Host arenas in, likelihoods[r * n_haps + h] (log10) out; synchronous.
@@ -104,6 +107,11 @@ GKLB_API int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likel
 
 /* doneNative.  Frees the device state of the global engine; idempotent; init may follow. */
 GKLB_API int gklb_pairhmm_done(void);
+
+/* Number of devices the global surface was initialised with, and the counters of its last compute call
+ * (summed over devices; phase times are the maximum over devices). */
+GKLB_API int gklb_pairhmm_devices_in_use(void);
+GKLB_API int gklb_pairhmm_last_stats(gklb_pairhmm_stats* out);
 
 /* ---- explicit engines: one per (host thread | device); used by the benchmark and multi-GPU host ---- */
 
