@@ -310,7 +310,7 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
 // Per-warp slot: the task's packed records, then (VAR 3) the prior table of 5 symbols x K rows x 32 lanes.
 uint32_t warp_slot_bytes(const ClassInst& c, const KernelEntry* k, bool list_mode) {
   const uint32_t rpw = (uint32_t)((32 / c.G) * k->nr);
-  const uint32_t rec = list_mode ? 0u : (uint32_t)align_up((size_t)rpw * 5 * c.stride, 128);
+  const uint32_t rec = (list_mode || c.multi) ? 0u : (uint32_t)align_up((size_t)rpw * 5 * c.stride, 128);
   const uint32_t tbl = (k->var >= 3) ? (uint32_t)(kPriorSyms * c.K * 32 * 8) : 0u;
   return rec + tbl;
 }

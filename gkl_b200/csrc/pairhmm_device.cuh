@@ -617,18 +617,22 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
                    : nullptr;
   const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
   const int rec0 = blk * RPW;
-  // VAR 3: the warp's prior table sits behind the record slot; lane-private column
-  V* tbv = reinterpret_cast<V*>(ctx.slot + ((RPW * rec_bytes + 127u) & ~127u)) + lane;
+  // VAR >= 3: the warp's prior table sits behind the record slot; lane-private column.  Multi-pass classes
+  // (reads of thousands of rows) do not stage their records: the rows are read from global memory pass by pass.
+  V* tbv = reinterpret_cast<V*>(ctx.slot + (MULTI ? 0u : ((RPW * rec_bytes + 127u) & ~127u))) + lane;
   S* tbs = reinterpret_cast<S*>(tbv);
-  // stage the block's packed records into this warp's slot
-  __syncwarp();
-  if (lane == 0) {
-    fence_proxy_async();
-    mbar_expect_tx(ctx.slot_bar, RPW * rec_bytes);
-    tma_bulk_g2s(ctx.slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, ctx.slot_bar);
+  const uint8_t* recs = MULTI ? p.cls.records + (size_t)rec0 * rec_bytes : ctx.slot;
+  if (!MULTI) {
+    // stage the block's packed records into this warp's slot
+    __syncwarp();
+    if (lane == 0) {
+      fence_proxy_async();
+      mbar_expect_tx(ctx.slot_bar, RPW * rec_bytes);
+      tma_bulk_g2s(ctx.slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, ctx.slot_bar);
+    }
+    mbar_wait(ctx.slot_bar, ctx.slot_parity);
+    ctx.slot_parity ^= 1;
   }
-  mbar_wait(ctx.slot_bar, ctx.slot_parity);
-  ctx.slot_parity ^= 1;
 
   int rid[P::NR], npad[P::NR];
 #pragma unroll
@@ -643,7 +647,7 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
   if (!MULTI) {
 #pragma unroll
     for (int x = 0; x < P::NR; x++)
-      load_lane_rows<P, K, VAR>(L, x, ctx.slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K,
+      load_lane_rows<P, K, VAR>(L, x, recs + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K,
                                 npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs);
   }
   for (int h = h_begin; h < h_end; h++) {
@@ -660,7 +664,7 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
       for (int pass = 0; pass < p.cls.n_pass; pass++) {
 #pragma unroll
         for (int x = 0; x < P::NR; x++)
-          load_lane_rows<P, K, VAR>(L, x, ctx.slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows,
+          load_lane_rows<P, K, VAR>(L, x, recs + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows,
                                     pass * cap + t * K, npad[x], t == 0 && pass == 0, ctx.ph2pr_s,
                                     reinterpret_cast<const S*>(p.mm), tbs);
         V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;

@@ -150,6 +150,17 @@ def test_adversarial_gap_open_patterns_stay_within_tolerance(eng):
     assert rel(out[ok], ref[ok]).max() <= REL_TOL
 
 
+def test_very_long_reads(eng, eng_d):
+    # thousands of rows: many passes, records read from global memory (they would not fit in shared memory)
+    rng = np.random.default_rng(8)
+    hap = synth.ACGT[rng.integers(0, 4, size=3000)]
+    reads = [bytes(hap[100:100 + L]) for L in (2500, 1031, 257)]
+    mk = lambda v: [bytes([v]) * len(r) for r in reads]
+    b = fixtures.PairHmmBatch.from_lists(reads, mk(35), mk(40), mk(40), mk(10), [bytes(hap), bytes(hap[50:2900])])
+    assert rel(eng.compute(b), checker(b)).max() <= REL_TOL
+    assert rel(eng_d.compute(b), checker(b, True)).max() <= 1e-9
+
+
 def test_haplotype_panel_larger_than_shared_memory_is_tiled(eng):
     b = synth.random_batch(51, 24, 800, read_len=(60, 120), hap_len=(250, 450))
     assert rel(eng.compute(b), checker(b)).max() <= REL_TOL
