@@ -53,9 +53,34 @@ struct PdhmmParams {
 
 __device__ __forceinline__ double shfl_up_d(double v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
 
+// Read bytes fall into ten classes for the prior's match test (pdhmm-serial.cc:228-277: raw byte equality, 'N' on
+// either side, or an SNP allele of the column matching the read letter case-insensitively): A C G T a c g t N other.
+// cmask[c] bit k tells whether a read byte of class k matches column c; "other" bytes match only an 'N' column or
+// an identical byte (the latter is tested explicitly).
+__device__ __forceinline__ uint32_t read_class(uint32_t x) {
+  switch (x) {
+    case 'A': return 0; case 'C': return 1; case 'G': return 2; case 'T': return 3;
+    case 'a': return 4; case 'c': return 5; case 'g': return 6; case 't': return 7;
+    case 'N': return 8; default: return 9;
+  }
+}
+__device__ __forceinline__ uint32_t column_mask(uint32_t y, uint32_t al) {
+  if (y == 'N') return 0x3FFu;
+  uint32_t m = 0x100u;  // a read 'N' matches every column
+  const uint32_t letters[4] = {'A', 'C', 'G', 'T'};
+  const uint32_t abit[4] = {8u, 16u, 32u, 64u};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    if (y == letters[k] || (al & abit[k])) m |= 1u << k;
+    if (y == (letters[k] | 0x20u) || (al & abit[k])) m |= 1u << (k + 4);
+  }
+  return m;
+}
+
 // Smem per group: y[c], info[c], allele[c] (bytes) and nspec[c] (uint16: first column >= c that needs the state
-// machine) for c in [-kPdMargin, max_hap + kPdMargin): 5 bytes per column
-template <int G, int K, int WARPS>
+// machine) for c in [-kPdMargin, max_hap + kPdMargin), plus cmask[c] (uint16, see read_class): 7 bytes per column
+// MULTI = false: the host guarantees max_read <= G*K, so every pair takes one pass and the carry line does not exist.
+template <int G, int K, int WARPS, bool MULTI>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
   constexpr int GPW = 32 / G;
   constexpr int CAP = G * K;
@@ -63,11 +88,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = lane % G, g = lane / G;
   const int col_pitch = (p.max_hap + 2 * kPdMargin + 1) & ~1;  // even: the uint16 prefix array follows three byte arrays
-  uint8_t* gs = smem + (size_t)(warp * GPW + g) * 5 * col_pitch;
+  uint8_t* gs = smem + (size_t)(warp * GPW + g) * 7 * col_pitch;
   uint8_t* ys = gs + kPdMargin;                  // haplotype byte of column c at ys[c] (c = 1..H)
   uint8_t* infos = gs + col_pitch + kPdMargin;   // state bits + DEL_END
   uint8_t* alleles = gs + 2 * col_pitch + kPdMargin;
   uint16_t* nspec = reinterpret_cast<uint16_t*>(gs + 3 * col_pitch) + kPdMargin;  // col_pitch is even
+  uint16_t* cmask = reinterpret_cast<uint16_t*>(gs + 5 * col_pitch) + kPdMargin;  // which read-byte classes match column c
   const int carry_pitch = p.max_hap + 2;
   double* carry_g = p.carry + ((size_t)blockIdx.x * WARPS + warp) * p.carry_stride + (size_t)g * 12 * carry_pitch;
   const unsigned long long n_warp_items = ((unsigned long long)p.n + GPW - 1) / GPW;
@@ -102,6 +128,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
       ys[c] = y;
       alleles[c] = al;
       infos[c] = 0;
+      cmask[c] = (uint16_t)((c >= 1 && c <= H) ? column_mask(y, al) : 0u);
     }
     __syncwarp();
     int end_state = 0;  // packed 2-bit end states for the three start states
@@ -134,7 +161,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
     end_state = __shfl_sync(0xffffffffu, end_state, g * G);
     __syncwarp();
 
-    const int n_pass = max(1, (R + CAP - 1) / CAP);
+    const int n_pass = MULTI ? max(1, (R + CAP - 1) / CAP) : 1;
     int n_pass_w = n_pass;
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) n_pass_w = max(n_pass_w, __shfl_xor_sync(0xffffffffu, n_pass_w, o));
@@ -150,6 +177,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
       // ---- per-row constants ----
       double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];
       uint32_t xb[K], xbit[K], shift[K];  // read byte, its allele bit, 2 * row-start state
+      uint32_t rcls[K], xeq[K];           // read-byte class; the byte itself when the class is "other" (else no byte)
       bool padrow[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
@@ -161,6 +189,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
         xb[j] = 0x100;  // matches nothing
         xbit[j] = 0;
         shift[j] = 0;
+        rcls[j] = 15;   // no class bit is ever set there
+        xeq[j] = 0x100;
         if (!padrow[j]) {
           const int8_t iq = p.read_ins_qual[ro + row], dq = p.read_del_qual[ro + row], gq = p.gcp[ro + row];
           if (iq < 0 || dq < 0 || gq < 0) atomicOr(p.error_flag, 1u);  // pdhmm-serial.cc:184-198
@@ -179,6 +209,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
           pMi[j] = eq / 3.0;
           const uint32_t x = (uint8_t)p.read_bases[ro + row];
           xb[j] = x;
+          rcls[j] = read_class(x);
+          xeq[j] = (rcls[j] == 9) ? x : 0x100u;
           const uint32_t u = x & 0xDF;  // upper case
           xbit[j] = (u == 'A') ? 8u : (u == 'C') ? 16u : (u == 'G') ? 32u : (u == 'T') ? 64u : 0u;
           // state the row starts in: NORMAL for the first row, then the end state of the previous row
@@ -196,10 +228,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
         D[j] = (padrow[j] && live) ? init : 0.0;
       }
       const bool first = (t == 0);
-      const bool from_carry = first && pass > 0;
+      const bool from_carry = MULTI && first && pass > 0;
       const double* cin = carry_g + (size_t)(pass & 1) * 6 * carry_pitch;
       double* cout = carry_g + (size_t)((pass + 1) & 1) * 6 * carry_pitch;
-      const bool write_carry = live && (t == G - 1) && (pass + 1 < n_pass);
+      const bool write_carry = MULTI && live && (t == G - 1) && (pass + 1 < n_pass);
       // diagonal inputs of the lane's first row at its first column: column 0 of the row above
       double gM = 0, gI = 0, gD = (first && pass == 0) ? init : 0.0, gbM = 0, gbI = 0, gbD = 0;
       if (from_carry && live) {
@@ -218,7 +250,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
         uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
         if (with_branch) { ubM = shfl_up_d(bM[K - 1], G); ubI = shfl_up_d(bI[K - 1], G); ubD = shfl_up_d(bD[K - 1], G); }
         if (first) {
-          if (pass == 0) { uM = uI = ubM = ubI = ubD = 0.0; uD = init; }  // row 0: D = init, everything else 0
+          if (!MULTI || pass == 0) { uM = uI = ubM = ubI = ubD = 0.0; uD = init; }  // row 0: D = init, everything else 0
           else if (live) {
             const int cc = min(max(c, 0), H + 1);
             uM = cin[cc]; uI = cin[carry_pitch + cc]; uD = cin[2 * carry_pitch + cc];
@@ -241,45 +273,64 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
         // nor the one lane 0 reaches next, needs the state machine: the window [s-G, s+1] holds no special column.
         // (Warp-uniform only when the warp carries one pair, i.e. G = 32.)
         int n_fast = 0;
-        if (G == 32) {
+        if (G == 32 && live && s >= G) {
           const int first_special = nspec[max(s - G, -kPdMargin)];
-          n_fast = min(first_special - (s + 1), n_steps - s + 1);
+          // fast steps also run without the per-lane activity test: every lane must be inside its haplotype
+          n_fast = min(first_special - (s + 1), H - s + 1) & ~1;  // pairs of steps
         }
+        n_fast = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(n_fast, 0));  // identical on all lanes; tells the compiler so
         if (n_fast > 0) {
-          // ---- fast steps: M/I/D only, the branch twins simply trail by one column ----
-#pragma unroll 2
-          for (int k = 0; k < n_fast; k++) {
-            if (live && (unsigned)(c - 1) < (unsigned)H) {
-              const uint32_t y = ys[c], al = alleles[c];
-              double tM = uM, tI = uI;
-              double dM = gM, dI = gI, dD = gD;
+          // ---- fast steps: M/I/D only.  Two steps per iteration ping-pong between two register sets, so the
+          // branch twins (which on plain columns are just the previous column's M/I/D) cost nothing: after an
+          // even number of steps they are the second set. ----
+          double M2[K], I2[K], D2[K];
+          auto half = [&](const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K], double (&Mo)[K],
+                          double (&Io)[K], double (&Do)[K]) {
+            const uint32_t y = ys[c], cm = cmask[c];
+            double tM = uM, tI = uI;
+            double dM = gM, dI = gI, dD = gD;
 #pragma unroll
-              for (int j = 0; j < K; j++) {
-                const double lM = M[j], lI = I[j], lD = D[j];
-                const bool match = (xb[j] == y) || (xb[j] == 'N') || (y == 'N') || ((xbit[j] & al) != 0);
-                const double prior = match ? pMa[j] : pMi[j];
-                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-                const double nD = lM * tMD[j] + lD * tII[j];
-                const double nI = tM * tMI[j] + tI * tII[j];
-                dM = lM; dI = lI; dD = lD;
-                bM[j] = lM; bI[j] = lI; bD[j] = lD;
-                M[j] = nM; I[j] = nI; D[j] = nD;
-                tM = nM; tI = nI;
-              }
-              finish_step();
+            for (int j = 0; j < K; j++) {
+              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const double prior = match ? pMa[j] : pMi[j];
+              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+              const double nD = Mi[j] * tMD[j] + Di[j] * tII[j];
+              const double nI = tM * tMI[j] + tI * tII[j];
+              dM = Mi[j]; dI = Ii[j]; dD = Di[j];
+              Mo[j] = nM; Io[j] = nI; Do[j] = nD;
+              tM = nM; tI = nI;
+            }
+            if (!MULTI || pass == n_pass - 1) sum += Mo[K - 1] + Io[K - 1];
+            if (write_carry) {
+              cout[c] = Mo[K - 1]; cout[carry_pitch + c] = Io[K - 1]; cout[2 * carry_pitch + c] = Do[K - 1];
+              cout[3 * carry_pitch + c] = Mi[K - 1]; cout[4 * carry_pitch + c] = Ii[K - 1];
+              cout[5 * carry_pitch + c] = Di[K - 1];
             }
             gM = uM; gI = uI; gD = uD;
             c++;
-            fetch(false);
+            uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
+            if (first) {
+              if (!MULTI || pass == 0) { uM = uI = 0.0; uD = init; }
+              else {
+                const int cc = min(max(c, 0), H + 1);
+                uM = cin[cc]; uI = cin[carry_pitch + cc]; uD = cin[2 * carry_pitch + cc];
+              }
+            }
+          };
+          for (int k = 0; k < n_fast; k += 2) {
+            half(M, I, D, M2, I2, D2);
+            half(M2, I2, D2, M, I, D);
           }
+#pragma unroll
+          for (int j = 0; j < K; j++) { bM[j] = M2[j]; bI[j] = I2[j]; bD[j] = D2[j]; }
           s += n_fast;
           // the branch twins of the lane above were not exchanged during the fast steps; the next (slow) step
           // needs them as its top values -- its diagonal twins are only read on special columns, which by
           // construction of the window are at least one slow step away
           ubM = shfl_up_d(bM[K - 1], G); ubI = shfl_up_d(bI[K - 1], G); ubD = shfl_up_d(bD[K - 1], G);
           if (first) {
-            if (pass == 0) { ubM = ubI = ubD = 0.0; }
-            else if (live) {
+            if (!MULTI || pass == 0) { ubM = ubI = ubD = 0.0; }
+            else {
               const int cc = min(max(c, 0), H + 1);
               ubM = cin[3 * carry_pitch + cc]; ubI = cin[4 * carry_pitch + cc]; ubD = cin[5 * carry_pitch + cc];
             }
@@ -287,35 +338,63 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
           gbM = gbI = gbD = 0.0;
           continue;
         }
-        // ---- one slow step: the full state machine ----
-        if (live && (unsigned)(c - 1) < (unsigned)H) {
-          const uint32_t y = ys[c], al = alleles[c];
-          const uint32_t info = infos[c];
-          const bool del_end = (info & 0x40) != 0;
-          double tM = uM, tI = uI, tbM = ubM, tbI = ubI;                               // top of row j
-          double dM = gM, dI = gI, dD = gD, dbM = gbM, dbI = gbI, dbD = gbD;          // diagonal of row j
+        // ---- one slow step ----
+        // Most columns that keep a window out of the fast path are INSIDE a deletion span: there only the branch
+        // twins behave differently (they stay put).  The expensive merges (max of twin and main values) happen on
+        // the column that closes a deletion (DEL_END: insertion inputs) and the one after it (AFTER_DEL); they are
+        // executed only when some lane of the warp sits on such a column.
+        const bool inrange = live && (unsigned)(c - 1) < (unsigned)H;
+        const uint32_t info = inrange ? infos[c] : 0u;
+        bool merge_lane = (info & 0x40u) != 0;
 #pragma unroll
-          for (int j = 0; j < K; j++) {
-            const uint32_t st = (info >> shift[j]) & 3u;
-            double lM = M[j], lI = I[j], lD = D[j];
-            const double lbM = bM[j], lbI = bI[j], lbD = bD[j];
-            double nbM, nbI, nbD;
-            if (st == 0) { nbM = lM; nbD = lD; nbI = lI; }
-            else if (st == 1) { nbM = lbM; nbD = lbD; nbI = lbI; }
-            else {
-              nbM = fmax(lbM, lM); nbD = fmax(lbD, lD); nbI = fmax(lbI, lI);
-              dM = fmax(dM, dbM); dI = fmax(dI, dbI); dD = fmax(dD, dbD);
-              lM = fmax(lM, lbM); lD = fmax(lD, lbD);
+        for (int j = 0; j < K; j++) merge_lane |= ((info >> shift[j]) & 3u) == 2u;
+        const bool merge = __any_sync(0xffffffffu, merge_lane);
+        if (inrange) {
+          const uint32_t y = ys[c], cm = cmask[c];
+          if (!merge) {
+            double tM = uM, tI = uI;
+            double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const bool inside = ((info >> shift[j]) & 3u) == 1u;
+              const double lM = M[j], lI = I[j], lD = D[j];
+              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const double prior = match ? pMa[j] : pMi[j];
+              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+              const double nD = lM * tMD[j] + lD * tII[j];
+              const double nI = tM * tMI[j] + tI * tII[j];
+              dM = lM; dI = lI; dD = lD;
+              bM[j] = inside ? bM[j] : lM; bI[j] = inside ? bI[j] : lI; bD[j] = inside ? bD[j] : lD;
+              M[j] = nM; I[j] = nI; D[j] = nD;
+              tM = nM; tI = nI;
             }
-            const bool match = (xb[j] == y) || (xb[j] == 'N') || (y == 'N') || ((xbit[j] & al) != 0);
-            const double prior = match ? pMa[j] : pMi[j];
-            const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-            const double nD = lM * tMD[j] + lD * tII[j];  // deletionToDeletion == insertionToInsertion
-            const double nI = del_end ? fmax(tbM, tM) * tMI[j] + fmax(tbI, tI) * tII[j] : tM * tMI[j] + tI * tII[j];
-            // the next row's diagonal is this row's previous column, its top this row's new column
-            dM = M[j]; dI = I[j]; dD = D[j]; dbM = lbM; dbI = lbI; dbD = lbD;
-            M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
-            tM = nM; tI = nI; tbM = nbM; tbI = nbI;
+          } else {
+            const bool del_end = (info & 0x40u) != 0;
+            double tM = uM, tI = uI, tbM = ubM, tbI = ubI;                               // top of row j
+            double dM = gM, dI = gI, dD = gD, dbM = gbM, dbI = gbI, dbD = gbD;          // diagonal of row j
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const uint32_t st = (info >> shift[j]) & 3u;
+              const bool inside = st == 1u, after = st == 2u;
+              const double lM = M[j], lI = I[j], lD = D[j];
+              const double lbM = bM[j], lbI = bI[j], lbD = bD[j];
+              const double mxM = fmax(lbM, lM), mxI = fmax(lbI, lI), mxD = fmax(lbD, lD);
+              const double nbM = after ? mxM : (inside ? lbM : lM);
+              const double nbI = after ? mxI : (inside ? lbI : lI);
+              const double nbD = after ? mxD : (inside ? lbD : lD);
+              const double eM = after ? fmax(dM, dbM) : dM, eI = after ? fmax(dI, dbI) : dI, eD = after ? fmax(dD, dbD) : dD;
+              const double leftM = after ? mxM : lM, leftD = after ? mxD : lD;
+              const double topM = del_end ? fmax(tbM, tM) : tM, topI = del_end ? fmax(tbI, tI) : tI;
+              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const double prior = match ? pMa[j] : pMi[j];
+              const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
+              const double nD = leftM * tMD[j] + leftD * tII[j];  // deletionToDeletion == insertionToInsertion
+              const double nI = topM * tMI[j] + topI * tII[j];
+              // the next row's diagonal is this row's previous column, its top this row's new column
+              dM = lM; dI = lI; dD = lD; dbM = lbM; dbI = lbI; dbD = lbD;
+              M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
+              tM = nM; tI = nI; tbM = nbM; tbI = nbI;
+            }
           }
           finish_step();
         }

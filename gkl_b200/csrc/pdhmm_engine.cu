@@ -112,8 +112,9 @@ void destroy(PdEngine* e) {
 int launch(PdEngine* e) {
   CU(cudaMemsetAsync(e->misc.p, 0, 8, e->stream));
   void* args[] = {&e->last};
-  CU(cudaLaunchKernel(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps>), dim3(e->last_grid), dim3(kWarps * 32), args,
-                      e->last_smem, e->stream));
+  const void* fn = (e->last.max_read <= kG * kK) ? reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, false>)
+                                                 : reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>);
+  CU(cudaLaunchKernel(fn, dim3(e->last_grid), dim3(kWarps * 32), args, e->last_smem, e->stream));
   e->stats.kernel_launches++;
   return GKLB_OK;
 }
@@ -148,7 +149,7 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
 
   constexpr int gpw = 32 / kG;
   const size_t col_pitch = ((size_t)b->max_hap + 2 * kPdMargin + 1) & ~(size_t)1;
-  const size_t smem = (size_t)kWarps * gpw * 5 * col_pitch;
+  const size_t smem = (size_t)kWarps * gpw * 7 * col_pitch;
   if (smem > (size_t)kSmemMax)
     return gklb_internal_fail(GKLB_ERR_INVALID, "maxHapLength %d does not fit in shared memory", b->max_hap);
 
@@ -247,7 +248,9 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
   e->carry_state = (rs && !strcmp(rs, "reset")) ? 0 : 1;
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) CU(cudaEventCreate(&ev));
-  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps>),
+  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, false>),
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));

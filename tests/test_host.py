@@ -54,6 +54,15 @@ def test_library_exports_every_symbol_of_the_header():
     for name in declared:
         assert hasattr(lib, name), name
     assert b"sm_100a" in lib.gklb_version()
+    # the PDHMM surface (include/gklb_pdhmm.h), exported by the same binary under both library names
+    from gkl_b200 import pdhmm
+    pd_header = (ROOT / "include" / "gklb_pdhmm.h").read_text()
+    pd_declared = set(re.findall(r"GKLB_API\s+[\w\s\*]+?\b(gklb_\w+)\s*\(", pd_header))
+    assert pd_declared == set(pdhmm.PD_EXPORTS), pd_declared ^ set(pdhmm.PD_EXPORTS)
+    import ctypes
+    pd_lib = ctypes.CDLL(str(native.LIB_PATH.with_name("libgkl_pdhmm.so")))
+    for name in pd_declared | declared:
+        assert hasattr(pd_lib, name), name
 
 
 def test_host_tables_are_bit_identical_to_the_oracle():
