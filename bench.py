@@ -306,7 +306,7 @@ def run_ours(args):
                     "api": "gklb_engine_compute (what computeLikelihoodsNative calls), pinned host buffers"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "k_sweep_tasks<VF2,16,7,8,false,4>", "achieved": ach_tf, "peak": peak_tf,
+            "roofline": {"bound": "fp32", "kernel": "k_sweep_tasks<VF2,16,7,12,false,5>", "achieved": ach_tf, "peak": peak_tf,
                          "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
                          "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": sweep_per_launch_ms, "peak_source": peak_src,
                          "hbm": {"achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,

@@ -21,7 +21,7 @@ import oracle  # noqa: E402  (measurement harness: the oracle is the checker onl
 from gkl_b200 import native, synth  # noqa: E402
 
 VARIANTS = [
-    "f2,16,7,8,4", "f2,16,7,8,3", "f2,16,7,8,2", "f2,16,7,8,1", "f2,16,7,8,0", "f2,16,8,8,4", "f2,16,7,10,4", "f2,16,7,12,4",
+    "f2,16,7,8,4", "f2,16,7,12,5", "f2,16,7,8,5", "f2,16,7,8,3", "f2,16,7,8,2", "f2,16,7,8,1", "f2,16,7,8,0", "f2,16,8,8,4", "f2,16,7,10,4", "f2,16,7,12,4",
     "f2,32,4,12,4", "f2,32,4,16,4", "f2,32,5,8,4",
     "f1,8,13,8,4", "f1,8,13,8,3", "f1,8,13,12,4", "f1,16,7,16,4",
     "d1,16,7,8,3", "d1,16,7,8,2",

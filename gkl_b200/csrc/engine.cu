@@ -224,8 +224,10 @@ int set_kernel_attrs() {
   }
   for (int pol : {POL_F2, POL_D1})
     for (int lm = 0; lm < 2; lm++) {
-      const void* fn = mega_kernel(pol, lm);
-      if (fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+      for (int w : {8, 12}) {
+        const void* fn = mega_kernel(pol, lm, w);
+        if (fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+      }
     }
   return GKLB_OK;
 }
@@ -325,6 +327,8 @@ int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, size_t* meta_bytes) 
   for (auto& c : e->classes) {
     worst_slots = std::max(worst_slots, slot_bytes_total(c, c.kf));
     if (c.kd) worst_slots = std::max(worst_slots, slot_bytes_total(c, c.kd));
+    // the multi-class kernel runs every class with its own warp count (up to 12) and the largest slot
+    worst_slots = std::max(worst_slots, 12u * (uint32_t)align_up((size_t)warp_slot_bytes(c, c.kf, false), 128));
   }
   const long long budget = (long long)kSmemMax - 4096 - worst_slots;
   e->tiles.clear();
@@ -420,7 +424,9 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
     if (c.multi) {
       int max_len = 0;
       for (auto& t : e->tiles) max_len = std::max(max_len, t.max_len);
-      const int warps = std::max(c.kf->warps, c.kd ? c.kd->warps : 0);
+      // per-warp scratch: sized for the widest CTA any kernel of this class may run with (the multi-class
+      // kernel uses up to 12 warps)
+      const int warps = std::max(12, std::max(c.kf->warps, c.kd ? c.kd->warps : 0));
       c.carry_stride = (size_t)(32 / c.G) * 6 * (max_len + 2) * 8;
       c.carry_off = carry_bytes;
       carry_bytes += c.carry_stride * warps * e->num_sms;
@@ -616,7 +622,16 @@ int class_cfg(const ClassInst& c) {
 }
 
 // One launch for all classes of a tile (see k_mega_tasks).  policy: POL_F2 or POL_D1.
+int mega_warps(int policy, bool list_mode) {
+  static const int w = [] {
+    const char* v = getenv("GKLB_MEGA_WARPS");
+    return v ? atoi(v) : 12;
+  }();
+  return (policy == POL_F2 && !list_mode && w == 12) ? 12 : 8;
+}
+
 int launch_mega_tile(gklb_engine* e, const Tile& t, int tile_index, int policy, bool list_mode) {
+  const int warps = mega_warps(policy, list_mode);
   MegaParams mp;
   memset(&mp, 0, sizeof(mp));
   // longest classes first: their tasks are the most expensive, schedule them early
@@ -641,9 +656,11 @@ int launch_mega_tile(gklb_engine* e, const Tile& t, int tile_index, int policy, 
   }
   unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
   mp.queue = counters + e->mega_counter0 + 2 * tile_index + (list_mode ? 1 : 0);
-  smem = smem_layout(8, t.bytes, slot_bytes, policy == POL_D1 ? 8 : 4).total;
-  if (smem > (size_t)kSmemMax) return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu)", smem);
-  const int grid = list_mode ? e->num_sms : std::min(e->num_sms, (tasks + 7) / 8);
+  smem = smem_layout(warps, t.bytes, slot_bytes, policy == POL_D1 ? 8 : 4).total;
+  if (smem > (size_t)kSmemMax)
+    return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu: panel %u, %d warps x %u, policy %d list %d)",
+                smem, t.bytes, warps, slot_bytes, policy, (int)list_mode);
+  const int grid = list_mode ? e->num_sms : std::min(e->num_sms, (tasks + warps - 1) / warps);
   if (grid <= 0) return GKLB_OK;
   if (!list_mode) {
     while ((int)e->kev.size() < e->kev_used + 2) {
@@ -653,7 +670,7 @@ int launch_mega_tile(gklb_engine* e, const Tile& t, int tile_index, int policy, 
     }
     CU(cudaEventRecord(e->kev[e->kev_used], e->stream));
   }
-  CU(launch_mega(mega_kernel(policy, list_mode ? 1 : 0), mp, slot_bytes, list_mode ? 1 : 0, grid, 8 * 32, smem, e->stream));
+  CU(launch_mega(mega_kernel(policy, list_mode ? 1 : 0, warps), mp, slot_bytes, list_mode ? 1 : 0, grid, warps * 32, smem, e->stream));
   if (!list_mode) {
     CU(cudaEventRecord(e->kev[e->kev_used + 1], e->stream));
     e->kev_used += 2;

@@ -285,7 +285,7 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
       my = (pad ? (S)1 : my) * gnext;
       if (j == 0) P::set(L.gTop, x, pad ? (S)0 : pgap);
     }
-    if (VAR == 4) {
+    if (VAR >= 4) {
       // W = X / pMX(row):  W = M(up) + kappa * W(up);  the row above a first real row has X = 0 (kappa = 0)
       const S pmx = ph2pr[ig];
       S kappa = (S)0;
@@ -349,7 +349,7 @@ struct Sweeper {
     uZ = P::shfl_up(Zl[K - 1], G);
     if (row0_above) {  // row 0: M = X = 0 (killed by the zeroed top constants), Y = init
       uZ = inj;
-      if (VAR == 4) uM = P::splat(0);  // the W update adds M(up) without a coefficient
+      if (VAR >= 4) uM = P::splat(0);  // the W update adds M(up) without a coefficient
     }
     if (MULTI) {
       if (first && carry_in != nullptr) {
@@ -375,7 +375,7 @@ struct Sweeper {
       for (int x = 0; x < P::NR; x++) m2[x] = mw[x][j / 8];
       const uint32_t bit = 0xFu << (4 * (j % 8));
       V Mn, Yn, Zn;
-      const V Xn = (VAR == 4) ? P::fma(L.pMX[j], upX, upM)  // W form: kappa * W(up) + M(up)
+      const V Xn = (VAR >= 4) ? P::fma(L.pMX[j], upX, upM)  // W form: kappa * W(up) + M(up)
                               : P::fma(j == 0 ? L.pXXtop : L.pXX[j], upX, P::mul(L.pMX[j], upM));
       if (VAR >= 3) {
         Mn = P::mul(pr[j], P::fma(L.Am[j], dM, dZ));
@@ -407,7 +407,7 @@ struct Sweeper {
       upX = Xn;
     }
     botX = upX;
-    if (VAR == 4) {
+    if (VAR >= 4) {
       sum = P::add(sum, upM);
       sumW = P::add(sumW, upX);
     } else {
@@ -424,7 +424,13 @@ struct Sweeper {
 
   template <bool GUARD>
   __device__ __forceinline__ void step() {
-    if (VAR >= 3) {
+    if (VAR == 5) {  // measurement variant: VAR 4 without the one-column-ahead prior prefetch (fewer registers)
+      const V* tn = tb + (size_t)(hb & 7u) * (K * 32);
+#pragma unroll
+      for (int j = 0; j < K; j++) pr[j] = tn[j * 32];
+      hb = hap[min(c + 1, haplen + 1)];
+      if (!GUARD || (unsigned)(c - 1) < (unsigned)haplen) cells(0u);
+    } else if (VAR >= 3) {
       V prn[K];  // priors of column c + 1, in flight while column c is computed
       const V* tn = tb + (size_t)(hb & 7u) * (K * 32);
 #pragma unroll
@@ -489,7 +495,7 @@ struct Sweeper {
       }
     }
     hb = hap[max(c, -kHapLeftMargin + 1)];
-    if (VAR >= 3) {
+    if (VAR == 3 || VAR == 4) {
       const V* t0 = tb + (size_t)(hb & 7u) * (K * 32);
 #pragma unroll
       for (int j = 0; j < K; j++) pr[j] = t0[j * 32];
@@ -502,7 +508,7 @@ struct Sweeper {
 #pragma unroll 2
     for (; s <= steady_end; s++) step<false>();
     for (; s <= n_steps; s++) step<true>();
-    return (VAR == 4) ? P::fma(L.xlast, sumW, sum) : sum;
+    return (VAR >= 4) ? P::fma(L.xlast, sumW, sum) : sum;
   }
 };
 
@@ -804,34 +810,35 @@ struct MegaParams {
   SweepParams cls[kMaxMegaClasses];
 };
 
-// product variants: fp32 uses the W form (VAR 4), fp64 must not (2^1020 leaves no headroom for X / pMX)
-template <class P> struct ProductVar { static constexpr int value = P::kDouble ? 3 : 4; };
-template <class P, int G, int K, bool MULTI>
+// product variants: fp32 uses the W form, fp64 must not (2^1020 leaves no headroom for X / pMX).  With 12 warps
+// per CTA (168 registers) the fp32 kernels drop the one-column-ahead prior prefetch (VAR 5); with 8 they keep it.
+template <class P, int WARPS> struct ProductVar { static constexpr int value = P::kDouble ? 3 : (WARPS >= 12 ? 5 : 4); };
+template <class P, int G, int K, bool MULTI, int WARPS>
 __device__ __noinline__ void mega_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
-  run_task<P, G, K, MULTI, ProductVar<P>::value>(p, task, ctx);
+  run_task<P, G, K, MULTI, ProductVar<P, WARPS>::value>(p, task, ctx);
 }
-template <class P, int G, int K, bool MULTI>
+template <class P, int G, int K, bool MULTI, int WARPS>
 __device__ __noinline__ void mega_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
                                        WarpCtx<typename P::S>& ctx) {
-  run_list_item<P, G, K, MULTI, ProductVar<P>::value>(p, wi, n_items, ctx);
+  run_list_item<P, G, K, MULTI, ProductVar<P, WARPS>::value>(p, wi, n_items, ctx);
 }
 
 #define GKLB_MEGA_DISPATCH(FN, ...)                                   \
   switch (cfg) {                                                      \
-    case 0: FN<P, 8, 4, false>(__VA_ARGS__); break;                   \
-    case 1: FN<P, 8, 5, false>(__VA_ARGS__); break;                   \
-    case 2: FN<P, 8, 6, false>(__VA_ARGS__); break;                   \
-    case 3: FN<P, 8, 7, false>(__VA_ARGS__); break;                   \
-    case 4: FN<P, 8, 8, false>(__VA_ARGS__); break;                   \
-    case 5: FN<P, 16, 5, false>(__VA_ARGS__); break;                  \
-    case 6: FN<P, 16, 6, false>(__VA_ARGS__); break;                  \
-    case 7: FN<P, 16, 7, false>(__VA_ARGS__); break;                  \
-    case 8: FN<P, 16, 8, false>(__VA_ARGS__); break;                  \
-    case 9: FN<P, 32, 5, false>(__VA_ARGS__); break;                  \
-    case 10: FN<P, 32, 6, false>(__VA_ARGS__); break;                 \
-    case 11: FN<P, 32, 7, false>(__VA_ARGS__); break;                 \
-    case 12: FN<P, 32, 8, false>(__VA_ARGS__); break;                 \
-    default: FN<P, 32, 8, true>(__VA_ARGS__); break;                  \
+    case 0: FN<P, 8, 4, false, WARPS>(__VA_ARGS__); break;                   \
+    case 1: FN<P, 8, 5, false, WARPS>(__VA_ARGS__); break;                   \
+    case 2: FN<P, 8, 6, false, WARPS>(__VA_ARGS__); break;                   \
+    case 3: FN<P, 8, 7, false, WARPS>(__VA_ARGS__); break;                   \
+    case 4: FN<P, 8, 8, false, WARPS>(__VA_ARGS__); break;                   \
+    case 5: FN<P, 16, 5, false, WARPS>(__VA_ARGS__); break;                  \
+    case 6: FN<P, 16, 6, false, WARPS>(__VA_ARGS__); break;                  \
+    case 7: FN<P, 16, 7, false, WARPS>(__VA_ARGS__); break;                  \
+    case 8: FN<P, 16, 8, false, WARPS>(__VA_ARGS__); break;                  \
+    case 9: FN<P, 32, 5, false, WARPS>(__VA_ARGS__); break;                  \
+    case 10: FN<P, 32, 6, false, WARPS>(__VA_ARGS__); break;                 \
+    case 11: FN<P, 32, 7, false, WARPS>(__VA_ARGS__); break;                 \
+    case 12: FN<P, 32, 8, false, WARPS>(__VA_ARGS__); break;                 \
+    default: FN<P, 32, 8, true, WARPS>(__VA_ARGS__); break;                  \
   }
 
 template <class P, int WARPS>

@@ -72,10 +72,11 @@ cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_
 
 static const KernelEntry g_table[] = {
     // ---- product: packed fp32, folded recurrence with the shared-memory prior table (VAR 3) ----
-    E_F2(8, 4, 8, false, 4),  E_F2(8, 5, 8, false, 4),  E_F2(8, 6, 8, false, 4),  E_F2(8, 7, 8, false, 4),
-    E_F2(8, 8, 8, false, 4),  E_F2(16, 5, 8, false, 4), E_F2(16, 6, 8, false, 4), E_F2(16, 7, 8, false, 4),
-    E_F2(16, 8, 8, false, 4), E_F2(32, 5, 8, false, 4), E_F2(32, 6, 8, false, 4), E_F2(32, 7, 8, false, 4),
-    E_F2(32, 8, 8, false, 4), E_F2(32, 8, 8, true, 4),
+    // K <= 7 fits 12 warps per SM in 168 registers without the prior prefetch (VAR 5); K = 8 keeps 8 warps (VAR 4)
+    E_F2(8, 4, 12, false, 5),  E_F2(8, 5, 12, false, 5),  E_F2(8, 6, 12, false, 5),  E_F2(8, 7, 12, false, 5),
+    E_F2(8, 8, 8, false, 4),   E_F2(16, 5, 12, false, 5), E_F2(16, 6, 12, false, 5), E_F2(16, 7, 12, false, 5),
+    E_F2(16, 8, 8, false, 4),  E_F2(32, 5, 12, false, 5), E_F2(32, 6, 12, false, 5), E_F2(32, 7, 12, false, 5),
+    E_F2(32, 8, 8, false, 4),  E_F2(32, 8, 8, true, 4),
     // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
     E_D1(8, 4, 8, false, 3),  E_D1(8, 5, 8, false, 3),  E_D1(8, 6, 8, false, 3),  E_D1(8, 7, 8, false, 3),
     E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 8, false, 3), E_D1(16, 6, 8, false, 3), E_D1(16, 7, 8, false, 3),
@@ -84,7 +85,7 @@ static const KernelEntry g_table[] = {
 #ifdef GKLB_EXPERIMENTAL
     // ---- measurement only ----
     E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0),
-    E_F2(16, 7, 10, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 4), E_F2(32, 4, 16, false, 4),
+    E_F2(16, 7, 8, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 7, 8, false, 5), E_F2(32, 5, 8, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 5), E_F2(8, 4, 16, false, 5),
     E_F1(8, 13, 8, false, 4), E_F1(8, 13, 8, false, 3), E_F1(8, 13, 12, false, 4), E_F1(16, 7, 16, false, 4),
     E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3),
 #endif
@@ -105,7 +106,8 @@ const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, i
   return nullptr;
 }
 
-const void* mega_kernel(int policy, int list_mode) {
+const void* mega_kernel(int policy, int list_mode, int warps) {
+  if (policy == POL_F2 && !list_mode && warps == 12) return reinterpret_cast<const void*>(&k_mega_tasks<VF2, 12>);
   if (policy == POL_F2 && !list_mode) return reinterpret_cast<const void*>(&k_mega_tasks<VF2, 8>);
   if (policy == POL_D1 && !list_mode) return reinterpret_cast<const void*>(&k_mega_tasks<VD1, 8>);
   if (policy == POL_D1 && list_mode) return reinterpret_cast<const void*>(&k_mega_list<VD1, 8>);

@@ -23,7 +23,7 @@ const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, i
 
 cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s);
 // Multi-class kernels (8 warps per CTA): POL_F2 / POL_D1 task kernels and the POL_D1 rerun-list kernel.
-const void* mega_kernel(int policy, int list_mode);
+const void* mega_kernel(int policy, int list_mode, int warps = 8);
 cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes, int list_mode, int grid, int threads,
                         size_t smem, cudaStream_t s);
 cudaError_t launch_pack(const PackParams& p, cudaStream_t s);
