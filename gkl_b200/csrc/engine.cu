@@ -157,7 +157,8 @@ struct gklb_engine {
   std::vector<ClassInst> classes;
   std::vector<Tile> tiles;
   DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
-  HostBuf h_meta, h_counters;
+  HostBuf h_meta, h_counters, h_out;
+  double* pending_out = nullptr;  // destination of the batch submitted with gklb_engine_submit, until gklb_engine_wait
   size_t arena_pitch = 0;
   const int64_t* p_read_off = nullptr;   // where the staged offsets / arenas live on the device
   const int64_t* p_hap_off = nullptr;
@@ -745,6 +746,36 @@ int do_compute(gklb_engine* e, const gklb_pairhmm_batch* b, double* out) {
   return GKLB_OK;
 }
 
+// Asynchronous compute: everything is queued on the engine's stream and the likelihoods travel to a pinned
+// buffer (a device->host copy into pageable memory would block the host until the kernels are done).
+int do_submit(gklb_engine* e, const gklb_pairhmm_batch* b, double* out) {
+  if (e->pending_out) return fail(GKLB_ERR_STATE, "a submitted batch is still in flight: call gklb_engine_wait first");
+  int rc;
+  if ((rc = do_stage(e, b, false))) return rc;
+  if ((rc = do_run(e))) return rc;
+  if (e->classes.empty()) return GKLB_OK;
+  if (!out) return fail(GKLB_ERR_INVALID, "likelihoods is null");
+  CU(e->h_out.ensure(sizeof(double) * (size_t)e->stats.pairs));
+  CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(double) * (size_t)e->stats.pairs, cudaMemcpyDeviceToHost, e->stream));
+  CU(cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(unsigned int) * (size_t)e->n_counters,
+                     cudaMemcpyDeviceToHost, e->stream));
+  e->pending_out = out;
+  return GKLB_OK;
+}
+
+int do_wait(gklb_engine* e) {
+  CU(cudaSetDevice(e->device));
+  CU(cudaStreamSynchronize(e->stream));
+  if (!e->pending_out) return GKLB_OK;
+  memcpy(e->pending_out, e->h_out.p, sizeof(double) * (size_t)e->stats.pairs);
+  e->pending_out = nullptr;
+  int64_t fb = 0;
+  const unsigned int* hc = static_cast<const unsigned int*>(e->h_counters.p);
+  for (auto& c : e->classes) fb += hc[c.counter0];
+  e->stats.fallback_pairs = fb;
+  return GKLB_OK;
+}
+
 int create_engine(gklb_engine** out, int device, int use_double) {
   int n = 0;
   cudaError_t ce = cudaGetDeviceCount(&n);
@@ -779,6 +810,7 @@ void destroy_engine(gklb_engine* e) {
     b->release();
   e->h_meta.release();
   e->h_counters.release();
+  e->h_out.release();
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto& ev : e->kev) cudaEventDestroy(ev);
@@ -953,6 +985,18 @@ int gklb_engine_compute(gklb_engine* e, const gklb_pairhmm_batch* batch, double*
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
   std::lock_guard<std::mutex> lk(e->mu);
   return do_compute(e, batch, likelihoods);
+}
+
+int gklb_engine_submit(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_submit(e, batch, likelihoods);
+}
+
+int gklb_engine_wait(gklb_engine* e) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_wait(e);
 }
 
 int gklb_engine_stage(gklb_engine* e, const gklb_pairhmm_batch* batch) {

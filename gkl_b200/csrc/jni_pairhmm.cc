@@ -10,6 +10,7 @@
 // bookkeeping, local references deleted as it goes -- GKL's JavaData pins 5R+H arrays and leaks the local
 // references, pairhmm/JavaData.h:135-145), pins the output double[] the way GKL does (:147-154) and calls the
 // C-ABI.  Errors become Java exceptions by class path like GKL's (IntelPairHmm.cc:64-68,141-145,171-178).
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -76,6 +77,27 @@ int append_field(JNIEnv* env, jobjectArray array, int index, jfieldID fid, Arena
   return len;
 }
 
+// Large calls are pipelined: reads are marshalled in blocks, and while block k+1 is being copied out of the Java
+// heap, block k is already on the GPU (two engines on the same device take turns).  In a JVM the 5R+H array
+// accesses of this binding cost as much as the kernels once those run at TCUPS rates.
+struct Pipeline {
+  gklb_engine* eng[2] = {nullptr, nullptr};
+  int use_double = 0;
+};
+Pipeline g_pipe;
+std::mutex g_pipe_mu;
+
+int pipeline_block_reads() {
+  const char* v = getenv("GKLB_JNI_BLOCK_READS");
+  const int n = v ? atoi(v) : 2048;
+  return n > 0 ? n : 2048;
+}
+
+void pipeline_reset() {
+  for (auto& e : g_pipe.eng)
+    if (e) { gklb_engine_destroy(e); e = nullptr; }
+}
+
 }  // namespace
 
 extern "C" {
@@ -111,6 +133,11 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_initNative(JNIEnv
     std::lock_guard<std::mutex> lk(g_fid_mu);
     g_fid = f;
   }
+  {
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    pipeline_reset();
+    g_pipe.use_double = use_double ? 1 : 0;
+  }
   const int rc = gklb_pairhmm_init(use_double ? 1 : 0, (int)max_threads);
   if (rc != GKLB_OK) throw_status(env, rc);
 }
@@ -132,6 +159,66 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihood
   Arena hap, bases, quals, ins, del, gcp;
   for (int h = 0; h < n_haps; h++)
     if (append_field(env, haplotypeDataArray, h, f.hap_bases, hap, -1, true) < 0) return;
+
+  const int block = pipeline_block_reads();
+  if (n_reads >= 2 * block && gklb_pairhmm_devices_in_use() == 1) {
+    if ((long long)env->GetArrayLength(likelihoodArray) < (long long)n_reads * n_haps) {
+      throw_java(env, "java/lang/IllegalArgumentException", "likelihood array is shorter than reads x haplotypes");
+      return;
+    }
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    const char* dev = getenv("GKLB_DEVICE");
+    for (auto& e : g_pipe.eng)
+      if (!e) {
+        const int rc = gklb_engine_create(&e, dev ? atoi(dev) : 0, g_pipe.use_double);
+        if (rc != GKLB_OK) { throw_status(env, rc); return; }
+      }
+    jdouble* out = env->GetDoubleArrayElements(likelihoodArray, nullptr);
+    if (!out) { throw_java(env, "java/lang/OutOfMemoryError", "Unable to access jdoubleArray"); return; }
+    Arena blk[2][5];
+    int rc = GKLB_OK;
+    bool thrown = false;
+    int k = 0;
+    for (int r0 = 0; r0 < n_reads && rc == GKLB_OK && !thrown; r0 += block, k++) {
+      const int r1 = r0 + block < n_reads ? r0 + block : n_reads;
+      Arena* a = blk[k & 1];
+      // the engine that used these arenas two blocks ago must be done with them (pinned staging is per engine,
+      // pageable sources are consumed at submit; waiting also bounds the pinned output buffers)
+      if (k >= 2) rc = gklb_engine_wait(g_pipe.eng[k & 1]);
+      if (rc != GKLB_OK) break;
+      for (int i = 0; i < 5; i++) { a[i].bytes.clear(); a[i].off.assign(1, 0); }
+      for (int r = r0; r < r1 && !thrown; r++) {
+        const int len = append_field(env, readDataArray, r, f.read_bases, a[0], -1, true);
+        if (len < 0) { thrown = true; break; }
+        if (append_field(env, readDataArray, r, f.ins_gop, a[2], len, false) < 0 ||
+            append_field(env, readDataArray, r, f.del_gop, a[3], len, false) < 0 ||
+            append_field(env, readDataArray, r, f.gcp, a[4], len, false) < 0 ||
+            append_field(env, readDataArray, r, f.read_quals, a[1], len, false) < 0)
+          thrown = true;
+      }
+      if (thrown) break;
+      gklb_pairhmm_batch b;
+      b.n_reads = r1 - r0;
+      b.n_haps = n_haps;
+      b.read_off = a[0].off.data();
+      b.read_bases = a[0].bytes.data();
+      b.read_quals = a[1].bytes.data();
+      b.ins_gop = a[2].bytes.data();
+      b.del_gop = a[3].bytes.data();
+      b.gcp = a[4].bytes.data();
+      b.hap_off = hap.off.data();
+      b.hap_bases = hap.bytes.data();
+      rc = gklb_engine_submit(g_pipe.eng[k & 1], &b, out + (size_t)r0 * n_haps);
+    }
+    for (auto& e : g_pipe.eng) {
+      const int w = gklb_engine_wait(e);
+      if (rc == GKLB_OK) rc = w;
+    }
+    env->ReleaseDoubleArrayElements(likelihoodArray, out, (rc == GKLB_OK && !thrown) ? 0 : JNI_ABORT);
+    if (rc != GKLB_OK && !thrown) throw_status(env, rc);
+    return;
+  }
+
   for (int r = 0; r < n_reads; r++) {
     const int len = append_field(env, readDataArray, r, f.read_bases, bases, -1, true);
     if (len < 0) return;
@@ -169,6 +256,10 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihood
 JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_doneNative(JNIEnv* env, jobject obj) {
   (void)env;
   (void)obj;
+  {
+    std::lock_guard<std::mutex> lk(g_pipe_mu);
+    pipeline_reset();
+  }
   gklb_pairhmm_done();  // GKL's is empty; ours releases device memory, streams and events.  Idempotent.
 }
 

@@ -42,7 +42,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_pairhmm_devices_in_use",
            "gklb_pairhmm_last_stats", "gklb_engine_create",
-           "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_stage",
+           "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_submit", "gklb_engine_wait", "gklb_engine_stage",
            "gklb_engine_stage_device", "gklb_engine_update_haps_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
            "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
            "gklb_version", "gklb_device_count", "gklb_pairhmm_table"]
@@ -74,6 +74,8 @@ def lib() -> C.CDLL:
             getattr(l, name).argtypes = [C.c_void_p]
         l.gklb_engine_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         l.gklb_engine_compute.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
+        l.gklb_engine_submit.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_void_p]
+        l.gklb_engine_wait.argtypes = [C.c_void_p]
         l.gklb_engine_stage.argtypes = [C.c_void_p, C.POINTER(_Batch)]
         l.gklb_engine_stage_device.argtypes = [C.c_void_p, C.POINTER(_Batch)]
         l.gklb_engine_fetch.argtypes = [C.c_void_p, C.c_void_p]
@@ -159,6 +161,16 @@ class Engine:
         s = make_batch(b, arenas, hap)
         _check(lib().gklb_engine_compute(self._h, C.byref(s), out_ptr if out_ptr is not None else _ptr(out)))
         return out
+
+    def submit(self, b: PairHmmBatch, out: np.ndarray) -> None:
+        """Asynchronous compute: returns once everything is queued; `out` is filled by wait()."""
+        b.validate()
+        s = make_batch(b)
+        self._keep = (b, out)
+        _check(lib().gklb_engine_submit(self._h, C.byref(s), _ptr(out)))
+
+    def wait(self) -> None:
+        _check(lib().gklb_engine_wait(self._h))
 
     def stage(self, b: PairHmmBatch, arenas=None, hap=None, device: bool = False) -> None:
         b.validate()

@@ -125,6 +125,16 @@ GKLB_API int gklb_engine_set_stream(gklb_engine* e, void* cuda_stream);
 
 GKLB_API int gklb_engine_compute(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods);
 
+/* Asynchronous form of compute, for callers that have host work to overlap with the GPU (the JNI layer marshals
+ * the next block of reads while the previous one is being computed):
+ *   submit  validate, plan, queue the copies and kernels on the engine's stream, queue the device->host copy of the
+ *           likelihoods into a pinned buffer; returns without waiting.  Pageable input arenas may be reused as soon
+ *           as submit returns; pinned ones only after wait.
+ *   wait    block until the submitted batch is done and move the likelihoods into the array given to submit.
+ * One batch may be in flight per engine. */
+GKLB_API int gklb_engine_submit(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods);
+GKLB_API int gklb_engine_wait(gklb_engine* e);
+
 /* Three-phase form of compute, for measuring the device-resident path:
  *   stage         validate, plan (length classes, work units), copy arenas host->device  [async]
  *   stage_device  same, but the six arenas are already device pointers (copied device->device

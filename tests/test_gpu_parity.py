@@ -204,6 +204,21 @@ def test_staged_run_fetch_equals_compute(eng):
     assert np.array_equal(eng.fetch(b.n_reads * b.n_haps), a)
 
 
+def test_submit_wait_equals_compute(eng):
+    b1, b2 = synth.config2(300, 40, seed=11), synth.config2(200, 24, seed=12)
+    want1, want2 = eng.compute(b1), eng.compute(b2)
+    other = native.Engine(0, False)
+    o1, o2 = np.zeros(b1.n_reads * b1.n_haps), np.zeros(b2.n_reads * b2.n_haps)
+    eng.submit(b1, o1)      # two engines in flight at once, as the JNI layer's read-block pipeline uses them
+    other.submit(b2, o2)
+    with pytest.raises(native.GklbError):
+        eng.submit(b2, o2)  # one batch in flight per engine
+    eng.wait()
+    other.wait()
+    other.close()
+    assert np.array_equal(o1, want1) and np.array_equal(o2, want2)
+
+
 def test_device_resident_inputs(eng):
     import torch
     b = synth.config2(200, 32)

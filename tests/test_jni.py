@@ -70,6 +70,19 @@ def test_results_through_the_jni_path(use_double):
 
 
 @pytest.mark.gpu
+def test_large_calls_are_pipelined_in_read_blocks(monkeypatch):
+    # GKLB_JNI_BLOCK_READS=50: a 330-read call is marshalled and submitted in 7 blocks on two alternating engines
+    monkeypatch.setenv("GKLB_JNI_BLOCK_READS", "50")
+    b = synth.random_batch(62, 330, 9, read_len=(20, 140), hap_len=(60, 200), unrelated=0.1)
+    rc, out, cls, msg, leaks = jni_fake.pairhmm(LIB, b)
+    assert rc == 0 and leaks == (0, 0), (cls, msg)
+    ref = (oracle.ref_pairhmm if oracle.ref_available() else oracle.port_pairhmm)(b, threads=oracle.host_threads())[0]
+    assert (np.abs(out - ref) / np.abs(ref)).max() <= 1e-5
+    rc, _, cls, _, leaks = jni_fake.pairhmm(LIB, b, fault=2)  # a null read in the middle of block 3
+    assert rc == 1 and cls == "java/lang/NullPointerException" and leaks == (0, 0)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fault,cls", [(2, "java/lang/NullPointerException"), (3, "java/lang/OutOfMemoryError"),
                                        (4, "java/lang/IllegalArgumentException"), (6, "java/lang/IllegalArgumentException")])
 def test_fault_injection_maps_to_gkl_exception_classes(fault, cls):
