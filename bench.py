@@ -283,6 +283,11 @@ def run_ours(args):
             traffic = None
         cpu_gcups, cpu_info = cpu_arm(b, 1, 1)
         cpu_out = cpu_info["out"]
+        import oracle  # the CPU arm: one more figure, a single host thread on a 300-read slice of the same batch
+        one = b.read_slice(0, min(300, b.n_reads))
+        fn1 = oracle.ref_pairhmm if oracle.ref_available() else oracle.port_pairhmm
+        fn1(one, False, threads=1)
+        cpu_1t = one.cells() / fn1(one, False, threads=1)[2] / 1e9
         ok = np.isfinite(cpu_out)
         parity = float(np.max(np.abs(resident_out[ok] - cpu_out[ok]) / np.abs(cpu_out[ok])))
         parity_e2e = float(np.max(np.abs(host_out.numpy()[ok] - cpu_out[ok]) / np.abs(cpu_out[ok])))
@@ -313,6 +318,7 @@ def run_ours(args):
                                  "peak_source": hbm_src, "algorithmic_bytes_per_launch": algorithmic_bytes(b)},
                          "note": "scalar fp32 recurrence on CUDA cores: neither HBM nor tensor bound"},
             "cpu_baseline": {"value": cpu_gcups, "unit": UNIT, "cores": cpu_info["cores"], "kind": cpu_info["kind"],
+                             "value_1_thread": cpu_1t,
                              "sample": f"the full rank-0 batch once ({cpu_info['detail']}, all host threads, pair loop only, "
                                        f"{cpu_info['seconds_per_step']:.2f} s)"},
         }

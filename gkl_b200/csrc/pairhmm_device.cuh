@@ -13,26 +13,32 @@
 // How it is mapped to the machine (nothing like the reference's striped AVX code):
 //   * a GROUP of G lanes (G = 8, 16 or 32; 32/G groups per warp) sweeps one read (two reads
 //     when packed) against one haplotype as a systolic array: lane t owns K consecutive read
-//     rows, holds their seven transition/prior constants and the M/Y/X+Y state of the previous
-//     column in registers, and at step s processes column c = s - t, top row to bottom row;
+//     rows, holds their per-row constants and the state of the previous column in registers,
+//     and at step s processes column c = s - t, top row to bottom row;
 //   * the bottom row of lane t-1 reaches lane t with three __shfl_up_sync per step; the
 //     diagonal inputs are simply the previous step's shuffle results;
 //   * packed fp32 (VF2): each lane carries TWO reads in the halves of 64-bit register pairs and
 //     all arithmetic is FFMA2/FMUL2/FADD2 (sm_100 fma.rn.ftz.f32x2) -- half the issue slots of
-//     scalar FFMA, which is what bounds this recurrence (selects and shuffles co-issue);
+//     scalar FFMA;
+//   * the kernel is bound by register-file operand bandwidth, so the recurrence is rewritten to
+//     read fewer operands per cell than the reference's 8 mul + 4 add (template parameter VAR,
+//     see LaneRows): Y is kept as Y/pMY and the diagonal state as pGAPM(next row)*(X+Y) (VAR 2);
+//     the prior of every (row, haplotype symbol) comes from a per-warp shared-memory table with
+//     one LDS per cell instead of a LOP3 + FSEL (VAR 3); X is kept as X/pMX(row) (VAR 4/5, fp32
+//     only, with a non-finite-sum guard that falls back to the fp64 kernel).  VAR 0/1 are the
+//     plain forms, kept for measurement;
 //   * reads shorter than G*K rows are padded at the TOP with rows that reproduce row 0
 //     (A=G=pMX=pMY=0, pXX=pYY=1, Y(c=0)=init): the last read row is then always the last row
-//     of the last lane, so the running sum lives in one fixed register;
+//     of the last lane, so the running sum lives in fixed registers;
 //   * reads longer than G*K rows take several passes; the bottom row of a pass is carried to
 //     the next pass through a per-warp global scratch line (the analogue of the reference's
 //     shiftOut arrays, avx-pairhmm-template.h:249,313-317);
-//   * prior(r,c) is selected with one LOP3 (one-hot base nibbles AND) and two FSEL per cell
-//     from constants pre-multiplied per row ((1-e)*pMM, (e/3)*pMM, (1-e)*pGAPM, (e/3)*pGAPM);
 //   * the haplotype panel lives in shared memory as one image fetched with a single TMA bulk
 //     copy (cp.async.bulk + mbarrier) per CTA; the packed read records of each task are
 //     fetched the same way into a per-warp slot;
 //   * persistent CTAs (one per SM) pull tasks (a block of reads x a chunk of haplotypes) from
-//     an atomic counter -- the analogue of the reference's schedule(dynamic,1).
+//     an atomic counter -- the analogue of the reference's schedule(dynamic,1); batches with
+//     several length classes are served by one multi-class launch (k_mega_*).
 #pragma once
 
 #include <cuda_runtime.h>

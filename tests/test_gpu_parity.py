@@ -106,6 +106,21 @@ def test_random_batches_double_precision_mode(eng_d, seed, kw):
     assert rel(out, ref).max() <= 1e-9
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_fuzz_small_batches(eng, eng_d, seed):
+    rng = np.random.default_rng(1000 + seed)
+    n_reads, n_haps = int(rng.integers(1, 41)), int(rng.integers(1, 13))
+    rmax, hmax = int(rng.integers(1, 301)), int(rng.integers(1, 501))
+    b = synth.random_batch(2000 + seed, n_reads, n_haps, read_len=(1, rmax), hap_len=(1, hmax),
+                           low_quality=float(rng.random() * 0.3), n_frac=float(rng.random() * 0.1),
+                           unrelated=float(rng.random() * 0.5))
+    for e, dbl, tol in ((eng, False, REL_TOL), (eng_d, True, 1e-9)):
+        out, ref = e.compute(b), checker(b, dbl)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(out), ok)
+        assert rel(out[ok], ref[ok]).max() <= tol, (seed, dbl)
+
+
 def test_every_length_class_boundary(eng):
     # one read at each class capacity and one past it (32, 33, 40, 41, ... 256, 257, 512, 513)
     rng = np.random.default_rng(7)
