@@ -1,6 +1,6 @@
 """Measurement harness (GPU box): parity + GCUPS of every compiled kernel variant on a C2-shaped batch.
 
-    python bench/sweep.py [--reads 4000] [--haps 128] [--iters 3] [--variants all|product]
+    python bench/sweep.py [--reads 4000] [--haps 128] [--iters 3] [--variants all|product|list:v1;v2]
 
 Build the library with `make -C gkl_b200/csrc EXPERIMENTAL=1` to get the measurement-only variants.
 Parity is checked against oracle/_ref (GKL's own AVX code) when present, else the oracle port.
@@ -59,7 +59,12 @@ def main():
           f"= {cells / cpu_secs / 1e9:.2f} GCUPS (wall {time.time() - t0:.1f}s)", flush=True)
     Path(args.out).parent.mkdir(parents=True, exist_ok=True)
     rows = []
-    variants = [None] + (VARIANTS if args.variants == "all" else [])
+    if args.variants == "all":
+        variants = [None] + VARIANTS
+    elif args.variants.startswith("list:"):   # e.g. list:f2,16,7,12,5;f2,16,7,12,6
+        variants = [None] + [v for v in args.variants[5:].split(";") if v]
+    else:
+        variants = [None]
     for v in variants:
         if v is None:
             os.environ.pop("GKLB_FORCE_KERNEL", None)

@@ -336,6 +336,9 @@ struct Sweeper {
   V botX, sum, sumW;
   V uM, uX, uZ;           // bottom row of the lane above at this step's column
   V dMp, dZp;             // ... and at the previous column
+  V uM1, uX1, uZ1;        // VAR 6: bottom row of the lane above at the step's second column
+  V aM, aX, aZ;           // VAR 6: this lane's bottom row at the step's first column (the second one is the state)
+  uint32_t hb1;           // VAR 6: symbol byte of the step's second column
   V inj;                  // what row 0 feeds the first row's M update
   const uint8_t* hap;
   int haplen, c;
@@ -426,6 +429,130 @@ struct Sweeper {
         carry_out[2 * carry_pitch + c] = Zl[K - 1];
       }
     }
+  }
+
+
+  // ---- VAR 6: two columns per step (fp32 W form, no prior prefetch) ------------------------------------
+  // Lane t processes columns c and c + 1 (c = 2 (s - t) - 1) row by row; the second column's cells read the
+  // same per-row constants as the first one's in the same operand slots, which lets the operand-reuse cache
+  // take a third of the register reads away, and the two columns give two dependency chains per warp.
+  __device__ __forceinline__ void fetch_up2() {
+    uM = P::shfl_up(aM, G);
+    uX = P::shfl_up(aX, G);
+    uZ = P::shfl_up(aZ, G);
+    uM1 = P::shfl_up(Ml[K - 1], G);
+    uX1 = P::shfl_up(botX, G);
+    uZ1 = P::shfl_up(Zl[K - 1], G);
+    if (row0_above) {
+      uZ = inj;
+      uZ1 = inj;
+      uM = P::splat(0);
+      uM1 = P::splat(0);
+    }
+  }
+
+  template <bool GUARD>
+  __device__ __forceinline__ void cells2(const V* t0, const V* t1) {
+    V dM0 = dMp, dZ0 = dZp;       // row above, column c - 1
+    V upM0 = uM, upX0 = uX;       // row above, column c
+    V dZ1 = uZ;                   // ... its diagonal state (feeds column c + 1)
+    V upM1 = uM1, upX1 = uX1;     // row above, column c + 1
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const V p0 = t0[j * 32], p1 = t1[j * 32];
+      const V Xa = P::fma(L.pMX[j], upX0, upM0);
+      const V Xb = P::fma(L.pMX[j], upX1, upM1);
+      const V Ma = P::mul(p0, P::fma(L.Am[j], dM0, dZ0));
+      const V Mb = P::mul(p1, P::fma(L.Am[j], upM0, dZ1));
+      const V Ya = P::fma(L.pXX[j], Yl[j], Ml[j]);
+      const V Yb = P::fma(L.pXX[j], Ya, Ma);
+      const V Za = P::fma(L.pMY[j], Ya, P::mul(L.Ax[j], Xa));
+      const V Zb = P::fma(L.pMY[j], Yb, P::mul(L.Ax[j], Xb));
+      dM0 = Ml[j];
+      dZ0 = Zl[j];
+      upM0 = Ma;
+      upX0 = Xa;
+      dZ1 = Za;
+      upM1 = Mb;
+      upX1 = Xb;
+      Ml[j] = Mb;
+      Yl[j] = Yb;
+      Zl[j] = Zb;
+    }
+    aM = upM0;
+    aX = upX0;
+    aZ = dZ1;
+    botX = upX1;
+    sum = P::add(sum, upM0);
+    sumW = P::add(sumW, upX0);
+    if (!GUARD || c + 1 <= haplen) {  // an odd haplotype length ends on a first column
+      sum = P::add(sum, upM1);
+      sumW = P::add(sumW, upX1);
+    }
+  }
+
+  template <bool GUARD>
+  __device__ __forceinline__ void step2() {
+    const V* t0 = tb + (size_t)(hb & 7u) * (K * 32);
+    const V* t1 = tb + (size_t)(hb1 & 7u) * (K * 32);
+    const bool act = !GUARD || (unsigned)(c - 1) < (unsigned)haplen;
+    if (GUARD) {
+      hb = hap[min(max(c + 2, -kHapLeftMargin + 1), haplen + 1)];
+      hb1 = hap[min(max(c + 3, -kHapLeftMargin + 1), haplen + 1)];
+    } else {
+      hb = hap[c + 2];   // c + 3 <= haplen + 2: inside the right margin
+      hb1 = hap[c + 3];
+    }
+    if (act) cells2<GUARD>(t0, t1);
+    dMp = uM1;
+    dZp = uZ1;
+    c += 2;
+    fetch_up2();
+  }
+
+  __device__ __forceinline__ V run2(const uint8_t* hap_, int haplen_, int t, typename P::S initY, const V* tb_) {
+    tb = tb_;
+    const V zero = P::splat(0);
+    hap = hap_;
+    haplen = haplen_;
+    first = (t == 0);
+    last = (t == G - 1);
+    row0_above = first;
+    carry_in = nullptr;
+    carry_out = nullptr;
+    carry_pitch = 0;
+    const V initYv = P::splat(initY);
+    inj = P::mul(L.gTop, initYv);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      Ml[j] = zero;
+      V y0 = zero;
+#pragma unroll
+      for (int x = 0; x < P::NR; x++)
+        if (L.padmask[x] & (1u << j)) P::set(y0, x, initY);
+      Yl[j] = y0;
+      Zl[j] = P::mul(L.pMY[j], y0);
+    }
+    botX = zero;
+    sum = zero;
+    sumW = zero;
+    aM = zero;   // column 0 of the bottom row, as both of the "previous step's" columns
+    aX = zero;
+    aZ = Zl[K - 1];
+    dMp = zero;
+    dZp = row0_above ? inj : zero;
+    c = 1 - 2 * t;
+    hb = hap[max(c, -kHapLeftMargin + 1)];
+    hb1 = hap[max(c + 1, -kHapLeftMargin + 1)];
+    fetch_up2();
+    const int n_steps = (haplen + 1) / 2 + G - 1;
+    const int steady_end = haplen / 2;   // lane 0 (the most advanced) still has both columns inside
+    int s = 1;
+    const int pre_end = min(G - 1, n_steps);
+    for (; s <= pre_end; s++) step2<true>();
+    for (; s <= steady_end; s++) step2<false>();
+    for (; s <= n_steps; s++) step2<true>();
+    return P::fma(L.xlast, sumW, sum);
   }
 
   template <bool GUARD>
@@ -524,6 +651,9 @@ __device__ __forceinline__ typename P::V sweep(const LaneRows<P, K>& L, const ui
                                                const typename P::V* carry_in, typename P::V* carry_out,
                                                int carry_pitch, const typename P::V* tb = nullptr) {
   Sweeper<P, G, K, MULTI, VAR> sw(L);
+  if constexpr (VAR == 6 && !MULTI && !P::kDouble) {  // the two-column sweep is single-pass fp32 only
+    return sw.run2(hap, haplen, t, initY, tb);
+  }
   return sw.run(hap, haplen, steady_end, n_steps, t, initY, pass0, carry_in, carry_out, carry_pitch, tb);
 }
 

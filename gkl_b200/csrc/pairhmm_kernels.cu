@@ -86,6 +86,7 @@ static const KernelEntry g_table[] = {
     // ---- measurement only ----
     E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0),
     E_F2(16, 7, 8, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 7, 8, false, 5), E_F2(32, 5, 8, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 5), E_F2(8, 4, 16, false, 5),
+    E_F2(16, 7, 12, false, 6), E_F2(16, 7, 8, false, 6), E_F2(16, 7, 10, false, 6), E_F2(16, 7, 10, false, 5),
     E_F1(8, 13, 8, false, 4), E_F1(8, 13, 8, false, 3), E_F1(8, 13, 12, false, 4), E_F1(16, 7, 16, false, 4),
     E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3),
 #endif

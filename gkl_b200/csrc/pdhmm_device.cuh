@@ -409,4 +409,312 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// k_pdhmm2 -- the single-pass kernel (reads of at most 32*K rows), organised around the haplotype.
+//   * a task is one haplotype x a block of reads (cross layout: pair r * n_haps + h; flat layout: one pair): the
+//     column tables (bytes, allele bits, state codes, class masks, next-special index) are built once per task and
+//     reused by every read of the block -- the reference rebuilds its per-pair prior matrix for each pair;
+//   * the state a row starts in follows from the orbit of the 3-entry end-state map (pdhmm-serial.cc:306,370-385):
+//     its pre-period is at most 2 and its period divides 6, so eight entries describe every row;
+//   * steps whose whole window of columns is plain run without the state machine: the fill (s < 32) and drain
+//     (lane 0 past the last column) phases as guarded single steps, the steady phase as ping-pong pairs;
+//   * everything else (columns inside or just after a deletion span) takes the general step of k_pdhmm.
+// ------------------------------------------------------------------------------------------------------------
+template <int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, int read_block, int n_blocks,
+                                                          unsigned int n_tasks) {
+  constexpr int G = 32;
+  constexpr int CAP = G * K;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane;
+  const int col_pitch = (p.max_hap + 2 * kPdMargin + 1) & ~1;
+  uint8_t* gs = smem + (size_t)warp * 7 * col_pitch;
+  uint8_t* ys = gs + kPdMargin;
+  uint8_t* infos = gs + col_pitch + kPdMargin;
+  uint8_t* alleles = gs + 2 * col_pitch + kPdMargin;
+  uint16_t* nspec = reinterpret_cast<uint16_t*>(gs + 3 * col_pitch) + kPdMargin;
+  uint16_t* cmask = reinterpret_cast<uint16_t*>(gs + 5 * col_pitch) + kPdMargin;
+  const bool cross = p.n_haps > 0;
+  const bool first = (t == 0);
+
+  for (;;) {
+    unsigned int task = 0;
+    if (lane == 0) task = atomicAdd(p.counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= n_tasks) break;
+    long long hi, r_begin, r_end;
+    if (cross) {
+      hi = task / (unsigned)n_blocks;
+      const long long blk = task - hi * (unsigned)n_blocks;
+      const long long n_reads = p.n / p.n_haps;
+      r_begin = blk * read_block;
+      r_end = min(n_reads, r_begin + read_block);
+    } else {
+      hi = task;
+      r_begin = task;
+      r_end = r_begin + 1;
+    }
+    const int H = (int)p.hap_lengths[hi];
+    const int8_t* hap = p.hap_bases + hi * p.max_hap;
+    const int8_t* pd = p.hap_pdbases + hi * p.max_hap;
+
+    // ---- column tables of the haplotype (once per task) ----
+    __syncwarp();
+    for (int c = t - kPdMargin; c < p.max_hap + kPdMargin; c += G) {
+      uint8_t y = 0, al = 0;
+      if (c >= 1 && c <= H) {
+        y = (uint8_t)hap[c - 1];
+        const uint8_t f = (uint8_t)pd[c - 1];
+        al = (f & 1) ? (f & 0x78) : 0;
+      }
+      ys[c] = y;
+      alleles[c] = al;
+      infos[c] = 0;
+      cmask[c] = (uint16_t)((c >= 1 && c <= H) ? column_mask(y, al) : 0u);
+    }
+    __syncwarp();
+    int end_state = 0;
+    if (t == 0) {
+      int s0 = 0, s1 = 1, s2 = 2;
+      for (int c = 1; c <= H; c++) {
+        const uint8_t f = (uint8_t)pd[c - 1];
+        infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0));
+        if (s0 == 2) s0 = 0;
+        if (s1 == 2) s1 = 0;
+        if (s2 == 2) s2 = 0;
+        if (f & 2) s0 = s1 = s2 = 1;
+        if (f & 4) s0 = s1 = s2 = 2;
+      }
+      end_state = s0 | (s1 << 2) | (s2 << 4);
+      int reach = 1, st = 0;
+      if (p.carry_state)
+        for (int r = 0; r < 3; r++) { st = (end_state >> (2 * st)) & 3; reach |= 1 << st; }
+      const uint32_t rmask = ((reach & 1) ? 0x03u : 0u) | ((reach & 2) ? 0x0Cu : 0u) | ((reach & 4) ? 0x30u : 0u) | 0x40u;
+      uint32_t nxt = 0xFFFFu;
+      for (int c = p.max_hap + kPdMargin - 1; c >= -kPdMargin; c--) {
+        if (c >= 1 && c <= H && (infos[c] & rmask)) nxt = (uint32_t)c;
+        nspec[c] = (uint16_t)nxt;
+      }
+    }
+    end_state = __shfl_sync(0xffffffffu, end_state, 0);
+    __syncwarp();
+    // orbit[k] = state row k starts in for k < 8; rows >= 2 repeat with a period that divides 6
+    uint32_t orbit = 0;
+    if (p.carry_state) {
+      int st = 0;
+#pragma unroll
+      for (int k = 1; k < 8; k++) {
+        st = (end_state >> (2 * st)) & 3;
+        orbit |= (uint32_t)st << (2 * k);
+      }
+    }
+    const double init = p.init_cond / (double)H;
+    const int n_steps = H + G - 1;
+
+    for (long long ri = r_begin; ri < r_end; ri++) {
+      const long long item = cross ? ri * p.n_haps + hi : ri;
+      const int R = (int)p.read_lengths[ri];
+      const int64_t ro = ri * (int64_t)p.max_read;
+      const int n_pad = CAP - R;
+      // ---- per-row constants ----
+      double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];
+      uint32_t shift[K], rcls[K], xeq[K];
+      bool padrow[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int row = t * K + j - n_pad;
+        padrow[j] = row < 0;
+        tMM[j] = tIM[j] = tMI[j] = tMD[j] = 0.0;
+        tII[j] = 1.0;
+        pMa[j] = pMi[j] = 0.0;
+        shift[j] = 0;
+        rcls[j] = 15;
+        xeq[j] = 0x100;
+        if (!padrow[j]) {
+          const int8_t iq = p.read_ins_qual[ro + row], dq = p.read_del_qual[ro + row], gq = p.gcp[ro + row];
+          if (iq < 0 || dq < 0 || gq < 0) atomicOr(p.error_flag, 1u);
+          const int qi = iq & 0xFF, qd = dq & 0xFF, qg = gq & 0xFF, qq = p.read_qual[ro + row] & 0xFF;
+          const int mn = min(qi, qd), mx = max(qi, qd);
+          tMM[j] = (mx > 254) ? 1.0 - (pow(10.0, -0.1 * mn) + pow(10.0, -0.1 * mx))
+                              : __ldg(p.mm + ((mx * (mx + 1)) >> 1) + mn);
+          tMI[j] = __ldg(p.q2err + min(qi, 254));
+          tMD[j] = __ldg(p.q2err + min(qd, 254));
+          const double eg = __ldg(p.q2err + min(qg, 254));
+          tIM[j] = 1.0 - eg;
+          tII[j] = eg;
+          const double eq = __ldg(p.q2err + min(qq, 254));
+          pMa[j] = 1.0 - eq;
+          pMi[j] = eq / 3.0;
+          const uint32_t x = (uint8_t)p.read_bases[ro + row];
+          rcls[j] = read_class(x);
+          xeq[j] = (rcls[j] == 9) ? x : 0x100u;
+          const int k = (row < 8) ? row : 2 + ((row - 2) % 6);
+          shift[j] = 2u * ((orbit >> (2 * k)) & 3u);
+        }
+      }
+      double M[K], I[K], D[K], bM[K], bI[K], bD[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        M[j] = I[j] = bM[j] = bI[j] = bD[j] = 0.0;
+        D[j] = padrow[j] ? init : 0.0;
+      }
+      double gM = 0, gI = 0, gD = first ? init : 0.0, gbM = 0, gbI = 0, gbD = 0;
+      double sum = 0.0;
+      int c = 1 - t;
+      double uM, uI, uD, ubM = 0.0, ubI = 0.0, ubD = 0.0;
+      auto fetch_main = [&]() {
+        uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
+        if (first) { uM = uI = 0.0; uD = init; }   // row 0: D = init, everything else 0
+      };
+      auto fetch_twins = [&]() {
+        ubM = shfl_up_d(bM[K - 1], G); ubI = shfl_up_d(bI[K - 1], G); ubD = shfl_up_d(bD[K - 1], G);
+        if (first) ubM = ubI = ubD = 0.0;
+      };
+      fetch_main();
+      fetch_twins();
+      int s = 1;
+      while (s <= n_steps) {
+        // lane 0 is at column s, lane 31 at s - 31.  A run of steps needs no state machine while the window
+        // [s - 32, s + 1] holds no special column (the +1 keeps one general step between a run and the next
+        // special column, which re-establishes the diagonal twins).
+        const int first_special = nspec[max(s - G, -kPdMargin)];
+        int n_run = min(first_special - (s + 1), n_steps - s + 1);
+        n_run = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(n_run, 0));  // identical on all lanes
+        if (n_run > 0) {
+          const int s_end = s + n_run;
+          // one guarded plain step, in place; the twins of a plain column are the previous column's values
+          auto single = [&]() {
+            if ((unsigned)(c - 1) < (unsigned)H) {
+              const uint32_t y = ys[c], cm = cmask[c];
+              double tM = uM, tI = uI;
+              double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const double lM = M[j], lI = I[j], lD = D[j];
+                const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+                const double prior = match ? pMa[j] : pMi[j];
+                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+                const double nD = lM * tMD[j] + lD * tII[j];
+                const double nI = tM * tMI[j] + tI * tII[j];
+                dM = lM; dI = lI; dD = lD;
+                bM[j] = lM; bI[j] = lI; bD[j] = lD;
+                M[j] = nM; I[j] = nI; D[j] = nD;
+                tM = nM; tI = nI;
+              }
+              sum += M[K - 1] + I[K - 1];
+            }
+            gM = uM; gI = uI; gD = uD;
+            c++;
+            s++;
+            fetch_main();
+          };
+          while (s < s_end && s < G) single();                       // fill
+          const int n_fast = max(0, min(s_end - s, H - s + 1)) & ~1;  // every lane inside the haplotype
+          if (n_fast > 0) {
+            double M2[K], I2[K], D2[K];
+            auto half = [&](const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K], double (&Mo)[K],
+                            double (&Io)[K], double (&Do)[K]) {
+              const uint32_t y = ys[c], cm = cmask[c];
+              double tM = uM, tI = uI;
+              double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+                const double prior = match ? pMa[j] : pMi[j];
+                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+                const double nD = Mi[j] * tMD[j] + Di[j] * tII[j];
+                const double nI = tM * tMI[j] + tI * tII[j];
+                dM = Mi[j]; dI = Ii[j]; dD = Di[j];
+                Mo[j] = nM; Io[j] = nI; Do[j] = nD;
+                tM = nM; tI = nI;
+              }
+              sum += Mo[K - 1] + Io[K - 1];
+              gM = uM; gI = uI; gD = uD;
+              c++;
+              uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
+              if (first) { uM = uI = 0.0; uD = init; }
+            };
+            for (int k = 0; k < n_fast; k += 2) {
+              half(M, I, D, M2, I2, D2);
+              half(M2, I2, D2, M, I, D);
+            }
+#pragma unroll
+            for (int j = 0; j < K; j++) { bM[j] = M2[j]; bI[j] = I2[j]; bD[j] = D2[j]; }
+            s += n_fast;
+          }
+          while (s < s_end) single();                                  // odd step, drain
+          // the twins of the lane above were not exchanged during the run; the next (general) step needs them
+          // as its top values -- its diagonal twins are only read on special columns, which by construction
+          // of the window are at least one general step away
+          fetch_twins();
+          gbM = gbI = gbD = 0.0;
+          continue;
+        }
+        // ---- one general step (as in k_pdhmm) ----
+        const bool inrange = (unsigned)(c - 1) < (unsigned)H;
+        const uint32_t info = inrange ? infos[c] : 0u;
+        bool merge_lane = (info & 0x40u) != 0;
+#pragma unroll
+        for (int j = 0; j < K; j++) merge_lane |= ((info >> shift[j]) & 3u) == 2u;
+        const bool merge = __any_sync(0xffffffffu, merge_lane);
+        if (inrange) {
+          const uint32_t y = ys[c], cm = cmask[c];
+          if (!merge) {
+            double tM = uM, tI = uI;
+            double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const bool inside = ((info >> shift[j]) & 3u) == 1u;
+              const double lM = M[j], lI = I[j], lD = D[j];
+              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const double prior = match ? pMa[j] : pMi[j];
+              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+              const double nD = lM * tMD[j] + lD * tII[j];
+              const double nI = tM * tMI[j] + tI * tII[j];
+              dM = lM; dI = lI; dD = lD;
+              bM[j] = inside ? bM[j] : lM; bI[j] = inside ? bI[j] : lI; bD[j] = inside ? bD[j] : lD;
+              M[j] = nM; I[j] = nI; D[j] = nD;
+              tM = nM; tI = nI;
+            }
+          } else {
+            const bool del_end = (info & 0x40u) != 0;
+            double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
+            double dM = gM, dI = gI, dD = gD, dbM = gbM, dbI = gbI, dbD = gbD;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const uint32_t st = (info >> shift[j]) & 3u;
+              const bool inside = st == 1u, after = st == 2u;
+              const double lM = M[j], lI = I[j], lD = D[j];
+              const double lbM = bM[j], lbI = bI[j], lbD = bD[j];
+              const double mxM = fmax(lbM, lM), mxI = fmax(lbI, lI), mxD = fmax(lbD, lD);
+              const double nbM = after ? mxM : (inside ? lbM : lM);
+              const double nbI = after ? mxI : (inside ? lbI : lI);
+              const double nbD = after ? mxD : (inside ? lbD : lD);
+              const double eM = after ? fmax(dM, dbM) : dM, eI = after ? fmax(dI, dbI) : dI, eD = after ? fmax(dD, dbD) : dD;
+              const double leftM = after ? mxM : lM, leftD = after ? mxD : lD;
+              const double topM = del_end ? fmax(tbM, tM) : tM, topI = del_end ? fmax(tbI, tI) : tI;
+              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const double prior = match ? pMa[j] : pMi[j];
+              const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
+              const double nD = leftM * tMD[j] + leftD * tII[j];
+              const double nI = topM * tMI[j] + topI * tII[j];
+              dM = lM; dI = lI; dD = lD; dbM = lbM; dbI = lbI; dbD = lbD;
+              M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
+              tM = nM; tI = nI; tbM = nbM; tbI = nbI;
+            }
+          }
+          sum += M[K - 1] + I[K - 1];
+        }
+        gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
+        c++;
+        s++;
+        fetch_main();
+        fetch_twins();
+      }
+      if (t == G - 1) p.out[item] = log10(sum) - p.log10_init;
+    }
+  }
+}
+
 }  // namespace gklb

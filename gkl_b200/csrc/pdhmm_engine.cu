@@ -90,6 +90,10 @@ struct PdEngine {
   bool have_last = false;
   size_t last_smem = 0;
   int last_grid = 0;
+  // k_pdhmm2 (single pass, haplotype-major tasks): reads per task, blocks per haplotype, tasks
+  bool use_v2 = false, allow_v2 = true;
+  int read_block = 1, n_blocks = 1;
+  unsigned int n_tasks = 0;
   gklb_pdhmm_stats stats{};
 };
 
@@ -111,6 +115,13 @@ void destroy(PdEngine* e) {
 
 int launch(PdEngine* e) {
   CU(cudaMemsetAsync(e->misc.p, 0, 8, e->stream));
+  if (e->use_v2) {
+    void* args2[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks};
+    CU(cudaLaunchKernel(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps>), dim3(e->last_grid), dim3(kWarps * 32),
+                        args2, e->last_smem, e->stream));
+    e->stats.kernel_launches++;
+    return GKLB_OK;
+  }
   void* args[] = {&e->last};
   const void* fn = (e->last.max_read <= kG * kK) ? reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, false>)
                                                  : reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>);
@@ -199,7 +210,26 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   p.carry_stride = carry_stride;
   p.carry_state = e->carry_state;
   e->last_smem = smem;
-  const long long warp_items = (n + gpw - 1) / gpw;
+  long long warp_items = (n + gpw - 1) / gpw;
+  // Reads that fit one pass take the haplotype-major kernel: a task is one haplotype x a block of reads, sized for
+  // about 16 tasks per resident warp so that the dynamic queue balances the load.
+  e->use_v2 = e->allow_v2 && b->max_read <= kG * kK;
+  if (e->use_v2) {
+    if (cross) {
+      const long long want = 16LL * kWarps * e->num_sms;
+      long long nb = std::min<long long>(n_reads, std::max<long long>(1, (want + n_haps - 1) / n_haps));
+      e->read_block = (int)((n_reads + nb - 1) / nb);
+      e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
+      warp_items = (long long)e->n_blocks * n_haps;
+    } else {
+      e->read_block = 1;
+      e->n_blocks = 1;
+      warp_items = n;
+    }
+    if (warp_items > 0xFFFFFFF0LL) e->use_v2 = false;  // the task counter is 32 bits wide
+    e->n_tasks = (unsigned int)warp_items;
+  }
+  if (!e->use_v2) warp_items = (n + gpw - 1) / gpw;
   e->last_grid = (int)std::min<long long>(e->num_sms, (warp_items + kWarps - 1) / kWarps);
   e->have_last = true;
   e->stats = gklb_pdhmm_stats{};
@@ -246,11 +276,15 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
   e->num_sms = prop.multiProcessorCount;
   const char* rs = getenv("GKLB_PDHMM_ROW_STATE");
   e->carry_state = (rs && !strcmp(rs, "reset")) ? 0 : 1;
+  const char* kv = getenv("GKLB_PDHMM_KERNEL");  // "1": the pair-at-a-time kernel for every batch (measurement)
+  e->allow_v2 = !(kv && !strcmp(kv, "1"));
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) CU(cudaEventCreate(&ev));
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, false>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
+                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));

@@ -77,3 +77,75 @@ def test_row_reset_semantics_switch():
         os.environ.pop("GKLB_PDHMM_ROW_STATE")
     reset = oracle.port_pdhmm(b, False, threads=oracle.host_threads())[0]
     assert np.abs(got - reset).max() <= 1e-9
+
+
+def _truncated_pairs(b, max_rows):
+    """The pairs of a flat batch with every read cut to its first 60..max_rows rows."""
+    pairs = []
+    for k in range(b.n):
+        hl, rl = int(b.hap_lengths[k]), min(int(b.read_lengths[k]), 60 + k % (max_rows - 59))
+        h0, r0 = k * b.max_hap, k * b.max_read
+        pairs.append((b.hap_bases[h0:h0 + hl], b.hap_pdbases[h0:h0 + hl], b.read_bases[r0:r0 + rl],
+                      b.read_qual[r0:r0 + rl], b.read_ins_qual[r0:r0 + rl], b.read_del_qual[r0:r0 + rl],
+                      b.gcp[r0:r0 + rl]))
+    return pb.PdhmmBatch.from_pairs(pairs)
+
+
+@pytest.mark.parametrize("row_state", ["carry", "reset"])
+def test_single_pass_kernel_on_the_hardest_golden_pairs(row_state):
+    """Reads of at most 128 rows take the haplotype-major kernel (k_pdhmm2).  The synthetic golden file has random PD
+    bytes (nested / unclosed spans, negative bytes), lower-case bases and quals up to 93, but only reads of 223+ rows:
+    cut its reads to 60..128 rows and run them through that kernel in both row-state modes, and through the
+    pair-at-a-time kernel, and compare everything with the restatement of the reference's scalar path."""
+    full, _ = pb.load_pdhmm_pairs_file(GOLDEN / "pdhmm_syn_1412_129_223.txt.gz")
+    b = _truncated_pairs(full, 128)
+    assert b.max_read == 128 and b.n == full.n
+    ref = oracle.port_pdhmm(b, row_state == "carry", threads=oracle.host_threads())[0]
+    got = {}
+    for kernel in ("2", "1"):
+        os.environ["GKLB_PDHMM_ROW_STATE"] = row_state
+        os.environ["GKLB_PDHMM_KERNEL"] = kernel
+        try:
+            h = IntelPDHMM()
+            h.initialize(None)
+            got[kernel] = h.compute_batch(b)
+            h.done()
+        finally:
+            os.environ.pop("GKLB_PDHMM_ROW_STATE")
+            os.environ.pop("GKLB_PDHMM_KERNEL")
+    assert np.abs(got["2"] - ref).max() <= 1e-9
+    assert np.abs(got["1"] - ref).max() <= 1e-9
+    assert np.array_equal(got["1"], got["2"])  # same arithmetic, cell for cell
+
+
+def test_single_pass_kernel_cross_layout_blocks():
+    """Cross layout (computeLikelihoods): a task of k_pdhmm2 is one haplotype x a block of reads; ragged read counts,
+    one-column haplotypes and PD spans at the haplotype ends must land at r * H + h."""
+    from gkl_b200 import synth
+    reads, haps = synth.config5(77, 19, seed=11)
+    rng = np.random.default_rng(5)
+    # shorten some reads / haplotypes, put spans at the very ends
+    cut = [int(rng.integers(1, len(r[0]) + 1)) if i % 5 == 0 else len(r[0]) for i, r in enumerate(reads)]
+    reads = [tuple(x[:n] for x in r) for r, n in zip(reads, cut)]
+    haps = list(haps)
+    haps[0] = (haps[0][0][:1], np.array([6], dtype=np.int8))
+    haps[1] = (haps[1][0][:2], np.array([2, 4], dtype=np.int8))
+    hb, pdb = haps[2][0].copy(), haps[2][1].copy()
+    pdb[-1] = 2   # a deletion that opens on the last column and never closes: the row-carry corner (P3)
+    haps[2] = (hb, pdb)
+    hb, pdb = haps[3][0].copy(), haps[3][1].copy()
+    pdb[0] = 2
+    pdb[3] = 4
+    haps[3] = (hb, pdb)
+    flat = pb.PdhmmBatch.cross(reads, haps)
+    ref = oracle.port_pdhmm(flat, True, threads=oracle.host_threads())[0]
+    rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
+    hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
+    h = IntelPDHMM()
+    h.initialize(None)
+    out = np.zeros(len(rd) * len(hp))
+    h.computeLikelihoods(rd, hp, out)
+    flat_out = h.compute_batch(flat)
+    h.done()
+    assert np.abs(out - ref).max() <= 1e-9
+    assert np.abs(flat_out - ref).max() <= 1e-9
