@@ -479,7 +479,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
       int s0 = 0, s1 = 1, s2 = 2;
       for (int c = 1; c <= H; c++) {
         const uint8_t f = (uint8_t)pd[c - 1];
-        infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0));
+        // bit 7: the twins written on this column are read later (it opens or closes a span outside a deletion)
+        infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0) | ((s0 != 1 && (f & 6)) ? 0x80 : 0));
         if (s0 == 2) s0 = 0;
         if (s1 == 2) s1 = 0;
         if (s2 == 2) s2 = 0;
@@ -583,8 +584,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
         n_run = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(n_run, 0));  // identical on all lanes
         if (n_run > 0) {
           const int s_end = s + n_run;
-          // one guarded plain step, in place; the twins of a plain column are the previous column's values
-          auto single = [&]() {
+          // one guarded plain step, in place.  The twins of a plain column are the previous column's values; nothing
+          // reads them during a run, so only the last step of a run stores them.
+          auto single = [&](bool save_twins) {
             if ((unsigned)(c - 1) < (unsigned)H) {
               const uint32_t y = ys[c], cm = cmask[c];
               double tM = uM, tI = uI;
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
                 const double nD = lM * tMD[j] + lD * tII[j];
                 const double nI = tM * tMI[j] + tI * tII[j];
                 dM = lM; dI = lI; dD = lD;
-                bM[j] = lM; bI[j] = lI; bD[j] = lD;
+                if (save_twins) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
                 M[j] = nM; I[j] = nI; D[j] = nD;
                 tM = nM; tI = nI;
               }
@@ -609,8 +611,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             s++;
             fetch_main();
           };
-          while (s < s_end && s < G) single();                       // fill
-          const int n_fast = max(0, min(s_end - s, H - s + 1)) & ~1;  // every lane inside the haplotype
+          while (s < s_end && s < G) {                                // fill: lanes enter one by one
+            const bool last_of_run = (s + 1 == s_end);
+            single(last_of_run);
+          }
+          // steady and drain: every lane has reached column 1; lanes past the last column compute values nobody
+          // reads (their sums are masked, the column tables have margins)
+          const int n_fast = max(0, s_end - s) & ~1;
           if (n_fast > 0) {
             double M2[K], I2[K], D2[K];
             auto half = [&](const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K], double (&Mo)[K],
@@ -629,7 +636,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
                 Mo[j] = nM; Io[j] = nI; Do[j] = nD;
                 tM = nM; tI = nI;
               }
-              sum += Mo[K - 1] + Io[K - 1];
+              const double add = Mo[K - 1] + Io[K - 1];
+              sum += (c <= H) ? add : 0.0;
               gM = uM; gI = uI; gD = uD;
               c++;
               uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
@@ -643,7 +651,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             for (int j = 0; j < K; j++) { bM[j] = M2[j]; bI[j] = I2[j]; bD[j] = D2[j]; }
             s += n_fast;
           }
-          while (s < s_end) single();                                  // odd step, drain
+          while (s < s_end) single(true);                              // the odd step of a run
           // the twins of the lane above were not exchanged during the run; the next (general) step needs them
           // as its top values -- its diagonal twins are only read on special columns, which by construction
           // of the window are at least one general step away
@@ -651,9 +659,64 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
           gbM = gbI = gbD = 0.0;
           continue;
         }
-        // ---- one general step (as in k_pdhmm) ----
         const bool inrange = (unsigned)(c - 1) < (unsigned)H;
         const uint32_t info = inrange ? infos[c] : 0u;
+        if (orbit == 0) {
+          // ---- one special-window step when every row starts NORMAL (always, unless the haplotype ends inside a
+          // deletion): the column state is the same for all rows, so the state machine reduces to the plain update
+          // plus three per-lane corrections.  AFTER_DEL: the left and diagonal inputs are first merged with their
+          // twins (pdhmm-serial.cc:330-352), after which the column behaves like a NORMAL one.  INSIDE_DEL: the
+          // twins stay frozen.  DEL_END: the insertion chain is redone with max(twin, value) tops (:362-365).  The
+          // twins are only stored where a later column reads them (bit 7 of the column code). ----
+          const uint32_t st = info & 3u;
+          const bool after = st == 2u, del_end = (info & 0x40u) != 0, capture = (info & 0x80u) != 0;
+          if (__any_sync(0xffffffffu, after)) {
+            if (after) {
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                M[j] = fmax(bM[j], M[j]); I[j] = fmax(bI[j], I[j]); D[j] = fmax(bD[j], D[j]);
+              }
+              gM = fmax(gM, gbM); gI = fmax(gI, gbI); gD = fmax(gD, gbD);
+            }
+          }
+          if (inrange) {
+            const uint32_t y = ys[c], cm = cmask[c];
+            double tM = uM, tI = uI;
+            double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              const double lM = M[j], lI = I[j], lD = D[j];
+              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const double prior = match ? pMa[j] : pMi[j];
+              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+              const double nD = lM * tMD[j] + lD * tII[j];
+              const double nI = tM * tMI[j] + tI * tII[j];
+              dM = lM; dI = lI; dD = lD;
+              if (capture) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
+              M[j] = nM; I[j] = nI; D[j] = nD;
+              tM = nM; tI = nI;
+            }
+          }
+          if (__any_sync(0xffffffffu, del_end)) {
+            if (del_end) {
+              double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const double nI = fmax(tbM, tM) * tMI[j] + fmax(tbI, tI) * tII[j];
+                I[j] = nI;
+                tM = M[j]; tI = nI; tbM = bM[j]; tbI = bI[j];
+              }
+            }
+          }
+          if (inrange) sum += M[K - 1] + I[K - 1];
+          gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
+          c++;
+          s++;
+          fetch_main();
+          fetch_twins();
+          continue;
+        }
+        // ---- one general step (as in k_pdhmm): rows of one lane may sit in different states ----
         bool merge_lane = (info & 0x40u) != 0;
 #pragma unroll
         for (int j = 0; j < K; j++) merge_lane |= ((info >> shift[j]) & 3u) == 2u;
