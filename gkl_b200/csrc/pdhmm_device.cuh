@@ -20,6 +20,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace gklb {
 
 constexpr int kPdMargin = 40;  // zero columns on both sides of a haplotype in shared memory
@@ -420,6 +422,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
 //     (lane 0 past the last column) phases as guarded single steps, the steady phase as ping-pong pairs;
 //   * everything else (columns inside or just after a deletion span) takes the general step of k_pdhmm.
 // ------------------------------------------------------------------------------------------------------------
+// The reference merges with std::max on non-negative finite doubles (pdhmm-serial.cc:330-365): a compare and a select,
+// without fmax's NaN handling.
+__device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, int read_block, int n_blocks,
                                                           unsigned int n_tasks) {
@@ -586,7 +592,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
           const int s_end = s + n_run;
           // one guarded plain step, in place.  The twins of a plain column are the previous column's values; nothing
           // reads them during a run, so only the last step of a run stores them.
-          auto single = [&](bool save_twins) {
+          auto single = [&](auto save_twins) {
             if ((unsigned)(c - 1) < (unsigned)H) {
               const uint32_t y = ys[c], cm = cmask[c];
               double tM = uM, tI = uI;
@@ -600,7 +606,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
                 const double nD = lM * tMD[j] + lD * tII[j];
                 const double nI = tM * tMI[j] + tI * tII[j];
                 dM = lM; dI = lI; dD = lD;
-                if (save_twins) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
+                if constexpr (decltype(save_twins)::value) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
                 M[j] = nM; I[j] = nI; D[j] = nD;
                 tM = nM; tI = nI;
               }
@@ -612,8 +618,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             fetch_main();
           };
           while (s < s_end && s < G) {                                // fill: lanes enter one by one
-            const bool last_of_run = (s + 1 == s_end);
-            single(last_of_run);
+            if (s + 1 == s_end) single(std::true_type{});
+            else single(std::false_type{});
           }
           // steady and drain: every lane has reached column 1; lanes past the last column compute values nobody
           // reads (their sums are masked, the column tables have margins)
@@ -651,7 +657,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             for (int j = 0; j < K; j++) { bM[j] = M2[j]; bI[j] = I2[j]; bD[j] = D2[j]; }
             s += n_fast;
           }
-          while (s < s_end) single(true);                              // the odd step of a run
+          while (s < s_end) single(std::true_type{});                            // the odd step of a run
           // the twins of the lane above were not exchanged during the run; the next (general) step needs them
           // as its top values -- its diagonal twins are only read on special columns, which by construction
           // of the window are at least one general step away
@@ -671,13 +677,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
           const uint32_t st = info & 3u;
           const bool after = st == 2u, del_end = (info & 0x40u) != 0, capture = (info & 0x80u) != 0;
           if (__any_sync(0xffffffffu, after)) {
-            if (after) {
 #pragma unroll
-              for (int j = 0; j < K; j++) {
-                M[j] = fmax(bM[j], M[j]); I[j] = fmax(bI[j], I[j]); D[j] = fmax(bD[j], D[j]);
-              }
-              gM = fmax(gM, gbM); gI = fmax(gI, gbI); gD = fmax(gD, gbD);
+            for (int j = 0; j < K; j++) {
+              M[j] = (after && M[j] < bM[j]) ? bM[j] : M[j];
+              I[j] = (after && I[j] < bI[j]) ? bI[j] : I[j];
+              D[j] = (after && D[j] < bD[j]) ? bD[j] : D[j];
             }
+            gM = (after && gM < gbM) ? gbM : gM;
+            gI = (after && gI < gbI) ? gbI : gI;
+            gD = (after && gD < gbD) ? gbD : gD;
           }
           if (inrange) {
             const uint32_t y = ys[c], cm = cmask[c];
@@ -698,17 +706,18 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             }
           }
           if (__any_sync(0xffffffffu, del_end)) {
-            if (del_end) {
-              double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
+            double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
 #pragma unroll
-              for (int j = 0; j < K; j++) {
-                const double nI = fmax(tbM, tM) * tMI[j] + fmax(tbI, tI) * tII[j];
-                I[j] = nI;
-                tM = M[j]; tI = nI; tbM = bM[j]; tbI = bI[j];
-              }
+            for (int j = 0; j < K; j++) {
+              const double nI = dmax(tbM, tM) * tMI[j] + dmax(tbI, tI) * tII[j];
+              I[j] = del_end ? nI : I[j];
+              tM = M[j]; tI = I[j]; tbM = bM[j]; tbI = bI[j];
             }
           }
-          if (inrange) sum += M[K - 1] + I[K - 1];
+          {
+            const double add = M[K - 1] + I[K - 1];
+            sum += inrange ? add : 0.0;
+          }
           gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
           c++;
           s++;
@@ -750,13 +759,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               const bool inside = st == 1u, after = st == 2u;
               const double lM = M[j], lI = I[j], lD = D[j];
               const double lbM = bM[j], lbI = bI[j], lbD = bD[j];
-              const double mxM = fmax(lbM, lM), mxI = fmax(lbI, lI), mxD = fmax(lbD, lD);
+              const double mxM = dmax(lbM, lM), mxI = dmax(lbI, lI), mxD = dmax(lbD, lD);
               const double nbM = after ? mxM : (inside ? lbM : lM);
               const double nbI = after ? mxI : (inside ? lbI : lI);
               const double nbD = after ? mxD : (inside ? lbD : lD);
-              const double eM = after ? fmax(dM, dbM) : dM, eI = after ? fmax(dI, dbI) : dI, eD = after ? fmax(dD, dbD) : dD;
+              const double eM = after ? dmax(dM, dbM) : dM, eI = after ? dmax(dI, dbI) : dI, eD = after ? dmax(dD, dbD) : dD;
               const double leftM = after ? mxM : lM, leftD = after ? mxD : lD;
-              const double topM = del_end ? fmax(tbM, tM) : tM, topI = del_end ? fmax(tbI, tI) : tI;
+              const double topM = del_end ? dmax(tbM, tM) : tM, topI = del_end ? dmax(tbI, tI) : tI;
               const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
               const double prior = match ? pMa[j] : pMi[j];
               const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
