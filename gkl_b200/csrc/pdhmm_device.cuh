@@ -425,6 +425,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
 // The reference merges with std::max on non-negative finite doubles (pdhmm-serial.cc:330-365): a compare and a select,
 // without fmax's NaN handling.
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+// (cond && a < b) ? b : a with the condition folded into the compare (one DSETP + one 64-bit select)
+__device__ __forceinline__ double dmax_if(double a, double b, bool cond) {
+  double r;
+  asm("{\n\t.reg .pred p, c;\n\tsetp.ne.u32 c, %3, 0;\n\tsetp.lt.and.f64 p, %1, %2, c;\n\tselp.f64 %0, %2, %1, p;\n\t}"
+      : "=d"(r) : "d"(a), "d"(b), "r"((unsigned)cond));
+  return r;
+}
 
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, int read_block, int n_blocks,
@@ -679,32 +686,38 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
           if (__any_sync(0xffffffffu, after)) {
 #pragma unroll
             for (int j = 0; j < K; j++) {
-              M[j] = (after && M[j] < bM[j]) ? bM[j] : M[j];
-              I[j] = (after && I[j] < bI[j]) ? bI[j] : I[j];
-              D[j] = (after && D[j] < bD[j]) ? bD[j] : D[j];
+              M[j] = dmax_if(M[j], bM[j], after);
+              I[j] = dmax_if(I[j], bI[j], after);
+              D[j] = dmax_if(D[j], bD[j], after);
             }
-            gM = (after && gM < gbM) ? gbM : gM;
-            gI = (after && gI < gbI) ? gbI : gI;
-            gD = (after && gD < gbD) ? gbD : gD;
+            gM = dmax_if(gM, gbM, after);
+            gI = dmax_if(gI, gbI, after);
+            gD = dmax_if(gD, gbD, after);
           }
-          if (inrange) {
-            const uint32_t y = ys[c], cm = cmask[c];
-            double tM = uM, tI = uI;
-            double dM = gM, dI = gI, dD = gD;
+          // the plain update; once every lane has started (s >= 32) nothing has to be protected: lanes past the last
+          // column compute values nobody reads
+          auto update = [&](auto guarded) {
+            if (!decltype(guarded)::value || inrange) {
+              const uint32_t y = ys[c], cm = cmask[c];
+              double tM = uM, tI = uI;
+              double dM = gM, dI = gI, dD = gD;
 #pragma unroll
-            for (int j = 0; j < K; j++) {
-              const double lM = M[j], lI = I[j], lD = D[j];
-              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
-              const double prior = match ? pMa[j] : pMi[j];
-              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-              const double nD = lM * tMD[j] + lD * tII[j];
-              const double nI = tM * tMI[j] + tI * tII[j];
-              dM = lM; dI = lI; dD = lD;
-              if (capture) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
-              M[j] = nM; I[j] = nI; D[j] = nD;
-              tM = nM; tI = nI;
+              for (int j = 0; j < K; j++) {
+                const double lM = M[j], lI = I[j], lD = D[j];
+                const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+                const double prior = match ? pMa[j] : pMi[j];
+                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
+                const double nD = lM * tMD[j] + lD * tII[j];
+                const double nI = tM * tMI[j] + tI * tII[j];
+                dM = lM; dI = lI; dD = lD;
+                if (capture) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
+                M[j] = nM; I[j] = nI; D[j] = nD;
+                tM = nM; tI = nI;
+              }
             }
-          }
+          };
+          if (s >= G) update(std::false_type{});
+          else update(std::true_type{});
           if (__any_sync(0xffffffffu, del_end)) {
             double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
 #pragma unroll
