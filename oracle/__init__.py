@@ -167,3 +167,44 @@ def port_tables():
         "ph2pr_d": np.ctypeslib.as_array(lib.gklport_ph2pr_d(), shape=(128,)).copy(),
         "mm_d": np.ctypeslib.as_array(lib.gklport_mm_d(), shape=(mm_size,)).copy(),
     }
+
+
+# ---- Smith-Waterman (smithwaterman/PairWiseSW.h) ----
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def _sw_call(fn, extra, seq1, off1, seq2, off2, params, strategy, threads):
+    n = len(off1) - 1
+    len1, len2 = np.diff(off1), np.diff(off2)
+    pitch = int(2 * max(int(len1.max(initial=1)), int(len2.max(initial=1))))
+    cig = np.zeros((n, pitch), dtype=np.uint8)
+    clen = np.zeros(n, dtype=np.int32)
+    offs = np.zeros(n, dtype=np.int32)
+    secs = C.c_double(0)
+    rc = fn(n, seq1, off1, seq2, off2, *[int(v) for v in params], int(strategy), *extra, int(threads),
+            cig.ctypes.data_as(C.c_void_p), pitch, clen, offs, *([None] if extra else []), C.byref(secs))
+    if rc != 0:
+        raise MemoryError(f"smith-waterman oracle failed: {rc}")
+    cigars = [bytes(cig[k, :clen[k]]).decode("ascii") for k in range(n)]
+    return cigars, offs, secs.value
+
+
+def port_sw(seq1, off1, seq2, off2, params, strategy: int, threads: int = 1):
+    """CPU restatement (oracle/sw_oracle.c).  seq1/seq2: uint8 arenas, off1/off2: int64[n+1]; params = (match,
+    mismatch, open, extend); strategy 9 SOFTCLIP, 10 INDEL, 11 LEADING_INDEL, 12 IGNORE.
+    Returns (cigar strings, alignment offsets int32[n], seconds)."""
+    lib = _load_port()
+    lib.gklport_sw.restype = C.c_int
+    lib.gklport_sw.argtypes = [C.c_int, _u8p, _i64p, _u8p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                               C.c_void_p, C.c_int, _i32p, _i32p, C.POINTER(C.c_double)]
+    return _sw_call(lib.gklport_sw, (), seq1, off1, seq2, off2, params, strategy, threads)
+
+
+def ref_sw(seq1, off1, seq2, off2, params, strategy: int, threads: int = 1, engine: int = 0):
+    """GKL's own compiled Smith-Waterman (engine: 0 its CPUID dispatch, 1 AVX2, 2 AVX-512), one
+    runSWOnePairBT call per pair as IntelSmithWaterman.cc:72-121 makes them."""
+    lib = _load_ref()
+    lib.gklref_sw.restype = C.c_int
+    lib.gklref_sw.argtypes = [C.c_int, _u8p, _i64p, _u8p, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                              C.c_int, C.c_void_p, C.c_int, _i32p, _i32p, C.c_void_p, C.POINTER(C.c_double)]
+    return _sw_call(lib.gklref_sw, (int(engine),), seq1, off1, seq2, off2, params, strategy, threads)
