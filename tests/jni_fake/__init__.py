@@ -53,3 +53,17 @@ def pdhmm(lib_path, b, object_api=False, n_reads=0, n_haps=0, fault=0):
                          p(b.read_ins_qual), p(b.read_del_qual), p(b.gcp), p(b.hap_lengths), p(b.read_lengths), int(fault),
                          p(out), ec, em, leaks)
     return rc, out[:n], ec.value.decode(), em.value.decode(), (leaks[0], leaks[1])
+
+
+def smithwaterman(lib_path, ref: bytes, alt: bytes, params, strategy: int, fault=0):
+    """One IntelSmithWaterman.alignNative call.  Returns (rc, cigar bytes (2 * max(len) like the Java wrapper
+    allocates), offset, exception class, message, leaks)."""
+    l = _lib()
+    cap = 2 * max(len(ref), len(alt), 1)
+    cigar = C.create_string_buffer(cap)
+    off = C.c_int(0)
+    ec, em = C.create_string_buffer(256), C.create_string_buffer(256)
+    leaks = (C.c_long * 2)()
+    rc = l.fakejvm_sw(str(lib_path).encode(), ref, len(ref), alt, len(alt), *[int(v) for v in params], int(strategy),
+                      int(fault), cigar, cap, C.byref(off), ec, em, leaks)
+    return rc, cigar.raw, off.value, ec.value.decode(), em.value.decode(), (leaks[0], leaks[1])

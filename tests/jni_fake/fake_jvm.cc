@@ -30,6 +30,7 @@ struct Vm {
   bool exc = false;
   long locals = 0, pins = 0, criticals = 0;
   bool fail_double_pin = false;
+  const void* fail_critical_of = nullptr;  // GetPrimitiveArrayCritical of this array returns NULL
   std::vector<ClassObj*> found;
   std::vector<std::pair<double*, DblArr*>> dbl_copies;
 };
@@ -115,6 +116,7 @@ void fSetDoubleArrayRegion(JNIEnv*, jdoubleArray a, jsize start, jsize len, cons
 }
 void* fGetPrimitiveArrayCritical(JNIEnv*, jarray a, jboolean* is_copy) {
   if (is_copy) *is_copy = JNI_FALSE;
+  if (a == g_vm->fail_critical_of) return nullptr;
   g_vm->pins++;
   g_vm->criticals++;
   Obj* o = static_cast<Obj*>(a);
@@ -314,6 +316,50 @@ int fakejvm_pdhmm(const char* lib_path, int object_api, long long n, int n_reads
       memcpy(out, static_cast<DblArr*>(r)->data.data(), sizeof(double) * (size_t)n);
       vm.locals--;  // the returned array is handed to the caller
     }
+  }
+  const bool exc = vm.exc;
+  if (exc) {
+    snprintf(exc_class, 255, "%s", vm.exc_class.c_str());
+    snprintf(exc_msg, 255, "%s", vm.exc_msg.c_str());
+  }
+  done(&vm.env, &self_cls);
+  leaks[0] = vm.locals;
+  leaks[1] = vm.pins;
+  g_vm = nullptr;
+  return exc ? 1 : 0;
+}
+
+// IntelSmithWaterman: initNative, one alignNative call, doneNative.  fault: 0 none, 1 the reference array cannot be
+// pinned (GetPrimitiveArrayCritical returns NULL).  cigar: `cigar_cap` bytes, zeroed here like a fresh Java byte[].
+// Returns 0 (no exception; *offset set), 1 (exception pending), <0 harness failure.
+int fakejvm_sw(const char* lib_path, const uint8_t* ref, int ref_len, const uint8_t* alt, int alt_len, int match,
+               int mismatch, int open, int extend, int strategy, int fault, char* cigar, int cigar_cap, int* offset,
+               char* exc_class, char* exc_msg, long* leaks) {
+  void* h = dlopen(lib_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) { snprintf(exc_msg, 255, "%s", dlerror()); return -2; }
+  typedef void (*SInit)(JNIEnv*, jclass);
+  typedef jint (*SAlign)(JNIEnv*, jclass, jbyteArray, jbyteArray, jbyteArray, jint, jint, jint, jint, jbyte);
+  SInit init = (SInit)dlsym(h, "Java_com_intel_gkl_smithwaterman_IntelSmithWaterman_initNative");
+  SAlign align = (SAlign)dlsym(h, "Java_com_intel_gkl_smithwaterman_IntelSmithWaterman_alignNative");
+  SInit done = (SInit)dlsym(h, "Java_com_intel_gkl_smithwaterman_IntelSmithWaterman_doneNative");
+  if (!init || !align || !done) return -3;
+  Vm vm;
+  init_vm(&vm);
+  g_vm = &vm;
+  ClassObj self_cls;
+  init(&vm.env, &self_cls);
+  if (!vm.exc) {
+    ByteArr* r = make_bytes(ref, 0, ref_len);
+    ByteArr* a = make_bytes(alt, 0, alt_len);
+    ByteArr* c = new ByteArr;
+    c->data.assign((size_t)cigar_cap, 0);
+    if (fault == 1) vm.fail_critical_of = r;
+    const jint off = align(&vm.env, &self_cls, r, a, c, match, mismatch, open, extend, (jbyte)strategy);
+    if (!vm.exc) {
+      *offset = off;
+      memcpy(cigar, c->data.data(), (size_t)cigar_cap);
+    }
+    delete r; delete a; delete c;
   }
   const bool exc = vm.exc;
   if (exc) {

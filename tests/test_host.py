@@ -63,6 +63,14 @@ def test_library_exports_every_symbol_of_the_header():
     pd_lib = ctypes.CDLL(str(native.LIB_PATH.with_name("libgkl_pdhmm.so")))
     for name in pd_declared | declared:
         assert hasattr(pd_lib, name), name
+    # the Smith-Waterman surface (include/gklb_sw.h), third library name
+    from gkl_b200 import smithwaterman
+    sw_header = (ROOT / "include" / "gklb_sw.h").read_text()
+    sw_declared = set(re.findall(r"GKLB_API\s+[\w\s\*]+?\b(gklb_\w+)\s*\(", sw_header))
+    assert sw_declared == set(smithwaterman.SW_EXPORTS), sw_declared ^ set(smithwaterman.SW_EXPORTS)
+    sw_lib = ctypes.CDLL(str(native.LIB_PATH.with_name("libgkl_smithwaterman.so")))
+    for name in sw_declared:
+        assert hasattr(sw_lib, name), name
 
 
 def test_host_tables_are_bit_identical_to_the_oracle():

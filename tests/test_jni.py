@@ -28,7 +28,11 @@ def test_exports_exactly_the_symbols_intelpairhmm_binds():
     # IntelPDHMM.java:206-216 (the same binary is installed as libgkl_pdhmm.so)
     for s in ("initNative", "computeLikelihoodsNative", "computePDHMMNative", "doneNative"):
         assert "Java_com_intel_gkl_pdhmm_IntelPDHMM_" + s in syms
-    assert not [s for s in syms if s.startswith("Java_") and "IntelPairHmm" not in s and "IntelPDHMM" not in s]
+    # IntelSmithWaterman.java:183-186 (the same binary is installed as libgkl_smithwaterman.so)
+    for s in ("initNative", "alignNative", "doneNative"):
+        assert "Java_com_intel_gkl_smithwaterman_IntelSmithWaterman_" + s in syms
+    assert not [s for s in syms if s.startswith("Java_") and "IntelPairHmm" not in s and "IntelPDHMM" not in s
+                and "IntelSmithWaterman" not in s]
 
 
 def test_library_refuses_to_load_into_a_jvm_without_a_gpu():
@@ -130,3 +134,28 @@ def test_pdhmm_flat_and_object_api_through_jni():
     assert rc == 0 and leaks == (0, 0), (cls, msg)
     want = exp.reshape(276, 48)[:40, :12].ravel()
     assert np.abs(out - want).max() <= 1e-4
+
+
+def test_smithwaterman_without_a_gpu_raises_from_initnative():
+    if has_gpu():
+        pytest.skip("a GPU is present")
+    rc, _, _, cls, msg, leaks = jni_fake.smithwaterman(LIB, b"ACGT", b"ACGT", (3, -1, -4, -3), 9)
+    assert rc == 1 and cls == "java/lang/RuntimeException" and leaks == (0, 0)
+
+
+@pytest.mark.gpu
+def test_smithwaterman_align_through_jni():
+    from tests.test_oracle_sw import load_sw_golden, PARAMS, STRATEGIES
+    refs, alts, exp = load_sw_golden()
+    for k in (0, 7, 100, len(refs) - 1):
+        col = 0
+        for p in PARAMS:
+            for st in STRATEGIES:
+                rc, cigar, off, cls, msg, leaks = jni_fake.smithwaterman(LIB, refs[k], alts[k], p, st)
+                assert rc == 0, (cls, msg)
+                assert (cigar.rstrip(b"\x00").decode(), off) == exp[k][col]
+                assert leaks == (0, 0)
+                col += 1
+    # GetPrimitiveArrayCritical failing -> IllegalArgumentException("Arrays aren't valid."), IntelSmithWaterman.cc:82-104
+    rc, _, _, cls, msg, leaks = jni_fake.smithwaterman(LIB, refs[0], alts[0], PARAMS[0], 9, fault=1)
+    assert rc == 1 and cls == "java/lang/IllegalArgumentException" and msg == "Arrays aren't valid." and leaks == (0, 0)
