@@ -10,11 +10,11 @@
 // in anti-diagonal order with the reference's tie rules (:225-251) and the CIGAR walked back from there (:269-437).
 //
 // Mapping: one warp per pair, pulled longest-first from an atomic queue.  The warp is a systolic array over seq1:
-// lane t owns 8 consecutive rows of a pass of 256 rows, keeps H and E of the previous column in registers and at step
-// s processes column s - t; the bottom row of lane t-1 (H, F) arrives by warp shuffle, its previous value is the
-// diagonal.  The eight backtrack nibbles of a lane's column are one 32-bit word, stored to a per-warp scratch area in
-// global memory that stays L2-resident; sequences longer than 256 rows take several passes with the bottom row of a
-// pass carried through a scratch line.  The choice among equal maxima and the walk back are done by the same warp
+// lane t owns K consecutive rows (K = 4, 8, 12 or 16, the smallest that covers seq1 in one pass of 32 K rows), keeps
+// H and E of the previous column in registers and at step s processes column s - t; the bottom row of lane t-1
+// (H, F) arrives by warp shuffle, its previous value is the diagonal.  The backtrack nibbles of a lane's column are
+// one or two 32-bit words, stored to a per-warp scratch area in global memory that stays L2-resident; sequences
+// longer than 512 rows take several passes with the bottom row of a pass carried through a scratch line.  The choice among equal maxima and the walk back are done by the same warp
 // right after the fill: the candidates are scanned 32 at a time with ballots, and the walk reads the backtrack words
 // through a 32-column x 16-row register window refreshed by coalesced loads.
 #pragma once
@@ -24,8 +24,18 @@
 
 namespace gklb {
 
-constexpr int kSwRowsPerLane = 8;
-constexpr int kSwPassRows = 32 * kSwRowsPerLane;
+// Rows per lane: the smallest of 4 / 8 / 12 / 16 whose 32-lane pass covers seq1, else 16 with several passes.
+__host__ __device__ inline int sw_rows_per_lane(int nrow) {
+  return nrow <= 128 ? 4 : nrow <= 256 ? 8 : nrow <= 384 ? 12 : 16;
+}
+// 32-bit backtrack words per lane and column (eight 4-bit codes each)
+__host__ __device__ inline int sw_words_per_lane(int k) { return (k + 7) / 8; }
+// backtrack words one pair needs
+__host__ __device__ inline size_t sw_bt_words(int nrow, int ncol) {
+  const int k = sw_rows_per_lane(nrow);
+  const size_t passes = (size_t)((nrow + 32 * k - 1) / (32 * k));
+  return passes * 32 * (size_t)sw_words_per_lane(k) * (size_t)(ncol + 1);
+}
 constexpr int kSwCutoff = -100000000;            // MATRIX_MIN_CUTOFF, smithwaterman_common.h:81
 constexpr int kSwLow = INT32_MIN / 2;            // LOW_INIT_VALUE, :82
 // run element: op in the low 4 bits (0 M, 1 I, 2 D, 9 S -- smithwaterman_common.h:42-47), length above
@@ -60,61 +70,63 @@ __device__ __forceinline__ int sw_edge(bool indel_edges, int k, int open, int ex
   return indel_edges ? open + (k - 1) * extend : 0;
 }
 
-template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p) {
-  constexpr int K = kSwRowsPerLane;
-  const int lane = threadIdx.x & 31;
-  const size_t wg = (size_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
-  uint32_t* bt = p.bt + wg * p.bt_stride;
-  int32_t* lines = p.lines + wg * p.lines_stride;
-  int32_t* carryH = lines;                       // [2][W]
-  int32_t* carryF = lines + 2 * (size_t)p.line_w;  // [2][W]
-  int32_t* lastrow = lines + 4 * (size_t)p.line_w;
-  int32_t* lastcol = lines + 5 * (size_t)p.line_w;
-  uint32_t* myruns = p.runs_scratch + wg * (size_t)(p.line_w + p.line_r + 4);
-  const bool indel_edges = (p.strategy == 10) || (p.strategy == 11);
-  const bool row_candidates = (p.strategy == 9) || (p.strategy == 12);
+struct SwWarpScratch {
+  uint32_t* bt;
+  int32_t *carryH, *carryF, *lastrow, *lastcol;
+  uint32_t* myruns;
+};
 
-  for (;;) {
-    unsigned int q = 0;
-    if (lane == 0) q = atomicAdd(p.queue, 1u);
-    q = __shfl_sync(0xffffffffu, q, 0);
-    if (q >= (unsigned)p.n) break;
-    const int pair = p.order[q];
+// One pair, K rows per lane.
+template <int K>
+__device__ __noinline__ void sw_pair(const SwParams& p, const SwWarpScratch& w, int pair, int lane) {
+  // scalars once into registers (p lives in the caller's frame)
+  const int w_match = p.match, w_mismatch = p.mismatch, w_open = p.open, w_extend = p.extend, strategy = p.strategy;
+  const int line_w = p.line_w;
+  constexpr int PASS_ROWS = 32 * K;
+  constexpr int KW = (K + 7) / 8;
+  uint32_t* bt = w.bt;
+  int32_t* carryH = w.carryH;
+  int32_t* carryF = w.carryF;
+  int32_t* lastrow = w.lastrow;
+  int32_t* lastcol = w.lastcol;
+  uint32_t* myruns = w.myruns;
+  const bool indel_edges = (strategy == 10) || (strategy == 11);
+  const bool row_candidates = (strategy == 9) || (strategy == 12);
+  {
     const uint8_t* s1 = p.seq1 + p.off1[pair];
     const uint8_t* s2 = p.seq2 + p.off2[pair];
     const int nrow = (int)(p.off1[pair + 1] - p.off1[pair]);
     const int ncol = (int)(p.off2[pair + 1] - p.off2[pair]);
-    const int n_pass = (nrow + kSwPassRows - 1) / kSwPassRows;
+    const int n_pass = (nrow + PASS_ROWS - 1) / PASS_ROWS;
     const int btw = ncol + 1;  // words per (pass, lane) line; column c at index c
     __syncwarp();
 
     // ------------------------------------------------------------------ fill
     for (int pass = 0; pass < n_pass; pass++) {
-      const int i0 = pass * kSwPassRows + lane * K;  // this lane's rows are i0+1 .. i0+K (1-based)
+      const int i0 = pass * PASS_ROWS + lane * K;  // this lane's rows are i0+1 .. i0+K (1-based)
       int Hl[K], El[K];   // H and E of the previous column
       uint32_t r1[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int i = i0 + j + 1;
-        Hl[j] = sw_edge(indel_edges, i, p.open, p.extend);     // column 0
+        Hl[j] = sw_edge(indel_edges, i, w_open, w_extend);     // column 0
         El[j] = kSwLow;                                         // PairWiseSW.h:90-93,223
         r1[j] = (i <= nrow) ? (uint32_t)s1[i - 1] : 0x100u;     // rows past the end: values nobody reads
       }
-      const int32_t* cinH = carryH + (size_t)((pass + 1) & 1) * p.line_w;   // bottom row of the previous pass
-      const int32_t* cinF = carryF + (size_t)((pass + 1) & 1) * p.line_w;
-      int32_t* coutH = carryH + (size_t)(pass & 1) * p.line_w;
-      int32_t* coutF = carryF + (size_t)(pass & 1) * p.line_w;
+      const int32_t* cinH = carryH + (size_t)((pass + 1) & 1) * line_w;   // bottom row of the previous pass
+      const int32_t* cinF = carryF + (size_t)((pass + 1) & 1) * line_w;
+      int32_t* coutH = carryH + (size_t)(pass & 1) * line_w;
+      int32_t* coutF = carryF + (size_t)(pass & 1) * line_w;
       const bool writes_carry = (lane == 31) && (pass + 1 < n_pass);
       if (writes_carry) {  // column 0 of the pass's bottom row
-        coutH[0] = sw_edge(indel_edges, i0 + K, p.open, p.extend);
+        coutH[0] = sw_edge(indel_edges, i0 + K, w_open, w_extend);
         coutF[0] = kSwLow;
       }
       // Row i0, the row above the first lane's rows: row 0 of the matrix (edge values, F = lowInitValue,
       // :86-89,212-222) in the first pass, the carried bottom row afterwards.
       auto row_above_first_lane = [&](int c, int& h, int& f) {
         if (pass == 0) {
-          h = (c == 0) ? 0 : sw_edge(indel_edges, c, p.open, p.extend);
+          h = (c == 0) ? 0 : sw_edge(indel_edges, c, w_open, w_extend);
           f = kSwLow;
         } else {
           h = __ldcg(cinH + c);
@@ -129,7 +141,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
         row_above_first_lane(1, tH, tF);
       }
       int fbot = kSwLow;     // F of the lane's bottom row at the column it processed last
-      uint32_t* btline = bt + ((size_t)pass * 32 + lane) * btw;
+      uint32_t* btline = bt + ((size_t)pass * 32 + lane) * KW * btw;   // KW lines of btw words
       const int last_local = nrow - 1 - i0;  // index of row nrow among this lane's rows when in 0..K-1
       const int n_steps = ncol + 31;
       int c = 1 - lane;
@@ -147,20 +159,22 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
         if (active) {
           const uint32_t b2 = s2[c - 1];
           int hd = dH, hu = uH, fu = uF;
-          uint32_t word = 0;
+          uint32_t word[KW];
+#pragma unroll
+          for (int q = 0; q < KW; q++) word[q] = 0;
 #pragma unroll
           for (int j = 0; j < K; j++) {
             // MAIN_CODE, PairWiseSW.h:27-62
-            const int ext_h = El[j] + p.extend, open_h = Hl[j] + p.open;
+            const int ext_h = El[j] + w_extend, open_h = Hl[j] + w_open;
             const int e = max(open_h, ext_h);
             uint32_t code = (open_h > ext_h) ? 0u : 4u;           // INSERT_EXT unless opening is strictly better
-            const int ext_v = fu + p.extend, open_v = hu + p.open;
+            const int ext_v = fu + w_extend, open_v = hu + w_open;
             const int f = max(ext_v, open_v);
             code |= (open_v > ext_v) ? 0u : 8u;                   // DELETE_EXT
-            int h = max(hd + ((r1[j] == b2) ? p.match : p.mismatch), kSwCutoff);
+            int h = max(hd + ((r1[j] == b2) ? w_match : w_mismatch), kSwCutoff);
             if (e > h) { code |= 1u; h = e; }                     // INSERT
             if (f > h) { code = (code & 12u) | 2u; h = f; }       // DELETE
-            word |= code << (4 * j);
+            word[j / 8] |= code << (4 * (j % 8));
             hd = Hl[j];   // H(i, c-1): the diagonal of the row below
             Hl[j] = h;
             El[j] = e;
@@ -168,7 +182,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
             fu = f;
           }
           fbot = fu;
-          btline[c] = word;
+#pragma unroll
+          for (int q = 0; q < KW; q++) btline[(size_t)q * btw + c] = word[q];
           if ((unsigned)last_local < (unsigned)K) {
             int v = Hl[0];
 #pragma unroll
@@ -223,8 +238,8 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
 
     // ------------------------------------------------------------------ walk back (getCIGAR, :269-437)
     int i, j;
-    if (p.strategy == 10) { i = nrow; j = ncol; }
-    else if (p.strategy == 11) { i = max_i; j = ncol; }
+    if (strategy == 10) { i = nrow; j = ncol; }
+    else if (strategy == 11) { i = max_i; j = ncol; }
     else { i = max_i; j = max_j; }
     int n_runs = 0, cur_op = -1, cur_len = 0;
     auto push = [&](int op, int len) {  // adjacent equal elements merge (:392-409)
@@ -235,11 +250,15 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
     };
     if (j < ncol) push(9, ncol - j);
     int state = 0;
-    // register window: lane l holds the backtrack words of column wc0 - l for the row blocks wb (w0) and wb - 1 (w1)
+    // register window: lane l holds the backtrack words of column wc0 - l for the lines wb (w0) and wb - 1 (w1)
     int wc0 = -1, wb = -1;
     uint32_t w0 = 0, w1 = 0;
     while (i > 0 && j > 0) {
-      const int blk = (i - 1) >> 3;  // global 8-row block = pass * 32 + lane of the fill
+      // row i sits in pass g / (32 K), lane (g % (32 K)) / K, row r = g % K of that lane, word r / 8, nibble r % 8;
+      // lines are numbered (pass * 32 + lane) * KW + word, which grows with the row
+      const int g = i - 1;
+      const int r = g % K;
+      const int blk = (g / K) * KW + (r >> 3);
       if (!(blk == wb || blk == wb - 1) || j > wc0 || j < wc0 - 31 || wc0 < 0) {
         wb = blk;
         wc0 = j;
@@ -248,7 +267,7 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
         w1 = (col >= 1 && blk >= 1) ? __ldcg(bt + (size_t)(blk - 1) * btw + col) : 0u;
       }
       const uint32_t word = __shfl_sync(0xffffffffu, (blk == wb) ? w0 : w1, wc0 - j);
-      const int btr = (int)((word >> (4 * ((i - 1) & 7))) & 15u);
+      const int btr = (int)((word >> (4 * (r & 7))) & 15u);
       if (state == 4) { j--; cur_len++; state = btr & 4; }
       else if (state == 8) { i--; cur_len++; state = btr & 8; }
       else {
@@ -260,10 +279,10 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
       }
     }
     int offset;
-    if (p.strategy == 9) {
+    if (strategy == 9) {
       if (j > 0) push(9, j);
       offset = i;
-    } else if (p.strategy == 12) {
+    } else if (strategy == 12) {
       if (j > 0) cur_len += j;  // an element of the last element's type (:371-377), merged with it
       offset = (int)(int16_t)(i - j);
     } else {
@@ -281,6 +300,34 @@ __global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p)
       p.run_start[pair] = (int32_t)base;
       p.run_count[pair] = n_runs;
       p.offsets[pair] = offset;
+    }
+  }
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) k_smith_waterman(const SwParams p) {
+  const int lane = threadIdx.x & 31;
+  const size_t wg = (size_t)blockIdx.x * WARPS + (threadIdx.x >> 5);
+  int32_t* lines = p.lines + wg * p.lines_stride;
+  SwWarpScratch w;
+  w.bt = p.bt + wg * p.bt_stride;
+  w.carryH = lines;                              // [2][W]
+  w.carryF = lines + 2 * (size_t)p.line_w;       // [2][W]
+  w.lastrow = lines + 4 * (size_t)p.line_w;
+  w.lastcol = lines + 5 * (size_t)p.line_w;
+  w.myruns = p.runs_scratch + wg * (size_t)(p.line_w + p.line_r + 4);
+  for (;;) {
+    unsigned int q = 0;
+    if (lane == 0) q = atomicAdd(p.queue, 1u);
+    q = __shfl_sync(0xffffffffu, q, 0);
+    if (q >= (unsigned)p.n) break;
+    const int pair = p.order[q];
+    const int nrow = (int)(p.off1[pair + 1] - p.off1[pair]);
+    switch (sw_rows_per_lane(nrow)) {
+      case 4: sw_pair<4>(p, w, pair, lane); break;
+      case 8: sw_pair<8>(p, w, pair, lane); break;
+      case 12: sw_pair<12>(p, w, pair, lane); break;
+      default: sw_pair<16>(p, w, pair, lane); break;
     }
   }
 }

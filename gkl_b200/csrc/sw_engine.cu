@@ -27,8 +27,8 @@ namespace {
                                 #call, cudaGetErrorString(e_));                                           \
   } while (0)
 
-constexpr int kWarps = 8;          // per CTA
-constexpr int kCtasPerSm = 2;      // 16 resident warps per SM (117 registers per thread) when the scratch budget allows
+constexpr int kWarps = 12;         // per CTA: 153 registers per thread leave room for 12 warps per SM
+constexpr int kCtasPerSm = 1;
 
 struct Buf {
   void* p = nullptr;
@@ -127,8 +127,7 @@ int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch
     max2 = std::max<int>(max2, (int)l2);
     size[k] = l1 * l2;
     cells += size[k];
-    const size_t passes = (size_t)((l1 + kSwPassRows - 1) / kSwPassRows);
-    bt_words = std::max(bt_words, passes * 32 * (size_t)(l2 + 1));
+    bt_words = std::max(bt_words, sw_bt_words((int)l1, (int)l2));
     total_runs += (size_t)(l1 + l2 + 2);
   }
   std::vector<int32_t> order(n);
