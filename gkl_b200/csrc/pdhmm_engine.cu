@@ -29,6 +29,7 @@ namespace {
   } while (0)
 
 constexpr int kG = 32, kK = 4, kWarps = 8;
+constexpr int kWarps2 = 12;  // k_pdhmm2 fits 168 registers (two 8-byte spills outside the loops): a third warp per scheduler
 constexpr int kMaxQual = 254;
 constexpr int kMmSizePd = ((kMaxQual + 1) * (kMaxQual + 2)) >> 1;
 constexpr int kSmemMax = 232448;
@@ -117,7 +118,7 @@ int launch(PdEngine* e) {
   CU(cudaMemsetAsync(e->misc.p, 0, 8, e->stream));
   if (e->use_v2) {
     void* args2[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks};
-    CU(cudaLaunchKernel(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps>), dim3(e->last_grid), dim3(kWarps * 32),
+    CU(cudaLaunchKernel(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps2>), dim3(e->last_grid), dim3(kWarps2 * 32),
                         args2, e->last_smem, e->stream));
     e->stats.kernel_launches++;
     return GKLB_OK;
@@ -160,7 +161,7 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
 
   constexpr int gpw = 32 / kG;
   const size_t col_pitch = ((size_t)b->max_hap + 2 * kPdMargin + 1) & ~(size_t)1;
-  const size_t smem = (size_t)kWarps * gpw * 7 * col_pitch;
+  size_t smem = (size_t)kWarps * gpw * 7 * col_pitch;
   if (smem > (size_t)kSmemMax)
     return gklb_internal_fail(GKLB_ERR_INVALID, "maxHapLength %d does not fit in shared memory", b->max_hap);
 
@@ -216,7 +217,7 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   e->use_v2 = e->allow_v2 && b->max_read <= kG * kK;
   if (e->use_v2) {
     if (cross) {
-      const long long want = 16LL * kWarps * e->num_sms;
+      const long long want = 16LL * kWarps2 * e->num_sms;
       long long nb = std::min<long long>(n_reads, std::max<long long>(1, (want + n_haps - 1) / n_haps));
       e->read_block = (int)((n_reads + nb - 1) / nb);
       e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
@@ -230,7 +231,13 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
     e->n_tasks = (unsigned int)warp_items;
   }
   if (!e->use_v2) warp_items = (n + gpw - 1) / gpw;
-  e->last_grid = (int)std::min<long long>(e->num_sms, (warp_items + kWarps - 1) / kWarps);
+  const int warps_per_cta = e->use_v2 ? kWarps2 : kWarps;
+  if (e->use_v2) {
+    smem = (size_t)kWarps2 * 7 * col_pitch;
+    if (smem > (size_t)kSmemMax) { e->use_v2 = false; smem = (size_t)kWarps * gpw * 7 * col_pitch; warp_items = (n + gpw - 1) / gpw; }
+  }
+  e->last_smem = smem;
+  e->last_grid = (int)std::min<long long>(e->num_sms, (warp_items + warps_per_cta - 1) / (e->use_v2 ? kWarps2 : kWarps));
   e->have_last = true;
   e->stats = gklb_pdhmm_stats{};
   e->stats.pairs = n;
@@ -284,7 +291,7 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps>),
+  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps2>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
