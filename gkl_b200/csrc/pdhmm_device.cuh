@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
             double dM = gM, dI = gI, dD = gD;
 #pragma unroll
             for (int j = 0; j < K; j++) {
-              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const bool match = ((((cm >> rcls[j]) & 1u) != 0u) | (xeq[j] == y));
               const double prior = match ? pMa[j] : pMi[j];
               const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
               const double nD = Mi[j] * tMD[j] + Di[j] * tII[j];
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
             for (int j = 0; j < K; j++) {
               const bool inside = ((info >> shift[j]) & 3u) == 1u;
               const double lM = M[j], lI = I[j], lD = D[j];
-              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const bool match = ((((cm >> rcls[j]) & 1u) != 0u) | (xeq[j] == y));
               const double prior = match ? pMa[j] : pMi[j];
               const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
               const double nD = lM * tMD[j] + lD * tII[j];
@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
               const double eM = after ? fmax(dM, dbM) : dM, eI = after ? fmax(dI, dbI) : dI, eD = after ? fmax(dD, dbD) : dD;
               const double leftM = after ? mxM : lM, leftD = after ? mxD : lD;
               const double topM = del_end ? fmax(tbM, tM) : tM, topI = del_end ? fmax(tbI, tI) : tI;
-              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
+              const bool match = ((((cm >> rcls[j]) & 1u) != 0u) | (xeq[j] == y));
               const double prior = match ? pMa[j] : pMi[j];
               const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
               const double nD = leftM * tMD[j] + leftD * tII[j];  // deletionToDeletion == insertionToInsertion
@@ -425,6 +425,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
 // The reference merges with std::max on non-negative finite doubles (pdhmm-serial.cc:330-365): a compare and a select,
 // without fmax's NaN handling.
 __device__ __forceinline__ double dmax(double a, double b) { return (a < b) ? b : a; }
+// The prior of one cell: the read byte's class bit against the column's class mask, or an identical "other" byte
+// (pdhmm-serial.cc:228-277).  One predicate and one 64-bit select (the compiler nests two selects otherwise).
+__device__ __forceinline__ double pick_prior(uint32_t cm, uint32_t rbit, uint32_t xeq, uint32_t y, double p_match,
+                                             double p_mismatch) {
+  double r;
+  asm("{\n\t.reg .pred p, q;\n\t.reg .b32 t;\n\tand.b32 t, %1, %2;\n\tsetp.ne.u32 p, t, 0;\n\t"
+      "setp.eq.or.u32 q, %3, %4, p;\n\tselp.f64 %0, %5, %6, q;\n\t}"
+      : "=d"(r) : "r"(cm), "r"(rbit), "r"(xeq), "r"(y), "d"(p_match), "d"(p_mismatch));
+  return r;
+}
 // (cond && a < b) ? b : a with the condition folded into the compare (one DSETP + one 64-bit select)
 __device__ __forceinline__ double dmax_if(double a, double b, bool cond) {
   double r;
@@ -533,7 +543,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
       const int n_pad = CAP - R;
       // ---- per-row constants ----
       double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];
-      uint32_t shift[K], rcls[K], xeq[K];
+      uint32_t shift[K], rbit[K], xeq[K];   // rbit: the read byte's class as a bit of the column masks
       bool padrow[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
@@ -543,7 +553,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
         tII[j] = 1.0;
         pMa[j] = pMi[j] = 0.0;
         shift[j] = 0;
-        rcls[j] = 15;
+        rbit[j] = 0;       // padding rows match nothing
         xeq[j] = 0x100;
         if (!padrow[j]) {
           const int8_t iq = p.read_ins_qual[ro + row], dq = p.read_del_qual[ro + row], gq = p.gcp[ro + row];
@@ -561,8 +571,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
           pMa[j] = 1.0 - eq;
           pMi[j] = eq / 3.0;
           const uint32_t x = (uint8_t)p.read_bases[ro + row];
-          rcls[j] = read_class(x);
-          xeq[j] = (rcls[j] == 9) ? x : 0x100u;
+          const uint32_t rc = read_class(x);
+          rbit[j] = 1u << rc;
+          xeq[j] = (rc == 9) ? x : 0x100u;
           const int k = (row < 8) ? row : 2 + ((row - 2) % 6);
           shift[j] = 2u * ((orbit >> (2 * k)) & 3u);
         }
@@ -607,8 +618,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
 #pragma unroll
               for (int j = 0; j < K; j++) {
                 const double lM = M[j], lI = I[j], lD = D[j];
-                const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
-                const double prior = match ? pMa[j] : pMi[j];
+                const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
                 const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
                 const double nD = lM * tMD[j] + lD * tII[j];
                 const double nI = tM * tMI[j] + tI * tII[j];
@@ -640,8 +650,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               double dM = gM, dI = gI, dD = gD;
 #pragma unroll
               for (int j = 0; j < K; j++) {
-                const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
-                const double prior = match ? pMa[j] : pMi[j];
+                const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
                 const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
                 const double nD = Mi[j] * tMD[j] + Di[j] * tII[j];
                 const double nI = tM * tMI[j] + tI * tII[j];
@@ -704,8 +713,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
 #pragma unroll
               for (int j = 0; j < K; j++) {
                 const double lM = M[j], lI = I[j], lD = D[j];
-                const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
-                const double prior = match ? pMa[j] : pMi[j];
+                const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
                 const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
                 const double nD = lM * tMD[j] + lD * tII[j];
                 const double nI = tM * tMI[j] + tI * tII[j];
@@ -752,8 +760,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             for (int j = 0; j < K; j++) {
               const bool inside = ((info >> shift[j]) & 3u) == 1u;
               const double lM = M[j], lI = I[j], lD = D[j];
-              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
-              const double prior = match ? pMa[j] : pMi[j];
+              const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
               const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
               const double nD = lM * tMD[j] + lD * tII[j];
               const double nI = tM * tMI[j] + tI * tII[j];
@@ -779,8 +786,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               const double eM = after ? dmax(dM, dbM) : dM, eI = after ? dmax(dI, dbI) : dI, eD = after ? dmax(dD, dbD) : dD;
               const double leftM = after ? mxM : lM, leftD = after ? mxD : lD;
               const double topM = del_end ? dmax(tbM, tM) : tM, topI = del_end ? dmax(tbI, tI) : tI;
-              const bool match = ((cm >> rcls[j]) & 1u) || (xeq[j] == y);
-              const double prior = match ? pMa[j] : pMi[j];
+              const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
               const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
               const double nD = leftM * tMD[j] + leftD * tII[j];
               const double nI = topM * tMI[j] + topI * tII[j];
