@@ -53,6 +53,15 @@ struct PdhmmParams {
   int carry_state;
 };
 
+// The three cell updates with a fixed evaluation order (the source order of pdhmm-serial.cc:354-365, products fused
+// into the following sum), so that every kernel and code path rounds identically.
+__device__ __forceinline__ double pd_match(double prior, double dM, double dI, double dD, double tMM, double tIM) {
+  return __dmul_rn(prior, fma(dD, tIM, fma(dI, tIM, __dmul_rn(dM, tMM))));
+}
+__device__ __forceinline__ double pd_gap(double a, double ca, double b, double cb) {  // a * ca + b * cb
+  return fma(b, cb, __dmul_rn(a, ca));
+}
+
 __device__ __forceinline__ double shfl_up_d(double v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
 
 // Read bytes fall into ten classes for the prior's match test (pdhmm-serial.cc:228-277: raw byte equality, 'N' on
@@ -295,9 +304,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
             for (int j = 0; j < K; j++) {
               const bool match = ((((cm >> rcls[j]) & 1u) != 0u) | (xeq[j] == y));
               const double prior = match ? pMa[j] : pMi[j];
-              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-              const double nD = Mi[j] * tMD[j] + Di[j] * tII[j];
-              const double nI = tM * tMI[j] + tI * tII[j];
+              const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+              const double nD = pd_gap(Mi[j], tMD[j], Di[j], tII[j]);
+              const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
               dM = Mi[j]; dI = Ii[j]; dD = Di[j];
               Mo[j] = nM; Io[j] = nI; Do[j] = nD;
               tM = nM; tI = nI;
@@ -362,9 +371,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
               const double lM = M[j], lI = I[j], lD = D[j];
               const bool match = ((((cm >> rcls[j]) & 1u) != 0u) | (xeq[j] == y));
               const double prior = match ? pMa[j] : pMi[j];
-              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-              const double nD = lM * tMD[j] + lD * tII[j];
-              const double nI = tM * tMI[j] + tI * tII[j];
+              const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+              const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+              const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
               dM = lM; dI = lI; dD = lD;
               bM[j] = inside ? bM[j] : lM; bI[j] = inside ? bI[j] : lI; bD[j] = inside ? bD[j] : lD;
               M[j] = nM; I[j] = nI; D[j] = nD;
@@ -389,9 +398,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
               const double topM = del_end ? fmax(tbM, tM) : tM, topI = del_end ? fmax(tbI, tI) : tI;
               const bool match = ((((cm >> rcls[j]) & 1u) != 0u) | (xeq[j] == y));
               const double prior = match ? pMa[j] : pMi[j];
-              const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
-              const double nD = leftM * tMD[j] + leftD * tII[j];  // deletionToDeletion == insertionToInsertion
-              const double nI = topM * tMI[j] + topI * tII[j];
+              const double nM = pd_match(prior, eM, eI, eD, tMM[j], tIM[j]);
+              const double nD = pd_gap(leftM, tMD[j], leftD, tII[j]);  // deletionToDeletion == insertionToInsertion
+              const double nI = pd_gap(topM, tMI[j], topI, tII[j]);
               // the next row's diagonal is this row's previous column, its top this row's new column
               dM = lM; dI = lI; dD = lD; dbM = lbM; dbI = lbI; dbD = lbD;
               M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
@@ -588,13 +597,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
       double sum = 0.0;
       int c = 1 - t;
       double uM, uI, uD, ubM = 0.0, ubI = 0.0, ubD = 0.0;
+      // Lane 0 holds only padding rows here (the host sends reads of more than 32 K - K rows to k_pdhmm), and a
+      // padding row IS row 0: M = I = 0, D = init at every column, twins likewise.  shfl_up hands lane 0 its own
+      // bottom row back, which is therefore exactly the row above it -- no first-lane fix-up anywhere.
       auto fetch_main = [&]() {
         uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
-        if (first) { uM = uI = 0.0; uD = init; }   // row 0: D = init, everything else 0
       };
       auto fetch_twins = [&]() {
         ubM = shfl_up_d(bM[K - 1], G); ubI = shfl_up_d(bI[K - 1], G); ubD = shfl_up_d(bD[K - 1], G);
-        if (first) ubM = ubI = ubD = 0.0;
       };
       fetch_main();
       fetch_twins();
@@ -619,9 +629,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               for (int j = 0; j < K; j++) {
                 const double lM = M[j], lI = I[j], lD = D[j];
                 const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
-                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-                const double nD = lM * tMD[j] + lD * tII[j];
-                const double nI = tM * tMI[j] + tI * tII[j];
+                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+                const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
                 dM = lM; dI = lI; dD = lD;
                 if constexpr (decltype(save_twins)::value) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
                 M[j] = nM; I[j] = nI; D[j] = nD;
@@ -651,9 +661,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
 #pragma unroll
               for (int j = 0; j < K; j++) {
                 const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
-                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-                const double nD = Mi[j] * tMD[j] + Di[j] * tII[j];
-                const double nI = tM * tMI[j] + tI * tII[j];
+                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+                const double nD = pd_gap(Mi[j], tMD[j], Di[j], tII[j]);
+                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
                 dM = Mi[j]; dI = Ii[j]; dD = Di[j];
                 Mo[j] = nM; Io[j] = nI; Do[j] = nD;
                 tM = nM; tI = nI;
@@ -663,7 +673,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               gM = uM; gI = uI; gD = uD;
               c++;
               uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
-              if (first) { uM = uI = 0.0; uD = init; }
             };
             for (int k = 0; k < n_fast; k += 2) {
               half(M, I, D, M2, I2, D2);
@@ -714,9 +723,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               for (int j = 0; j < K; j++) {
                 const double lM = M[j], lI = I[j], lD = D[j];
                 const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
-                const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-                const double nD = lM * tMD[j] + lD * tII[j];
-                const double nI = tM * tMI[j] + tI * tII[j];
+                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+                const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
                 dM = lM; dI = lI; dD = lD;
                 if (capture) { bM[j] = lM; bI[j] = lI; bD[j] = lD; }
                 M[j] = nM; I[j] = nI; D[j] = nD;
@@ -730,7 +739,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
             double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
 #pragma unroll
             for (int j = 0; j < K; j++) {
-              const double nI = dmax(tbM, tM) * tMI[j] + dmax(tbI, tI) * tII[j];
+              const double nI = pd_gap(dmax(tbM, tM), tMI[j], dmax(tbI, tI), tII[j]);
               I[j] = del_end ? nI : I[j];
               tM = M[j]; tI = I[j]; tbM = bM[j]; tbI = bI[j];
             }
@@ -761,9 +770,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               const bool inside = ((info >> shift[j]) & 3u) == 1u;
               const double lM = M[j], lI = I[j], lD = D[j];
               const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
-              const double nM = prior * (dM * tMM[j] + dI * tIM[j] + dD * tIM[j]);
-              const double nD = lM * tMD[j] + lD * tII[j];
-              const double nI = tM * tMI[j] + tI * tII[j];
+              const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+              const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+              const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
               dM = lM; dI = lI; dD = lD;
               bM[j] = inside ? bM[j] : lM; bI[j] = inside ? bI[j] : lI; bD[j] = inside ? bD[j] : lD;
               M[j] = nM; I[j] = nI; D[j] = nD;
@@ -787,9 +796,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
               const double leftM = after ? mxM : lM, leftD = after ? mxD : lD;
               const double topM = del_end ? dmax(tbM, tM) : tM, topI = del_end ? dmax(tbI, tI) : tI;
               const double prior = pick_prior(cm, rbit[j], xeq[j], y, pMa[j], pMi[j]);
-              const double nM = prior * (eM * tMM[j] + eI * tIM[j] + eD * tIM[j]);
-              const double nD = leftM * tMD[j] + leftD * tII[j];
-              const double nI = topM * tMI[j] + topI * tII[j];
+              const double nM = pd_match(prior, eM, eI, eD, tMM[j], tIM[j]);
+              const double nD = pd_gap(leftM, tMD[j], leftD, tII[j]);
+              const double nI = pd_gap(topM, tMI[j], topI, tII[j]);
               dM = lM; dI = lI; dD = lD; dbM = lbM; dbI = lbI; dbD = lbD;
               M[j] = nM; I[j] = nI; D[j] = nD; bM[j] = nbM; bI[j] = nbI; bD[j] = nbD;
               tM = nM; tI = nI; tbM = nbM; tbI = nbI;

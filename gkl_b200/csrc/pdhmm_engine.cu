@@ -214,7 +214,7 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   long long warp_items = (n + gpw - 1) / gpw;
   // Reads that fit one pass take the haplotype-major kernel: a task is one haplotype x a block of reads, sized for
   // about 16 tasks per resident warp so that the dynamic queue balances the load.
-  e->use_v2 = e->allow_v2 && b->max_read <= kG * kK;
+  e->use_v2 = e->allow_v2 && b->max_read <= kG * kK - kK;  // lane 0 all padding, see k_pdhmm2
   if (e->use_v2) {
     if (cross) {
       const long long want = 16LL * kWarps2 * e->num_sms;
