@@ -23,9 +23,10 @@ def main():
     ap.add_argument("--haps", type=int, default=128)
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--cpu-reads", type=int, default=150)
+    ap.add_argument("--read-len", type=int, default=101)
     ap.add_argument("--out", default="gpurun_out/pdhmm_bench.json")
     a = ap.parse_args()
-    reads, haps = synth.config5(a.reads, a.haps)
+    reads, haps = synth.config5(a.reads, a.haps, a.read_len)
     rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
     hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
     cells = sum(len(r[0]) for r in reads) * sum(len(h[0]) for h in haps)
@@ -43,7 +44,7 @@ def main():
     n_cpu = min(a.cpu_reads, a.reads)
     flat = pb.PdhmmBatch.cross(reads[:n_cpu], haps)
     threads = oracle.host_threads()
-    res = {"workload": f"config5: {a.reads} reads (len 101) x {a.haps} haplotypes (len 200-400) with PD flag bytes",
+    res = {"workload": f"config5: {a.reads} reads (len {a.read_len}) x {a.haps} haplotypes (len 200-400) with PD flag bytes",
            "cells": cells, "gpu_kernel_ms": ms, "gpu_kernel_gcups": cells / ms / 1e6,
            "gpu_e2e_gcups_incl_python_marshalling": cells / e2e_s / 1e9,
            "gpu_phases_ms": {"h2d": st.h2d_ms, "kernel": st.kernel_ms, "d2h": st.d2h_ms}, "cpu_threads": threads,

@@ -29,7 +29,16 @@ namespace {
   } while (0)
 
 constexpr int kG = 32, kK = 4, kWarps = 8;
-constexpr int kWarps2 = 12;  // k_pdhmm2 fits 168 registers (two 8-byte spills outside the loops): a third warp per scheduler
+// k_pdhmm2 instantiations: rows per lane, warps per CTA, longest read (32 K - K: lane 0 stays all padding).
+// K = 4 fits 168 registers (two 8-byte spills outside the loops), i.e. a third warp per scheduler; K = 5 / 6 serve
+// 150-base reads and need the full register file.
+struct V2Config { int K, warps, max_read; const void* fn; };
+const V2Config kV2[] = {
+    {4, 12, 32 * 4 - 4, reinterpret_cast<const void*>(&k_pdhmm2<4, 12>)},
+    {5, 8, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm2<5, 8>)},
+    {6, 8, 32 * 6 - 6, reinterpret_cast<const void*>(&k_pdhmm2<6, 8>)},
+};
+constexpr int kNumV2 = (int)(sizeof(kV2) / sizeof(kV2[0]));
 constexpr int kMaxQual = 254;
 constexpr int kMmSizePd = ((kMaxQual + 1) * (kMaxQual + 2)) >> 1;
 constexpr int kSmemMax = 232448;
@@ -93,6 +102,7 @@ struct PdEngine {
   int last_grid = 0;
   // k_pdhmm2 (single pass, haplotype-major tasks): reads per task, blocks per haplotype, tasks
   bool use_v2 = false, allow_v2 = true;
+  int v2 = 0;  // index into kV2
   int read_block = 1, n_blocks = 1;
   unsigned int n_tasks = 0;
   gklb_pdhmm_stats stats{};
@@ -118,8 +128,7 @@ int launch(PdEngine* e) {
   CU(cudaMemsetAsync(e->misc.p, 0, 8, e->stream));
   if (e->use_v2) {
     void* args2[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks};
-    CU(cudaLaunchKernel(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps2>), dim3(e->last_grid), dim3(kWarps2 * 32),
-                        args2, e->last_smem, e->stream));
+    CU(cudaLaunchKernel(kV2[e->v2].fn, dim3(e->last_grid), dim3(kV2[e->v2].warps * 32), args2, e->last_smem, e->stream));
     e->stats.kernel_launches++;
     return GKLB_OK;
   }
@@ -214,7 +223,10 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   long long warp_items = (n + gpw - 1) / gpw;
   // Reads that fit one pass take the haplotype-major kernel: a task is one haplotype x a block of reads, sized for
   // about 16 tasks per resident warp so that the dynamic queue balances the load.
-  e->use_v2 = e->allow_v2 && b->max_read <= kG * kK - kK;  // lane 0 all padding, see k_pdhmm2
+  e->use_v2 = false;
+  for (int i = kNumV2 - 1; i >= 0 && e->allow_v2; i--)
+    if (b->max_read <= kV2[i].max_read) { e->use_v2 = true; e->v2 = i; }
+  const int kWarps2 = kV2[e->v2].warps;
   if (e->use_v2) {
     if (cross) {
       const long long want = 16LL * kWarps2 * e->num_sms;
@@ -291,8 +303,7 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-  CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm2<kK, kWarps2>),
-                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  for (const V2Config& c : kV2) CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
   CU(cudaMemcpy(e->tables.p, t.q2err, sizeof(t.q2err), cudaMemcpyHostToDevice));

@@ -91,15 +91,16 @@ def _truncated_pairs(b, max_rows):
     return pb.PdhmmBatch.from_pairs(pairs)
 
 
+@pytest.mark.parametrize("max_rows", [124, 155, 186])
 @pytest.mark.parametrize("row_state", ["carry", "reset"])
-def test_single_pass_kernel_on_the_hardest_golden_pairs(row_state):
-    """Reads of at most 124 rows take the haplotype-major kernel (k_pdhmm2).  The synthetic golden file has random PD
+def test_single_pass_kernel_on_the_hardest_golden_pairs(row_state, max_rows):
+    """Reads of at most 124 / 155 / 186 rows take the haplotype-major kernel (k_pdhmm2 with 4 / 5 / 6 rows per lane).  The synthetic golden file has random PD
     bytes (nested / unclosed spans, negative bytes), lower-case bases and quals up to 93, but only reads of 223+ rows:
-    cut its reads to 60..124 rows and run them through that kernel in both row-state modes, and through the
+    cut its reads to 60..max_rows rows and run them through that kernel in both row-state modes, and through the
     pair-at-a-time kernel, and compare everything with the restatement of the reference's scalar path."""
     full, _ = pb.load_pdhmm_pairs_file(GOLDEN / "pdhmm_syn_1412_129_223.txt.gz")
-    b = _truncated_pairs(full, 124)
-    assert b.max_read == 124 and b.n == full.n
+    b = _truncated_pairs(full, max_rows)
+    assert b.max_read == max_rows and b.n == full.n
     ref = oracle.port_pdhmm(b, row_state == "carry", threads=oracle.host_threads())[0]
     got = {}
     for kernel in ("2", "1"):
