@@ -1,5 +1,6 @@
 #!/bin/bash
-# Round-end style check: GPU tests, smoke, both bench arms.
+# What the driver runs at round end, in one gpurun call: GPU tests, smoke(), both bench arms.
+#   gpurun --timeout 2400 -- bash bench/gpu_check.sh
 mkdir -p gpurun_out
 ( time timeout 1500 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -6
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2

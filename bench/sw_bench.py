@@ -82,6 +82,20 @@ def main():
             res[f"mismatches_vs_cpu_{name}"] = int(sum(1 for k in range(a.pairs) if rc[k] != cig[k] or ro[k] != off[k]))
         _, _, secs1 = oracle.ref_sw(s1, o1, s2, o2, params, strat, 1)
         res["cpu_1_thread_gcups"] = cells / secs1 / 1e9
+    # the reference API as it is: one pair per call (IntelSmithWaterman.align) -- latency, not throughput
+    t0 = time.perf_counter()
+    for k in range(200):
+        sw.align(refs[k], alts[k], P, SWOverhangStrategy.SOFTCLIP)
+    res["single_pair_call_us_gpu"] = (time.perf_counter() - t0) / 200 * 1e6
+    st1 = sw.stats()
+    res["single_pair_last_call_device_us"] = {"h2d": st1.h2d_ms * 1e3, "kernel": st1.kernel_ms * 1e3, "d2h": st1.d2h_ms * 1e3}
+    if oracle.ref_available():
+        t0 = time.perf_counter()
+        for k in range(200):
+            a1, b1 = pack([refs[k]])
+            a2, b2 = pack([alts[k]])
+            oracle.ref_sw(a1, b1, a2, b2, params, strat, 1)
+        res["single_pair_call_us_cpu_incl_python"] = (time.perf_counter() - t0) / 200 * 1e6
     pc, po, _ = oracle.port_sw(s1, o1, s2, o2, params, strat, threads)
     res["mismatches_vs_restatement"] = int(sum(1 for k in range(a.pairs) if pc[k] != cig[k] or po[k] != off[k]))
     sw.close()

@@ -140,9 +140,15 @@ int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch
   const size_t lines_stride = 5 * (size_t)line_w + (size_t)line_r;
   const size_t runs_stride = (size_t)line_w + line_r + 4;
   const size_t per_warp = 4 * (bt_words + lines_stride + runs_stride);
-  size_t free_b = 0, total_b = 0;
-  CU(cudaMemGetInfo(&free_b, &total_b));
-  const size_t budget = std::min<size_t>((size_t)16 << 30, (free_b + e->bt.cap + e->lines.cap + e->runs_scratch.cap) / 2);
+  // scratch budget: half of what is free, at most 16 GB; asked of the driver only when the batch could come near it
+  // (cudaMemGetInfo costs more than a small alignment)
+  const long long max_warps = std::min<long long>((long long)e->num_sms * kCtasPerSm * kWarps, ((long long)n + 0));
+  size_t budget = (size_t)1 << 30;
+  if (per_warp * (size_t)std::max<long long>(max_warps, 1) > budget) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    budget = std::min<size_t>((size_t)16 << 30, (free_b + e->bt.cap + e->lines.cap + e->runs_scratch.cap) / 2);
+  }
   long long warps = std::min<long long>((long long)e->num_sms * kCtasPerSm * kWarps, (long long)(budget / per_warp));
   if (warps < 1)
     return gklb_internal_fail(GKLB_ERR_OOM, "backtrack scratch of %zu bytes for one pair does not fit in device memory", per_warp);

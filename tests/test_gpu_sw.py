@@ -88,3 +88,56 @@ def test_argument_validation_matches_the_java_wrapper(sw):
         sw.align(b"A" * 32768, b"TCCG", p, SWOverhangStrategy.IGNORE)
     with pytest.raises(IllegalArgumentException):
         sw.align(b"ACCG", b"TCCG", SWParameters(64 * 1024 + 1, -5, -10, -10), SWOverhangStrategy.IGNORE)
+
+
+def test_batch_api_edge_cases(sw):
+    """Empty batch is a no-op, an unknown strategy code is refused (IntelSmithWaterman.java:144), one long and one
+    one-base pair share a batch (scratch is sized by the largest pair)."""
+    import ctypes as C
+    from gkl_b200 import native
+    from gkl_b200.smithwaterman import _SwBatch, _lib
+    lib = _lib()
+    empty = _SwBatch(0, None, None, None, None, 3, -1, -4, -3, 9)
+    assert lib.gklb_sw_align_batch(C.byref(empty), C.c_void_p(1), 8, C.c_void_p(1), C.c_void_p(1)) == native.OK
+    s1, o1 = pack([b"ACGT"])
+    s2, o2 = pack([b"ACGT"])
+    cig = np.zeros((1, 8), dtype=np.uint8)
+    clen, offs = np.zeros(1, np.int32), np.zeros(1, np.int32)
+    bad = _SwBatch(1, s1.ctypes.data, o1.ctypes.data, s2.ctypes.data, o2.ctypes.data, 3, -1, -4, -3, 13)
+    assert lib.gklb_sw_align_batch(C.byref(bad), cig.ctypes.data, 8, clen.ctypes.data, offs.ctypes.data) == native.ERR_INVALID
+    rng = np.random.default_rng(3)
+    long_a = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=5000)]
+    long_b = np.delete(long_a, slice(1000, 1040))
+    long_b[2500] = ord("A") if long_b[2500] != ord("A") else ord("C")
+    a, b = [long_a.tobytes(), b"G"], [long_b.tobytes(), b"G"]
+    s1, o1 = pack(a)
+    s2, o2 = pack(b)
+    for strat in STRATEGIES:
+        ref = oracle.port_sw(s1, o1, s2, o2, PARAMS[0], strat, threads=2)
+        cigs, off = sw.align_batch(a, b, SWParameters(*PARAMS[0]), SWOverhangStrategy(strat))
+        assert cigs == ref[0] and np.array_equal(off, ref[1])
+    assert cigs[1] == "1M"
+
+
+def test_cigar_buffer_rule_when_the_caller_buffer_is_short(sw):
+    """getCIGAR drops the elements that do not fit into what is left of the caller's buffer (PairWiseSW.h:426-431); the
+    one-pair entry point takes the buffer length like runSWOnePairBT does."""
+    import ctypes as C
+    from gkl_b200.smithwaterman import _lib
+    ref = np.frombuffer(b"ACGTACGTTTGACCA" * 4, dtype=np.uint8).copy()
+    alt = np.concatenate([ref[:20], ref[26:]]).copy()
+    full = sw.align(ref.tobytes(), alt.tobytes(), SWParameters(3, -1, -4, -3), SWOverhangStrategy.SOFTCLIP).cigar
+    assert "D" in full and len(full) > 5
+    for cap in (len(full), len(full) - 1, 3, 2):
+        buf = np.zeros(cap, dtype=np.uint8)
+        count, off = C.c_uint32(0), C.c_int32(0)
+        rc = _lib().gklb_sw_align(3, -1, -4, -3, ref.ctypes.data, alt.ctypes.data, len(ref), len(alt), 9, buf.ctypes.data,
+                                  cap, C.byref(count), C.byref(off))
+        assert rc == 0
+        # the same rule restated: elements first to last, each written only if it still fits
+        import re
+        want = ""
+        for el in re.findall(r"\d+[MIDS]", full):
+            if len(want) + len(el) <= cap:
+                want += el
+        assert bytes(buf[:count.value]).decode() == want
