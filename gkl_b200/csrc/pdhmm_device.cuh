@@ -88,6 +88,60 @@ __device__ __forceinline__ uint32_t column_mask(uint32_t y, uint32_t al) {
   return m;
 }
 
+// Column tables of one haplotype in shared memory, built by the G lanes of a group (lane t of G): the haplotype byte,
+// the SNP allele bits, the class mask of the match test, the state code of every column for each of the three
+// possible row-start states (+ DEL_END in bit 6, "twins written here are read later" in bit 7) and, for every
+// column, the first column at or after it that needs the state machine.  Returns the packed end states (the state
+// after the last column for each start state; pdhmm-serial.cc:370-385), valid on every lane.
+__device__ __forceinline__ int pd_build_column_tables(int t, int G, int group_leader_lane, int H, int max_hap,
+                                                      const int8_t* hap, const int8_t* pd, int carry_state, uint8_t* ys,
+                                                      uint8_t* infos, uint8_t* alleles, uint16_t* nspec, uint16_t* cmask) {
+  __syncwarp();
+  for (int c = t - kPdMargin; c < max_hap + kPdMargin; c += G) {
+    uint8_t y = 0, al = 0;
+    if (c >= 1 && c <= H) {
+      y = (uint8_t)hap[c - 1];
+      const uint8_t f = (uint8_t)pd[c - 1];
+      al = (f & 1) ? (f & 0x78) : 0;
+    }
+    ys[c] = y;
+    alleles[c] = al;
+    infos[c] = 0;
+    cmask[c] = (uint16_t)((c >= 1 && c <= H) ? column_mask(y, al) : 0u);
+  }
+  __syncwarp();
+  int end_state = 0;  // packed 2-bit end states for the three start states
+  if (t == 0) {
+    int s0 = 0, s1 = 1, s2 = 2;  // state entering column c when the row started NORMAL / INSIDE / AFTER
+    for (int c = 1; c <= H; c++) {
+      const uint8_t f = (uint8_t)pd[c - 1];
+      infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0) | ((s0 != 1 && (f & 6)) ? 0x80 : 0));
+      // pdhmm-serial.cc:370-385
+      if (s0 == 2) s0 = 0;
+      if (s1 == 2) s1 = 0;
+      if (s2 == 2) s2 = 0;
+      if (f & 2) s0 = s1 = s2 = 1;
+      if (f & 4) s0 = s1 = s2 = 2;
+    }
+    end_state = s0 | (s1 << 2) | (s2 << 4);
+    // which row-start states can occur at all: NORMAL, then the end state of the previous row, ...
+    int reach = 1, st = 0;
+    if (carry_state)
+      for (int r = 0; r < 3; r++) { st = (end_state >> (2 * st)) & 3; reach |= 1 << st; }
+    const uint32_t rmask = ((reach & 1) ? 0x03u : 0u) | ((reach & 2) ? 0x0Cu : 0u) | ((reach & 4) ? 0x30u : 0u) | 0x40u;
+    // a column is "plain" when every reachable start state sees it NORMAL and it does not close a deletion;
+    // nspec[c] = the first column >= c that is not plain (0xFFFF if none)
+    uint32_t nxt = 0xFFFFu;
+    for (int c = max_hap + kPdMargin - 1; c >= -kPdMargin; c--) {
+      if (c >= 1 && c <= H && (infos[c] & rmask)) nxt = (uint32_t)c;
+      nspec[c] = (uint16_t)nxt;
+    }
+  }
+  end_state = __shfl_sync(0xffffffffu, end_state, group_leader_lane);
+  __syncwarp();
+  return end_state;
+}
+
 // Smem per group: y[c], info[c], allele[c] (bytes) and nspec[c] (uint16: first column >= c that needs the state
 // machine) for c in [-kPdMargin, max_hap + kPdMargin), plus cmask[c] (uint16, see read_class): 7 bytes per column
 // MULTI = false: the host guarantees max_read <= G*K, so every pair takes one pass and the carry line does not exist.
@@ -128,49 +182,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
     const int64_t ro = ri * (int64_t)p.max_read;
 
     // ---- per-pair column tables in shared memory ----
-    __syncwarp();
-    for (int c = t - kPdMargin; c < p.max_hap + kPdMargin; c += G) {
-      uint8_t y = 0, al = 0;
-      if (c >= 1 && c <= H) {
-        y = (uint8_t)hap[c - 1];
-        const uint8_t f = (uint8_t)pd[c - 1];
-        al = (f & 1) ? (f & 0x78) : 0;
-      }
-      ys[c] = y;
-      alleles[c] = al;
-      infos[c] = 0;
-      cmask[c] = (uint16_t)((c >= 1 && c <= H) ? column_mask(y, al) : 0u);
-    }
-    __syncwarp();
-    int end_state = 0;  // packed 2-bit end states for the three start states
-    if (t == 0) {
-      int s0 = 0, s1 = 1, s2 = 2;  // state entering column c when the row started NORMAL / INSIDE / AFTER
-      for (int c = 1; c <= H; c++) {
-        const uint8_t f = (uint8_t)pd[c - 1];
-        infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0));
-        // pdhmm-serial.cc:370-385
-        if (s0 == 2) s0 = 0;
-        if (s1 == 2) s1 = 0;
-        if (s2 == 2) s2 = 0;
-        if (f & 2) s0 = s1 = s2 = 1;
-        if (f & 4) s0 = s1 = s2 = 2;
-      }
-      end_state = s0 | (s1 << 2) | (s2 << 4);
-      // which row-start states can occur at all: NORMAL, then the end state of the previous row, ...
-      int reach = 1, st = 0;
-      if (p.carry_state)
-        for (int r = 0; r < 3; r++) { st = (end_state >> (2 * st)) & 3; reach |= 1 << st; }
-      const uint32_t rmask = ((reach & 1) ? 0x03u : 0u) | ((reach & 2) ? 0x0Cu : 0u) | ((reach & 4) ? 0x30u : 0u) | 0x40u;
-      // a column is "plain" when every reachable start state sees it NORMAL and it does not close a deletion;
-      // nspec[c] = the first column >= c that is not plain (0xFFFF if none)
-      uint32_t nxt = 0xFFFFu;
-      for (int c = p.max_hap + kPdMargin - 1; c >= -kPdMargin; c--) {
-        if (c >= 1 && c <= H && (infos[c] & rmask)) nxt = (uint32_t)c;
-        nspec[c] = (uint16_t)nxt;
-      }
-    }
-    end_state = __shfl_sync(0xffffffffu, end_state, g * G);
-    __syncwarp();
+    const int end_state = pd_build_column_tables(t, G, g * G, H, p.max_hap, hap, pd, p.carry_state, ys, infos, alleles,
+                                                 nspec, cmask);
 
     const int n_pass = MULTI ? max(1, (R + CAP - 1) / CAP) : 1;
     int n_pass_w = n_pass;
@@ -492,46 +505,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
     const int8_t* pd = p.hap_pdbases + hi * p.max_hap;
 
     // ---- column tables of the haplotype (once per task) ----
-    __syncwarp();
-    for (int c = t - kPdMargin; c < p.max_hap + kPdMargin; c += G) {
-      uint8_t y = 0, al = 0;
-      if (c >= 1 && c <= H) {
-        y = (uint8_t)hap[c - 1];
-        const uint8_t f = (uint8_t)pd[c - 1];
-        al = (f & 1) ? (f & 0x78) : 0;
-      }
-      ys[c] = y;
-      alleles[c] = al;
-      infos[c] = 0;
-      cmask[c] = (uint16_t)((c >= 1 && c <= H) ? column_mask(y, al) : 0u);
-    }
-    __syncwarp();
-    int end_state = 0;
-    if (t == 0) {
-      int s0 = 0, s1 = 1, s2 = 2;
-      for (int c = 1; c <= H; c++) {
-        const uint8_t f = (uint8_t)pd[c - 1];
-        // bit 7: the twins written on this column are read later (it opens or closes a span outside a deletion)
-        infos[c] = (uint8_t)(s0 | (s1 << 2) | (s2 << 4) | ((f & 4) ? 0x40 : 0) | ((s0 != 1 && (f & 6)) ? 0x80 : 0));
-        if (s0 == 2) s0 = 0;
-        if (s1 == 2) s1 = 0;
-        if (s2 == 2) s2 = 0;
-        if (f & 2) s0 = s1 = s2 = 1;
-        if (f & 4) s0 = s1 = s2 = 2;
-      }
-      end_state = s0 | (s1 << 2) | (s2 << 4);
-      int reach = 1, st = 0;
-      if (p.carry_state)
-        for (int r = 0; r < 3; r++) { st = (end_state >> (2 * st)) & 3; reach |= 1 << st; }
-      const uint32_t rmask = ((reach & 1) ? 0x03u : 0u) | ((reach & 2) ? 0x0Cu : 0u) | ((reach & 4) ? 0x30u : 0u) | 0x40u;
-      uint32_t nxt = 0xFFFFu;
-      for (int c = p.max_hap + kPdMargin - 1; c >= -kPdMargin; c--) {
-        if (c >= 1 && c <= H && (infos[c] & rmask)) nxt = (uint32_t)c;
-        nspec[c] = (uint16_t)nxt;
-      }
-    }
-    end_state = __shfl_sync(0xffffffffu, end_state, 0);
-    __syncwarp();
+    const int end_state = pd_build_column_tables(t, G, 0, H, p.max_hap, hap, pd, p.carry_state, ys, infos, alleles, nspec,
+                                                 cmask);
     // orbit[k] = state row k starts in for k < 8; rows >= 2 repeat with a period that divides 6
     uint32_t orbit = 0;
     if (p.carry_state) {
