@@ -88,7 +88,7 @@ int itoa_len(int v) {
 }
 
 // The tail of getCIGAR (PairWiseSW.h:411-436): elements are emitted last to first; one that does not fit into what is
-// left of the buffer, or has length 0, is skipped.  Returns strnlen of what was written.
+// left of the buffer, or has length 0, is skipped.  Returns the number of bytes written; a NUL follows when it fits.
 int write_cigar(const uint32_t* runs, int n_runs, char* cigar, int cap) {
   int cur = 0;
   for (int k = n_runs - 1; k >= 0; k--) {
@@ -102,7 +102,8 @@ int write_cigar(const uint32_t* runs, int n_runs, char* cigar, int cap) {
       cigar[cur++] = st;
     }
   }
-  return (int)strnlen(cigar, (size_t)cur);
+  if (cur < cap) cigar[cur] = 0;
+  return cur;  // == strnlen of what was written (:436): every byte written is a digit or a letter
 }
 
 int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch, int32_t* cigar_len, int32_t* offsets) {
@@ -223,7 +224,6 @@ int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch
   cudaEventElapsedTime(&e->stats.kernel_ms, e->ev[1], e->ev[2]);
   cudaEventElapsedTime(&e->stats.d2h_ms, e->ev[2], e->ev[3]);
 
-  memset(cigars, 0, (size_t)n * (size_t)pitch);
   for (int k = 0; k < n; k++) {
     const long long l1 = b->seq1_off[k + 1] - b->seq1_off[k], l2 = b->seq2_off[k + 1] - b->seq2_off[k];
     const int cap = (int)std::min<long long>(pitch, 2 * std::max(l1, l2));  // IntelSmithWaterman.java:135

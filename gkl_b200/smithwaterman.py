@@ -153,7 +153,8 @@ class IntelSmithWaterman:
         s2, o2 = pack(alts)
         return self.align_packed(s1, o1, s2, o2, parameters, code)
 
-    def align_packed(self, s1, o1, s2, o2, parameters: SWParameters, code: int):
+    def align_packed_raw(self, s1, o1, s2, o2, parameters: SWParameters, code: int):
+        """The C-ABI call alone: returns (cigar rows uint8[n, pitch], cigar lengths int32[n], offsets int32[n])."""
         n = len(o1) - 1
         pitch = int(2 * max(int(np.diff(o1).max()), int(np.diff(o2).max())))
         cig = np.zeros((n, pitch), dtype=np.uint8)
@@ -164,7 +165,11 @@ class IntelSmithWaterman:
         rc = _lib().gklb_sw_align_batch(C.byref(b), cig.ctypes.data, pitch, clen.ctypes.data, offs.ctypes.data)
         if rc:
             _raise(rc)
-        return [bytes(cig[k, :clen[k]]).decode("ascii") for k in range(n)], offs
+        return cig, clen, offs
+
+    def align_packed(self, s1, o1, s2, o2, parameters: SWParameters, code: int):
+        cig, clen, offs = self.align_packed_raw(s1, o1, s2, o2, parameters, code)
+        return [bytes(cig[k, :clen[k]]).decode("ascii") for k in range(len(clen))], offs
 
     def stats(self) -> SwStats:
         st = SwStats()

@@ -47,9 +47,10 @@ typedef struct gklb_sw_stats {
 } gklb_sw_stats;
 
 GKLB_API int gklb_sw_init(void);
-/* cigars: n rows of cigar_pitch bytes, zero filled by the call; row k receives pair k's CIGAR (not terminated when it
- * fills the row).  Each pair's buffer length is min(cigar_pitch, 2 * max(len1, len2)) -- the array the Java wrapper
- * allocates (IntelSmithWaterman.java:135); elements that do not fit are dropped like getCIGAR drops them. */
+/* cigars: n rows of cigar_pitch bytes; row k receives pair k's CIGAR, cigar_len[k] bytes, followed by a NUL when
+ * the pair's buffer has room for it (the rest of the row is not touched).  Each pair's buffer length is
+ * min(cigar_pitch, 2 * max(len1, len2)) -- the array the Java wrapper allocates (IntelSmithWaterman.java:135);
+ * elements that do not fit are dropped like getCIGAR drops them. */
 GKLB_API int gklb_sw_align_batch(const gklb_sw_batch* batch, char* cigars, int32_t cigar_pitch, int32_t* cigar_len,
                                  int32_t* offsets);
 /* runSWOnePairBT (PairWiseSW.h:454): returns GKLB_OK or an error; *cigar_count = strnlen of what was written. */
