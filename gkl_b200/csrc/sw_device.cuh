@@ -78,7 +78,7 @@ struct SwWarpScratch {
 
 // One pair, K rows per lane.
 template <int K>
-__device__ __noinline__ void sw_pair(const SwParams& p, const SwWarpScratch& w, int pair, int lane) {
+__device__ __forceinline__ void sw_pair(const SwParams& p, const SwWarpScratch& w, int pair, int lane) {
   // scalars once into registers (p lives in the caller's frame)
   const int w_match = p.match, w_mismatch = p.mismatch, w_open = p.open, w_extend = p.extend, strategy = p.strategy;
   const int line_w = p.line_w;
@@ -190,15 +190,14 @@ __device__ __noinline__ void sw_pair(const SwParams& p, const SwWarpScratch& w, 
             for (int j = 1; j < K; j++) v = (j == last_local) ? Hl[j] : v;
             lastrow[c] = v;
           }
-          if (c == ncol) {
-#pragma unroll
-            for (int j = 0; j < K; j++)
-              if (i0 + j + 1 <= nrow) lastcol[i0 + j + 1] = Hl[j];
-          }
           if (writes_carry) { coutH[c] = Hl[K - 1]; coutF[c] = fbot; }
         }
         if (lane != 0 || active) dH = uH;  // this step's top is the next step's diagonal
       }
+      // every lane's last active step was column ncol: its registers hold the last column
+#pragma unroll
+      for (int j = 0; j < K; j++)
+        if (i0 + j + 1 <= nrow) lastcol[i0 + j + 1] = Hl[j];
       __syncwarp();
     }
 

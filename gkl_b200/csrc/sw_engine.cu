@@ -27,7 +27,7 @@ namespace {
                                 #call, cudaGetErrorString(e_));                                           \
   } while (0)
 
-constexpr int kWarps = 12;         // per CTA: 153 registers per thread leave room for 12 warps per SM
+constexpr int kWarps = 16;         // per CTA: 126 registers per thread, 16 warps per SM
 constexpr int kCtasPerSm = 1;
 
 struct Buf {
