@@ -76,10 +76,10 @@ struct SwWarpScratch {
   uint32_t* myruns;
 };
 
-// One pair, K rows per lane.
+// One pair, K rows per lane.  Inlined into the kernel's switch so that the scratch pointers keep their global address
+// space (a call boundary turns them into generic pointers).
 template <int K>
 __device__ __forceinline__ void sw_pair(const SwParams& p, const SwWarpScratch& w, int pair, int lane) {
-  // scalars once into registers (p lives in the caller's frame)
   const int w_match = p.match, w_mismatch = p.mismatch, w_open = p.open, w_extend = p.extend, strategy = p.strategy;
   const int line_w = p.line_w;
   constexpr int PASS_ROWS = 32 * K;
