@@ -72,11 +72,12 @@ cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_
 
 static const KernelEntry g_table[] = {
     // ---- product: packed fp32, folded recurrence with the shared-memory prior table (VAR 3) ----
-    // K <= 7 fits 12 warps per SM in 168 registers without the prior prefetch (VAR 5); K = 8 keeps 8 warps (VAR 4)
+    // 12 warps per SM in 168 registers without the prior prefetch (VAR 5); K = 8 spills ~60 bytes outside the steady
+    // loop and is still 1-2 % faster than 8 warps with the prefetch (VAR 4); the multi-pass kernel keeps 8 warps
     E_F2(8, 4, 12, false, 5),  E_F2(8, 5, 12, false, 5),  E_F2(8, 6, 12, false, 5),  E_F2(8, 7, 12, false, 5),
-    E_F2(8, 8, 8, false, 4),   E_F2(16, 5, 12, false, 5), E_F2(16, 6, 12, false, 5), E_F2(16, 7, 12, false, 5),
-    E_F2(16, 8, 8, false, 4),  E_F2(32, 5, 12, false, 5), E_F2(32, 6, 12, false, 5), E_F2(32, 7, 12, false, 5),
-    E_F2(32, 8, 8, false, 4),  E_F2(32, 8, 8, true, 4),
+    E_F2(8, 8, 12, false, 5),  E_F2(16, 5, 12, false, 5), E_F2(16, 6, 12, false, 5), E_F2(16, 7, 12, false, 5),
+    E_F2(16, 8, 12, false, 5), E_F2(32, 5, 12, false, 5), E_F2(32, 6, 12, false, 5), E_F2(32, 7, 12, false, 5),
+    E_F2(32, 8, 12, false, 5), E_F2(32, 8, 8, true, 4),
     // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
     E_D1(8, 4, 8, false, 3),  E_D1(8, 5, 8, false, 3),  E_D1(8, 6, 8, false, 3),  E_D1(8, 7, 8, false, 3),
     E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 8, false, 3), E_D1(16, 6, 8, false, 3), E_D1(16, 7, 8, false, 3),
@@ -86,6 +87,7 @@ static const KernelEntry g_table[] = {
     // ---- measurement only ----
     E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0),
     E_F2(16, 7, 8, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 7, 8, false, 5), E_F2(32, 5, 8, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 5), E_F2(8, 4, 16, false, 5),
+    E_F2(16, 8, 8, false, 4), E_F2(32, 8, 8, false, 4), E_F2(8, 8, 8, false, 4),
     E_F2(16, 7, 12, false, 6), E_F2(16, 7, 8, false, 6), E_F2(16, 7, 10, false, 6), E_F2(16, 7, 10, false, 5),
     E_F1(8, 13, 8, false, 4), E_F1(8, 13, 8, false, 3), E_F1(8, 13, 12, false, 4), E_F1(16, 7, 16, false, 4),
     E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3),
