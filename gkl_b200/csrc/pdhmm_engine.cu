@@ -220,36 +220,40 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   p.carry_stride = carry_stride;
   p.carry_state = e->carry_state;
   e->last_smem = smem;
+  // Reads that fit one pass take the haplotype-major kernel (the smallest rows-per-lane variant that covers them,
+  // if its column tables fit in shared memory): a task is one haplotype x a block of reads, sized for about 16 tasks
+  // per resident warp so that the dynamic queue balances the load.  Everything else: one pair per group, k_pdhmm.
   long long warp_items = (n + gpw - 1) / gpw;
-  // Reads that fit one pass take the haplotype-major kernel: a task is one haplotype x a block of reads, sized for
-  // about 16 tasks per resident warp so that the dynamic queue balances the load.
+  int warps_per_cta = kWarps;
   e->use_v2 = false;
   for (int i = kNumV2 - 1; i >= 0 && e->allow_v2; i--)
-    if (b->max_read <= kV2[i].max_read) { e->use_v2 = true; e->v2 = i; }
-  const int kWarps2 = kV2[e->v2].warps;
+    if (b->max_read <= kV2[i].max_read && (size_t)kV2[i].warps * 7 * col_pitch <= (size_t)kSmemMax) {
+      e->use_v2 = true;
+      e->v2 = i;
+    }
   if (e->use_v2) {
+    const int w2 = kV2[e->v2].warps;
+    long long tasks = n;
+    e->read_block = 1;
+    e->n_blocks = 1;
     if (cross) {
-      const long long want = 16LL * kWarps2 * e->num_sms;
-      long long nb = std::min<long long>(n_reads, std::max<long long>(1, (want + n_haps - 1) / n_haps));
+      const long long want = 16LL * w2 * e->num_sms;
+      const long long nb = std::min<long long>(n_reads, std::max<long long>(1, (want + n_haps - 1) / n_haps));
       e->read_block = (int)((n_reads + nb - 1) / nb);
       e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
-      warp_items = (long long)e->n_blocks * n_haps;
-    } else {
-      e->read_block = 1;
-      e->n_blocks = 1;
-      warp_items = n;
+      tasks = (long long)e->n_blocks * n_haps;
     }
-    if (warp_items > 0xFFFFFFF0LL) e->use_v2 = false;  // the task counter is 32 bits wide
-    e->n_tasks = (unsigned int)warp_items;
-  }
-  if (!e->use_v2) warp_items = (n + gpw - 1) / gpw;
-  const int warps_per_cta = e->use_v2 ? kWarps2 : kWarps;
-  if (e->use_v2) {
-    smem = (size_t)kWarps2 * 7 * col_pitch;
-    if (smem > (size_t)kSmemMax) { e->use_v2 = false; smem = (size_t)kWarps * gpw * 7 * col_pitch; warp_items = (n + gpw - 1) / gpw; }
+    if (tasks > 0xFFFFFFF0LL) {
+      e->use_v2 = false;  // the task counter is 32 bits wide
+    } else {
+      e->n_tasks = (unsigned int)tasks;
+      warp_items = tasks;
+      warps_per_cta = w2;
+      smem = (size_t)w2 * 7 * col_pitch;
+    }
   }
   e->last_smem = smem;
-  e->last_grid = (int)std::min<long long>(e->num_sms, (warp_items + warps_per_cta - 1) / (e->use_v2 ? kWarps2 : kWarps));
+  e->last_grid = (int)std::min<long long>(e->num_sms, (warp_items + warps_per_cta - 1) / warps_per_cta);
   e->have_last = true;
   e->stats = gklb_pdhmm_stats{};
   e->stats.pairs = n;
