@@ -97,3 +97,26 @@ def test_product_package_does_not_touch_the_oracle():
             text = p.read_text()
             assert "import oracle" not in text and "from oracle" not in text, p
             assert "libgklb_oracle" not in text and "libgkl_ref" not in text, p
+
+
+def test_smithwaterman_mirror_validates_like_the_java_wrapper_and_refuses_without_a_gpu():
+    # IntelSmithWaterman.java:122-145; no device call is made for rejected arguments
+    import pytest
+    from gkl_b200.pairhmm import IllegalArgumentException, NullPointerException
+    from gkl_b200.smithwaterman import IntelSmithWaterman, SWOverhangStrategy, SWParameters
+    sw = IntelSmithWaterman()
+    p = SWParameters(10, -5, -10, -10)
+    for args, exc in (((None, b"A", p, SWOverhangStrategy.IGNORE), NullPointerException),
+                      ((b"A", None, p, SWOverhangStrategy.IGNORE), NullPointerException),
+                      ((b"A", b"A", None, SWOverhangStrategy.IGNORE), NullPointerException),
+                      ((b"A", b"A", p, None), NullPointerException),
+                      ((b"", b"A", p, SWOverhangStrategy.IGNORE), IllegalArgumentException),
+                      ((b"A" * 32768, b"A", p, SWOverhangStrategy.IGNORE), IllegalArgumentException),
+                      ((b"A", b"A", SWParameters(65537, 0, 0, 0), SWOverhangStrategy.IGNORE), IllegalArgumentException),
+                      ((b"A", b"A", p, 13), IllegalArgumentException)):
+        with pytest.raises(exc):
+            sw.align(*args)
+    assert [s.value for s in SWOverhangStrategy] == [9, 10, 11, 12]  # getStrategy (:153-170)
+    import torch
+    if not torch.cuda.is_available():
+        assert sw.load() is False  # no CPU path: GATK keeps its Java aligner
