@@ -106,7 +106,7 @@ int write_cigar(const uint32_t* runs, int n_runs, char* cigar, int cap) {
   return cur;  // == strnlen of what was written (:436): every byte written is a digit or a letter
 }
 
-int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch, int32_t* cigar_len, int32_t* offsets) {
+int align_chunk(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch, int32_t* cigar_len, int32_t* offsets) {
   if (!b || !cigars || !cigar_len || !offsets) return gklb_internal_fail(GKLB_ERR_INVALID, "null argument");
   if (b->n < 0) return gklb_internal_fail(GKLB_ERR_INVALID, "negative batch size");
   if (b->n == 0) return GKLB_OK;
@@ -159,8 +159,8 @@ int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch
 
   CU(cudaEventRecord(e->ev[0], s));
   const size_t b1 = (size_t)b->seq1_off[n], b2 = (size_t)b->seq2_off[n];
-  CU(e->seq1.ensure(b1 + 16));
-  CU(e->seq2.ensure(b2 + 16));
+  CU(e->seq1.ensure(b1 - (size_t)b->seq1_off[0] + 16));
+  CU(e->seq2.ensure(b2 - (size_t)b->seq2_off[0] + 16));
   CU(e->off1.ensure(sizeof(int64_t) * (n + 1)));
   CU(e->off2.ensure(sizeof(int64_t) * (n + 1)));
   CU(e->order.ensure(sizeof(int32_t) * n));
@@ -233,6 +233,48 @@ int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch
     cigar_len[k] = write_cigar(runs.data() + start, count, cigars + (size_t)k * pitch, cap);
     offsets[k] = heads[2 * (size_t)n + k];
   }
+  return GKLB_OK;
+}
+
+// The run arena of one launch is indexed with 32 bits and sized for the worst case (len1 + len2 + 2 elements per
+// pair), so very large batches are cut into consecutive chunks of pairs (GKLB_SW_MAX_RUN_ELEMENTS overrides the
+// bound, for tests); outputs are per pair, so the chunks simply write their own rows.
+int align_batch(SwEngine* e, const gklb_sw_batch* b, char* cigars, int32_t pitch, int32_t* cigar_len, int32_t* offsets) {
+  if (!b || !cigars || !cigar_len || !offsets) return gklb_internal_fail(GKLB_ERR_INVALID, "null argument");
+  if (b->n < 0) return gklb_internal_fail(GKLB_ERR_INVALID, "negative batch size");
+  if (b->n == 0) return GKLB_OK;
+  if (!b->seq1_off || !b->seq2_off) return gklb_internal_fail(GKLB_ERR_INVALID, "null array in batch");
+  static const long long max_elements = [] {
+    const char* v = getenv("GKLB_SW_MAX_RUN_ELEMENTS");
+    return (v && atoll(v) > 0) ? atoll(v) : (1LL << 27);
+  }();
+  gklb_sw_stats total{};
+  int k0 = 0;
+  while (k0 < b->n) {
+    long long elements = 0;
+    int k1 = k0;
+    while (k1 < b->n) {
+      const long long add = (b->seq1_off[k1 + 1] - b->seq1_off[k1]) + (b->seq2_off[k1 + 1] - b->seq2_off[k1]) + 2;
+      if (k1 > k0 && elements + add > max_elements) break;
+      elements += add;
+      k1++;
+    }
+    gklb_sw_batch part = *b;
+    part.n = k1 - k0;
+    part.seq1_off = b->seq1_off + k0;
+    part.seq2_off = b->seq2_off + k0;
+    const int rc = align_chunk(e, &part, cigars + (size_t)k0 * pitch, pitch, cigar_len + k0, offsets + k0);
+    if (rc) return rc;
+    total.pairs += e->stats.pairs;
+    total.cells += e->stats.cells;
+    total.h2d_ms += e->stats.h2d_ms;
+    total.kernel_ms += e->stats.kernel_ms;
+    total.d2h_ms += e->stats.d2h_ms;
+    total.kernel_launches += e->stats.kernel_launches;
+    total.warps = std::max(total.warps, e->stats.warps);
+    k0 = k1;
+  }
+  e->stats = total;
   return GKLB_OK;
 }
 

@@ -141,3 +141,29 @@ def test_cigar_buffer_rule_when_the_caller_buffer_is_short(sw):
             if len(want) + len(el) <= cap:
                 want += el
         assert bytes(buf[:count.value]).decode() == want
+
+
+def test_large_batches_are_cut_into_chunks(sw):
+    """The run arena of one launch is bounded; with the bound forced low (it is read once per process, so a fresh
+    process) the same batch goes through several launches and must give the same answers."""
+    import subprocess
+    import sys
+    code = (
+        "import os, sys, numpy as np\n"
+        "os.environ['GKLB_SW_MAX_RUN_ELEMENTS'] = '900'\n"
+        "sys.path.insert(0, '.')\n"
+        "import oracle\n"
+        "from gkl_b200.smithwaterman import IntelSmithWaterman, SWOverhangStrategy, SWParameters\n"
+        "from tests.test_oracle_sw import pack, random_pairs\n"
+        "a, b, params, strat = random_pairs(3, 300, max_len=60)\n"
+        "s1, o1 = pack(a); s2, o2 = pack(b)\n"
+        "ref = oracle.port_sw(s1, o1, s2, o2, params, strat, threads=2)\n"
+        "sw = IntelSmithWaterman(); assert sw.load()\n"
+        "cig, off = sw.align_batch(a, b, SWParameters(*params), SWOverhangStrategy(strat))\n"
+        "st = sw.stats(); sw.close()\n"
+        "assert cig == ref[0] and np.array_equal(off, ref[1])\n"
+        "assert st.kernel_launches > 5 and st.pairs == 300, (st.kernel_launches, st.pairs)\n"
+        "print('chunks ok', st.kernel_launches)\n")
+    from pathlib import Path
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=str(Path(__file__).resolve().parents[1]))
+    assert r.returncode == 0 and "chunks ok" in r.stdout, r.stdout + r.stderr
