@@ -718,10 +718,16 @@ int do_fetch(gklb_engine* e, double* out) {
   CU(cudaSetDevice(e->device));
   if (e->classes.empty()) return GKLB_OK;
   if (!out) return fail(GKLB_ERR_INVALID, "likelihoods is null");
-  CU(cudaMemcpyAsync(out, e->d_out.p, sizeof(double) * (size_t)e->stats.pairs, cudaMemcpyDeviceToHost, e->stream));
+  // Small results travel through the engine's pinned buffer: a device->host copy into the caller's (usually
+  // pageable) array is staged by the driver and costs tens of microseconds more per call than the memcpy here.
+  const size_t out_bytes = sizeof(double) * (size_t)e->stats.pairs;
+  const bool via_pinned = out_bytes <= ((size_t)2 << 20) && !e->pending_out;  // the buffer also serves submit/wait
+  if (via_pinned) CU(e->h_out.ensure(out_bytes));
+  CU(cudaMemcpyAsync(via_pinned ? e->h_out.p : (void*)out, e->d_out.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(unsigned int) * (size_t)e->n_counters,
                      cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
+  if (via_pinned) memcpy(out, e->h_out.p, out_bytes);
   int64_t fb = 0;
   const unsigned int* hc = static_cast<const unsigned int*>(e->h_counters.p);
   for (auto& c : e->classes) fb += hc[c.counter0];
