@@ -85,3 +85,21 @@ def test_restatement_matches_gkl_on_adversarial_pairs():
         for engine in (1, 2) if oracle.ref_avx512_supported() else (1,):
             r = oracle.ref_sw(s1, o1, s2, o2, params, strat, threads=oracle.host_threads(), engine=engine)
             assert p[0] == r[0] and np.array_equal(p[1], r[1]), (seed, engine)
+
+
+@pytest.mark.skipif(not oracle.ref_available() or not oracle.REFERENCE_ROOT.is_dir(),
+                    reason="needs /root/reference and oracle/_ref (development container)")
+def test_restatement_matches_gkl_on_the_whole_reference_test_file():
+    """All 14 196 pairs of src/test/resources/smith-waterman.SOFTCLIP.in with the parameters and strategy of
+    SmithWatermanUnitTest.simpleTest (which aligns them without asserting anything)."""
+    path = oracle.REFERENCE_ROOT / "src/test/resources/smith-waterman.SOFTCLIP.in"
+    lines = [l for l in path.read_text().split("\n") if l]
+    refs = [l.encode() for l in lines[0::2]]
+    alts = [l.encode() for l in lines[1::2]]
+    n = min(len(refs), len(alts))
+    s1, o1 = pack(refs[:n])
+    s2, o2 = pack(alts[:n])
+    threads = oracle.host_threads()
+    p = oracle.port_sw(s1, o1, s2, o2, PARAMS[0], 9, threads=threads)
+    r = oracle.ref_sw(s1, o1, s2, o2, PARAMS[0], 9, threads=threads)
+    assert n == 14196 and p[0] == r[0] and np.array_equal(p[1], r[1])
