@@ -42,6 +42,16 @@ __global__ void __launch_bounds__(256) k(float* out, const float* in, int iters)
         if (MODE == 6) acc2[i] = __ffma2_rn(acc2[i], a2[0], b2[0]);  // FFMA2, shared operands
       }
     }
+    if (MODE == 8 || MODE == 9 || MODE == 10) {
+#pragma unroll
+      for (int i = 0; i < N_ACC / 2; i++) {
+        // FFMA2 whose first operand is a 32-bit scalar broadcast to both halves (SASS R.F32), as in the
+        // two-haplotypes-per-lane sweep: a distinct scalar per instruction
+        if (MODE == 8) acc2[i] = __ffma2_rn(make_float2(a[i], a[i]), acc2[i], b2[i]);
+        if (MODE == 9) acc2[i] = __fmul2_rn(make_float2(a[i], a[i]), acc2[i]);   // FMUL2, scalar x pair
+        if (MODE == 10) acc2[i] = __fmul2_rn(a2[i], acc2[i]);                    // FMUL2, pair x pair
+      }
+    }
   }
   float s = 0;
 #pragma unroll
@@ -92,5 +102,8 @@ int main() {
   run<7>("ffma_imm", 2, N_ACC, p.multiProcessorCount, out, in);
   run<5>("ffma2_3_distinct", 4, N_ACC / 2, p.multiProcessorCount, out, in);
   run<6>("ffma2_shared_operands", 4, N_ACC / 2, p.multiProcessorCount, out, in);
+  run<8>("ffma2_scalar_a_2_pairs", 4, N_ACC / 2, p.multiProcessorCount, out, in);
+  run<9>("fmul2_scalar_x_pair", 2, N_ACC / 2, p.multiProcessorCount, out, in);
+  run<10>("fmul2_pair_x_pair", 2, N_ACC / 2, p.multiProcessorCount, out, in);
   return 0;
 }

@@ -23,6 +23,7 @@
 
 #include "../../include/gklb_pairhmm.h"
 #include "pairhmm_device.cuh"
+#include "pairhmm_h2.cuh"
 #include "pairhmm_kernels.h"
 #include "pairhmm_tables.h"
 
@@ -134,6 +135,11 @@ struct Tile {
   int hap0 = 0, n = 0, max_len = 0;
   size_t meta_off = 0;
   uint32_t bytes = 0;
+  // the same haplotypes as a pair image (pairhmm_h2.cuh): sorted by length, two per byte column
+  int n_pairs = 0;
+  size_t pmeta_off = 0;
+  uint32_t pbytes = 0;
+  std::vector<int> order;   // haplotype indices (in the batch) by decreasing length; pair q = order[2q], order[2q+1]
 };
 
 }  // namespace
@@ -209,7 +215,7 @@ int parse_forced(gklb_engine* e) {
   int G, K, W, V;
   if (sscanf(s, "%7[^,],%d,%d,%d,%d", pol, &G, &K, &W, &V) != 5)
     return fail(GKLB_ERR_INVALID, "GKLB_FORCE_KERNEL must be policy,G,K,warps,var (got '%s')", s);
-  int p = !strcmp(pol, "f2") ? POL_F2 : !strcmp(pol, "f1") ? POL_F1 : !strcmp(pol, "d1") ? POL_D1 : -1;
+  int p = !strcmp(pol, "f2") ? POL_F2 : !strcmp(pol, "f1") ? POL_F1 : !strcmp(pol, "d1") ? POL_D1 : !strcmp(pol, "h2") ? POL_H2 : -1;
   if (p < 0 || !find_kernel(p, G, K, W, 0, V)) return fail(GKLB_ERR_INVALID, "no compiled kernel for '%s'", s);
   e->forced = true;
   e->f_policy = p; e->f_G = G; e->f_K = K; e->f_warps = W; e->f_var = V;
@@ -314,7 +320,8 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
 uint32_t warp_slot_bytes(const ClassInst& c, const KernelEntry* k, bool list_mode) {
   const uint32_t rpw = (uint32_t)((32 / c.G) * k->nr);
   const uint32_t rec = (list_mode || c.multi) ? 0u : (uint32_t)align_up((size_t)rpw * 5 * c.stride, 128);
-  const uint32_t tbl = (k->var >= 3) ? (uint32_t)(kPriorSyms * c.K * 32 * 8) : 0u;
+  const uint32_t tbl = (k->policy == POL_H2) ? (uint32_t)(kPriorSyms * c.K * 32 * 4)
+                       : (k->var >= 3)          ? (uint32_t)(kPriorSyms * c.K * 32 * 8) : 0u;
   return rec + tbl;
 }
 
@@ -353,6 +360,21 @@ int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, size_t* meta_bytes) 
     t.bytes = (uint32_t)align_up(align_up((size_t)8 * t.n, 16) + data, 16);
     t.meta_off = *meta_bytes;
     *meta_bytes += align_up(t.bytes, 128);
+    // pair image: haplotypes by decreasing length, adjacent ones share a byte column (never larger than t.bytes)
+    t.order.resize(t.n);
+    for (int i = 0; i < t.n; i++) t.order[i] = t.hap0 + i;
+    std::stable_sort(t.order.begin(), t.order.end(), [&](int x, int y) {
+      return b->hap_off[x + 1] - b->hap_off[x] > b->hap_off[y + 1] - b->hap_off[y];
+    });
+    t.n_pairs = (t.n + 1) / 2;
+    size_t pdata = 0;
+    for (int q = 0; q < t.n_pairs; q++) {
+      const int a = t.order[2 * q];
+      pdata += kHapLeftMargin + (size_t)(b->hap_off[a + 1] - b->hap_off[a]) + kHapRightMargin;
+    }
+    t.pbytes = (uint32_t)align_up(align_up((size_t)20 * t.n_pairs, 16) + pdata, 16);
+    t.pmeta_off = *meta_bytes;
+    *meta_bytes += align_up(t.pbytes, 128);
     e->tiles.push_back(t);
   }
   return GKLB_OK;
@@ -372,6 +394,32 @@ void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) 
     uint8_t* dst = img + off + kHapLeftMargin;
     for (int c = 0; c < len; c++) dst[c] = panel_byte(b->hap_bases[o + c]);
     off += kHapLeftMargin + len + kHapRightMargin;
+  }
+}
+
+void build_pair_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) {
+  memset(img, 0, t.pbytes);
+  int32_t* ppos = reinterpret_cast<int32_t*>(img);
+  int32_t* lenA = ppos + t.n_pairs;
+  int32_t* lenB = lenA + t.n_pairs;
+  int32_t* idxA = lenB + t.n_pairs;
+  int32_t* idxB = idxA + t.n_pairs;
+  size_t off = align_up((size_t)20 * t.n_pairs, 16);
+  for (int q = 0; q < t.n_pairs; q++) {
+    const int a = t.order[2 * q];
+    const bool has_b = 2 * q + 1 < t.n;
+    const int bb = has_b ? t.order[2 * q + 1] : a;   // an odd haplotype out is paired with itself, result B dropped
+    const int64_t oa = b->hap_off[a], ob = b->hap_off[bb];
+    const int la = (int)(b->hap_off[a + 1] - oa), lb = (int)(b->hap_off[bb + 1] - ob);
+    ppos[q] = (int32_t)(off + kHapLeftMargin - 1);
+    lenA[q] = la;
+    lenB[q] = lb;
+    idxA[q] = a;
+    idxB[q] = has_b ? bb : -1;
+    uint8_t* dst = img + off + kHapLeftMargin;
+    for (int c = 0; c < la; c++)
+      dst[c] = (uint8_t)(base_index(b->hap_bases[oa + c]) | (c < lb ? base_index(b->hap_bases[ob + c]) << 3 : 0));
+    off += kHapLeftMargin + la + kHapRightMargin;
   }
 }
 
@@ -468,7 +516,10 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
   if (carry_bytes) CU(e->d_carry.ensure(carry_bytes));
 
   uint8_t* hm = static_cast<uint8_t*>(e->h_meta.p);
-  for (auto& t : e->tiles) build_tile_image(t, &hb, hm + t.meta_off);
+  for (auto& t : e->tiles) {
+    build_tile_image(t, &hb, hm + t.meta_off);
+    build_pair_image(t, &hb, hm + t.pmeta_off);
+  }
   for (auto& c : e->classes) {
     memcpy(hm + c.meta_rid, c.rid.data(), sizeof(int32_t) * c.n_rec);
     memcpy(hm + c.meta_len, c.len.data(), sizeof(int32_t) * c.n_rec);
@@ -526,6 +577,16 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
   return GKLB_OK;
 }
 
+int tasks_per_warp_target() {
+  // aim at ~this many tasks per resident warp: enough for the dynamic queue to balance the tail, few enough that
+  // the per-task constant set-up stays negligible (GKLB_TASKS_PER_WARP overrides, for measurement)
+  static const int v = [] {
+    const char* s = getenv("GKLB_TASKS_PER_WARP");
+    return s && atoi(s) > 0 ? atoi(s) : 32;
+  }();
+  return v;
+}
+
 // Fill the per-class kernel parameters for one (class, tile, kernel) combination.
 void fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index,
                  SweepParams* out, int* grid_out, size_t* smem_out, uint32_t* slot_bytes_out) {
@@ -564,12 +625,7 @@ void fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kernel
   const int slots = e->num_sms * k->warps;
   if (!list_mode) {
     const int n_blocks = c.n_rec / rpw;
-    // aim at ~tasks_per_warp tasks per resident warp: enough for the dynamic queue to balance the tail, few
-    // enough that the per-task constant set-up stays negligible (GKLB_TASKS_PER_WARP overrides, for measurement)
-    static const long long tasks_per_warp = [] {
-      const char* v = getenv("GKLB_TASKS_PER_WARP");
-      return (long long)(v && atoi(v) > 0 ? atoi(v) : 32);
-    }();
+    const long long tasks_per_warp = tasks_per_warp_target();
     long long chunk = ((long long)n_blocks * t.n) / (tasks_per_warp * slots);
     chunk = std::max(1LL, std::min(chunk, 32LL));
     if (c.multi) chunk = 1;
@@ -590,7 +646,62 @@ void fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kernel
   p.slot_bytes = *slot_bytes_out;
 }
 
+// The two-haplotypes-per-lane kernel (pairhmm_h2.cuh): tasks are (block of 32/G records) x (chunk of pairs).
+int launch_h2(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, int tile_index) {
+  const HostTables& ht = host_tables();
+  H2Params p;
+  memset(&p, 0, sizeof(p));
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  p.panel.image = dm + t.pmeta_off;
+  p.panel.bytes = t.pbytes;
+  p.panel.n_pairs = t.n_pairs;
+  p.panel.n_haps_total = e->n_haps;
+  p.panel.max_hap_len = t.max_len;
+  p.cls.records = static_cast<const uint8_t*>(e->d_records.p) + c.rec_off;
+  p.cls.rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
+  p.cls.rec_len = reinterpret_cast<const int32_t*>(dm + c.meta_len);
+  p.cls.n_rec = c.n_rec;
+  p.cls.rows = c.rows;
+  p.cls.stride = c.stride;
+  p.cls.n_pass = 1;
+  p.ph2pr = e->d_ph2pr_f;
+  p.mm = e->d_mm_f;
+  p.out = static_cast<double*>(e->d_out.p);
+  unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
+  p.fb_count = counters + c.counter0;
+  p.fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + c.fb_off : nullptr;
+  p.task_counter = counters + c.counter0 + 1 + 2 * tile_index;
+  p.init_const = ht.init_f;
+  p.log10_init = ht.log10_init_f;
+  const int gpw = 32 / c.G;
+  const int n_blocks = c.n_rec / gpw;
+  const int slots = e->num_sms * k->warps;
+  long long chunk = ((long long)n_blocks * t.n_pairs) / ((long long)tasks_per_warp_target() * slots);
+  chunk = std::max(1LL, std::min(chunk, 32LL));
+  chunk = std::min<long long>(chunk, t.n_pairs);
+  p.pair_chunk = (int)chunk;
+  p.n_chunks = (t.n_pairs + p.pair_chunk - 1) / p.pair_chunk;
+  p.n_tasks = n_blocks * p.n_chunks;
+  const int grid = std::min(e->num_sms, (p.n_tasks + k->warps - 1) / k->warps);
+  p.slot_bytes = warp_slot_bytes(c, k, false);
+  const size_t smem = smem_layout(k->warps, t.pbytes, p.slot_bytes, 4).total;
+  if (smem > (size_t)kSmemMax) return fail(GKLB_ERR_STATE, "shared memory plan exceeds the device limit (%zu)", smem);
+  if (grid <= 0) return GKLB_OK;
+  while ((int)e->kev.size() < e->kev_used + 2) {
+    cudaEvent_t ev;
+    CU(cudaEventCreate(&ev));
+    e->kev.push_back(ev);
+  }
+  CU(cudaEventRecord(e->kev[e->kev_used], e->stream));
+  CU(launch_h2_kernel(k->fn_tasks, p, grid, k->warps * 32, smem, e->stream));
+  CU(cudaEventRecord(e->kev[e->kev_used + 1], e->stream));
+  e->kev_used += 2;
+  e->stats.kernel_launches++;
+  return GKLB_OK;
+}
+
 int launch_one(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index) {
+  if (k->policy == POL_H2) return launch_h2(e, c, t, k, tile_index);
   SweepParams p;
   int grid;
   size_t smem;

@@ -1,0 +1,307 @@
+// pairhmm_h2.cuh -- the "two haplotypes per lane" forward sweep (policy H2), sm_100a.
+//
+// Same recurrence and the same systolic mapping as pairhmm_device.cuh (lane t of a group of G lanes
+// owns K consecutive read rows, the bottom row moves to lane t+1 by shuffle), but the two halves of
+// every packed fp32 register pair hold the SAME read against TWO haplotypes of similar length
+// instead of two reads against one haplotype.  What that buys on sm_100:
+//   * every per-row constant (pMM, kappa, pXX, pMY', Ax) is now a 32-bit scalar that FFMA2/FMUL2 read
+//     through their broadcast operand form (SASS `R.F32`): 5 K registers instead of 10 K, and one
+//     32-bit register-file read instead of a 64-bit one for a third of the operands -- the packed-read
+//     kernel is bound by register operand bandwidth;
+//   * with the registers that frees, a lane can own up to 13 rows: 101-row reads run as 8 lanes x 13
+//     rows (3 padding rows, 7-step fill) instead of 16 x 7 (11 padding rows, 15-step fill), and the
+//     per-step overhead (shuffles, symbol fetch, loop) is amortised over twice as many cells;
+//   * constants and the prior table are set up for one read per lane instead of two.
+// The price is the prior: the two haplotypes show different symbols, so it is two LDS.32 per cell pair
+// instead of one LDS.64 (the shared-memory bandwidth used is the same).
+//
+// The panel is a PAIR image (built on the host by engine.cu: haplotypes of a tile sorted by length and
+// paired): one byte per column = symbol of haplotype A | symbol of haplotype B << 3.
+// Reference semantics: avx-pairhmm-template.h:106-223,325-371 and IntelPairHmm.cc:150-169, as in
+// pairhmm_device.cuh (W form of the insertion state, folded Y and diagonal states).
+#pragma once
+
+#include "pairhmm_device.cuh"
+
+namespace gklb {
+
+struct PairPanelRef {      // one haplotype tile as a pair image, bulk-copied to shared memory:
+  const uint8_t* image;    //   int32 ppos[n]   byte offset of column 0 of pair i inside the image
+  uint32_t bytes;          //   int32 lenA[n], lenB[n]   (lenA >= lenB; lenB == 0: no second haplotype)
+  int n_pairs;             //   int32 idxA[n], idxB[n]   haplotype index in the batch
+  int n_haps_total;        //   pad to 16, then per pair: left margin | bytes | right margin
+  int max_hap_len;
+};
+
+struct H2Params {
+  PairPanelRef panel;
+  ClassRef cls;
+  const float* ph2pr;
+  const float* mm;
+  double* out;
+  int pair_chunk;          // haplotype pairs per task
+  int n_chunks;
+  int n_tasks;
+  unsigned int* task_counter;
+  uint2* fb_items;         // (record, haplotype) of pairs whose scaled sum is < 1e-28f or not finite
+  unsigned int* fb_count;
+  float init_const;        // 2^120
+  float log10_init;
+  uint32_t slot_bytes;
+};
+
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+
+template <int K>
+struct LaneRowsH2 {
+  float Am[K], kap[K], pXX[K], pMY[K], Ax[K];
+  float gTop, xlast;
+  uint32_t padmask;
+};
+
+// One read's rows [row0, row0 + K) -> scalar constants + this lane's column of the prior table.
+// Same construction as load_lane_rows<.., VAR 5> (pairhmm_device.cuh), one read per lane.
+template <int K>
+__device__ __forceinline__ void load_lane_rows_h2(LaneRowsH2<K>& L, const uint8_t* rec, int stride, int n_rows, int row0,
+                                                  int n_pad, bool top_is_row0, const float* __restrict__ ph2pr,
+                                                  const float* __restrict__ mm, float* tbl) {
+  uint32_t pm = 0;
+#pragma unroll
+  for (int j = 0; j < K; j++) {
+    const int row = row0 + j;
+    const bool pad = row < n_pad;
+    const uint32_t nib = rec[row];
+    const int q = rec[stride + row], ig = rec[2 * stride + row], dg = rec[3 * stride + row], cg = rec[4 * stride + row];
+    const float e = ph2pr[q];
+    const float om = 1.0f - e;   // stripeINITIALIZATION: _1_distm = 1 - distm
+    const float th = e / 3.0f;   //                       distm = distm / 3
+    const float pmm = __ldg(mm + mm_index(ig, dg));
+    const float pc = ph2pr[cg];
+    const float pmx = ph2pr[ig];
+    float am = pmm, my = ph2pr[dg], xx = pc;
+    if (pad) { am = 0.0f; my = 1.0f; xx = 1.0f; pm |= 1u << j; }
+    const uint32_t symnib[kPriorSyms] = {1u, 2u, 4u, 8u, 15u};
+#pragma unroll
+    for (int sy = 0; sy < kPriorSyms; sy++) tbl[(sy * K + j) * 32] = pad ? 0.0f : ((nib & symnib[sy]) ? om : th);
+    // pGAPM of the row below (0 past the last row and for padding rows, whose M must stay 0)
+    float gnext = 0.0f;
+    if (row + 1 < n_rows && row + 1 >= n_pad) gnext = 1.0f - ph2pr[rec[4 * stride + row + 1]];
+    my *= gnext;
+    if (j == 0) L.gTop = pad ? 0.0f : 1.0f - pc;
+    // W = X / pMX(row):  W = M(up) + kappa * W(up);  the row above a first real row has X = 0 (kappa = 0)
+    float kappa = 0.0f;
+    if (!pad && row - 1 >= n_pad) kappa = pc * ph2pr[rec[2 * stride + row - 1]] / pmx;
+    const float ax = pad ? 0.0f : gnext * pmx;
+    if (j == K - 1) L.xlast = pad ? 0.0f : pmx;
+    if (j == 0 && top_is_row0) { am = 0.0f; kappa = 0.0f; }
+    L.Am[j] = am; L.kap[j] = kappa; L.pXX[j] = xx; L.pMY[j] = my; L.Ax[j] = ax;
+  }
+  L.padmask = pm;
+}
+
+template <int G, int K>
+struct SweeperH2 {
+  const LaneRowsH2<K>& L;
+  float2 Ml[K], Yl[K], Zl[K];
+  float2 botX, sum, sumW;
+  float2 uM, uX, uZ, dMp, dZp, inj;
+  const uint8_t* hap;
+  const float* tb;
+  int lenA, lenB, c;
+  uint32_t hb;
+  bool row0_above;
+
+  __device__ __forceinline__ SweeperH2(const LaneRowsH2<K>& L_) : L(L_) {}
+
+  __device__ __forceinline__ void fetch_up() {
+    uM = make_float2(__shfl_up_sync(0xffffffffu, Ml[K - 1].x, 1, G), __shfl_up_sync(0xffffffffu, Ml[K - 1].y, 1, G));
+    uX = make_float2(__shfl_up_sync(0xffffffffu, botX.x, 1, G), __shfl_up_sync(0xffffffffu, botX.y, 1, G));
+    uZ = make_float2(__shfl_up_sync(0xffffffffu, Zl[K - 1].x, 1, G), __shfl_up_sync(0xffffffffu, Zl[K - 1].y, 1, G));
+    if (row0_above) {  // row 0: M = X = 0, Y = init
+      uZ = inj;
+      uM = make_float2(0.0f, 0.0f);
+    }
+  }
+
+  template <bool GUARD>
+  __device__ __forceinline__ void cells(const float* tA, const float* tB) {
+    float2 dM = dMp, dZ = dZp, upM = uM, upX = uX;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const float2 pr = make_float2(tA[j * 32], tB[j * 32]);
+      const float2 Xn = __ffma2_rn(bc2(L.kap[j]), upX, upM);              // W form: kappa * W(up) + M(up)
+      const float2 Mn = __fmul2_rn(pr, __ffma2_rn(bc2(L.Am[j]), dM, dZ));
+      const float2 Yn = __ffma2_rn(bc2(L.pXX[j]), Yl[j], Ml[j]);           // Y / pMY
+      const float2 Zn = __ffma2_rn(bc2(L.pMY[j]), Yn, __fmul2_rn(bc2(L.Ax[j]), Xn));
+      dM = Ml[j];
+      dZ = Zl[j];
+      Ml[j] = Mn;
+      Yl[j] = Yn;
+      Zl[j] = Zn;
+      upM = Mn;
+      upX = Xn;
+    }
+    botX = upX;
+    if (GUARD) {  // past the end of the shorter haplotype only the longer one still accumulates
+      const bool b = c <= lenB;
+      sum = make_float2(sum.x + upM.x, sum.y + (b ? upM.y : 0.0f));
+      sumW = make_float2(sumW.x + upX.x, sumW.y + (b ? upX.y : 0.0f));
+    } else {
+      sum = __fadd2_rn(sum, upM);
+      sumW = __fadd2_rn(sumW, upX);
+    }
+  }
+
+  template <bool GUARD>
+  __device__ __forceinline__ void step() {
+    const float* tA = tb + (hb & 7u) * (K * 32);
+    const float* tB = tb + ((hb >> 3) & 7u) * (K * 32);
+    hb = hap[min(c + 1, lenA + 1)];
+    if (!GUARD || (unsigned)(c - 1) < (unsigned)lenA) cells<GUARD>(tA, tB);
+    dMp = uM;
+    dZp = uZ;
+    c++;
+    fetch_up();
+  }
+
+  // returns (sum of haplotype A, sum of haplotype B) on the last lane of the group
+  __device__ __forceinline__ float2 run(const uint8_t* hap_, int lenA_, int lenB_, int steady_end, int n_steps, int t,
+                                        float2 initY, const float* tb_) {
+    tb = tb_;
+    hap = hap_;
+    lenA = lenA_;
+    lenB = lenB_;
+    row0_above = (t == 0);
+    const float2 zero = make_float2(0.0f, 0.0f);
+    inj = __fmul2_rn(bc2(L.gTop), initY);
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      Ml[j] = zero;
+      const float2 y0 = (L.padmask & (1u << j)) ? initY : zero;
+      Yl[j] = y0;
+      Zl[j] = __fmul2_rn(bc2(L.pMY[j]), y0);
+    }
+    botX = zero;
+    sum = zero;
+    sumW = zero;
+    dMp = zero;
+    dZp = row0_above ? inj : zero;
+    c = 1 - t;
+    hb = hap[max(c, -kHapLeftMargin + 1)];
+    fetch_up();
+    int s = 1;
+    const int pre_end = min(G - 1, n_steps);
+    for (; s <= pre_end; s++) step<true>();
+#pragma unroll 2
+    for (; s <= steady_end; s++) step<false>();
+    for (; s <= n_steps; s++) step<true>();
+    return __ffma2_rn(bc2(L.xlast), sumW, sum);
+  }
+};
+
+// Per-CTA setup for the H2 kernels: mbarriers, ph2pr table, pair image (one TMA bulk copy).
+struct WarpCtxH2 {
+  uint64_t* slot_bar;
+  uint32_t slot_parity;
+  uint8_t* slot;
+  const float* ph2pr_s;
+  const uint8_t* panel_s;
+  const int32_t *ppos, *lenA, *lenB, *idxA, *idxB;
+  int warp, lane;
+};
+
+__device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const PairPanelRef& panel, const float* ph2pr, int warps,
+                                                  uint32_t slot_bytes) {
+  const SmemLayout lay = smem_layout(warps, panel.bytes, slot_bytes, sizeof(float));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
+  float* ph2pr_s = reinterpret_cast<float*>(smem + lay.ph2pr);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 1 + warps; i++) mbar_init(&bars[i], 1);
+    fence_mbar_init();
+  }
+  for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = ph2pr[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bars[0], panel.bytes);
+    tma_bulk_g2s(smem + lay.panel, panel.image, panel.bytes, &bars[0]);
+  }
+  mbar_wait(&bars[0], 0);
+  WarpCtxH2 c;
+  c.warp = threadIdx.x >> 5;
+  c.lane = threadIdx.x & 31;
+  c.slot_bar = &bars[1 + c.warp];
+  c.slot_parity = 0;
+  c.slot = smem + lay.slots + (size_t)c.warp * lay.slot_bytes;
+  c.ph2pr_s = ph2pr_s;
+  c.panel_s = smem + lay.panel;
+  c.ppos = reinterpret_cast<const int32_t*>(c.panel_s);
+  c.lenA = c.ppos + panel.n_pairs;
+  c.lenB = c.lenA + panel.n_pairs;
+  c.idxA = c.lenB + panel.n_pairs;
+  c.idxB = c.idxA + panel.n_pairs;
+  return c;
+}
+
+// One task = (block of 32/G records) x (chunk of haplotype pairs), executed by one warp.
+template <int G, int K>
+__device__ __forceinline__ void run_task_h2(const H2Params& p, unsigned int task, WarpCtxH2& ctx) {
+  constexpr int GPW = 32 / G;
+  const int lane = ctx.lane;
+  const int t = lane % G, g = lane / G;
+  const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
+  const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
+  const int rec0 = blk * GPW;
+  float* tbs = reinterpret_cast<float*>(ctx.slot + ((GPW * rec_bytes + 127u) & ~127u)) + lane;
+  __syncwarp();
+  if (lane == 0) {
+    fence_proxy_async();
+    mbar_expect_tx(ctx.slot_bar, GPW * rec_bytes);
+    tma_bulk_g2s(ctx.slot, p.cls.records + (size_t)rec0 * rec_bytes, GPW * rec_bytes, ctx.slot_bar);
+  }
+  mbar_wait(ctx.slot_bar, ctx.slot_parity);
+  ctx.slot_parity ^= 1;
+
+  const int rec = rec0 + g;
+  const int rid = p.cls.rec_rid[rec];
+  const int npad = p.cls.rows - p.cls.rec_len[rec];
+  LaneRowsH2<K> L;
+  load_lane_rows_h2<K>(L, ctx.slot + (size_t)g * rec_bytes, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
+                       p.mm, tbs);
+  const int q_begin = chunk * p.pair_chunk, q_end = min(p.panel.n_pairs, q_begin + p.pair_chunk);
+  for (int q = q_begin; q < q_end; q++) {
+    const int lenA = ctx.lenA[q], lenB = ctx.lenB[q];
+    const uint8_t* hap = ctx.panel_s + ctx.ppos[q];
+    const float2 initY = make_float2(p.init_const / (float)lenA, p.init_const / (float)max(lenB, 1));
+    SweeperH2<G, K> sw(L);
+    // steps G..min(lenA, lenB) need no guard: every lane is inside both haplotypes
+    const float2 sum = sw.run(hap, lenA, lenB, min(lenA, lenB), lenA + G - 1, t, initY, tbs);
+    if (t == G - 1 && rid >= 0) {
+#pragma unroll
+      for (int x = 0; x < 2; x++) {
+        const int h = x == 0 ? ctx.idxA[q] : ctx.idxB[q];
+        if (x == 1 && lenB == 0) continue;
+        double* o = p.out + (size_t)rid * p.panel.n_haps_total + h;
+        if (!finish_pair<VF1>(x == 0 ? sum.x : sum.y, (double)p.log10_init, o)) {
+          *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the rerun
+          const unsigned int k = atomicAdd(p.fb_count, 1u);
+          p.fb_items[k] = make_uint2((unsigned)rec, (unsigned)h);
+        }
+      }
+    }
+  }
+}
+
+template <int G, int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_h2_tasks(const H2Params p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  WarpCtxH2 ctx = setup_cta_h2(smem, p.panel, p.ph2pr, WARPS, p.slot_bytes);
+  for (;;) {
+    unsigned int task = 0;
+    if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= (unsigned)p.n_tasks) break;
+    run_task_h2<G, K>(p, task, ctx);
+  }
+}
+
+}  // namespace gklb

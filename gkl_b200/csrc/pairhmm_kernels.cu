@@ -70,6 +70,8 @@ cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_
 #define E_F1(G, K, W, M, V) {POL_F1, G, K, W, M, V, 1, GKLB_TASKS(VF1, G, K, W, M, V), nullptr}
 #define E_D1(G, K, W, M, V) {POL_D1, G, K, W, M, V, 1, GKLB_TASKS(VD1, G, K, W, M, V), GKLB_LIST(VD1, G, K, W, M, V)}
 
+#define E_H2(G, K, W) {POL_H2, G, K, W, false, 5, 1, reinterpret_cast<const void*>(&k_h2_tasks<G, K, W>), nullptr}
+
 static const KernelEntry g_table[] = {
     // ---- product: packed fp32, folded recurrence with the shared-memory prior table (VAR 3) ----
     // 12 warps per SM in 168 registers without the prior prefetch (VAR 5); K = 8 spills ~60 bytes outside the steady
@@ -85,12 +87,14 @@ static const KernelEntry g_table[] = {
     E_D1(32, 8, 8, false, 3), E_D1(32, 8, 8, true, 3),
 #ifdef GKLB_EXPERIMENTAL
     // ---- measurement only ----
+    E_H2(8, 13, 8), E_H2(8, 13, 10), E_H2(8, 13, 12), E_H2(16, 7, 12), E_H2(16, 7, 16), E_H2(16, 10, 12), E_H2(16, 10, 8),
+    E_H2(8, 7, 16), E_H2(32, 5, 12), E_H2(32, 5, 16),
     E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0),
     E_F2(16, 7, 8, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 7, 8, false, 5), E_F2(32, 5, 8, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 5), E_F2(8, 4, 16, false, 5),
     E_F2(16, 8, 8, false, 4), E_F2(32, 8, 8, false, 4), E_F2(8, 8, 8, false, 4),
     E_F2(16, 7, 12, false, 6), E_F2(16, 7, 8, false, 6), E_F2(16, 7, 10, false, 6), E_F2(16, 7, 10, false, 5),
     E_F1(8, 13, 8, false, 4), E_F1(8, 13, 8, false, 3), E_F1(8, 13, 12, false, 4), E_F1(16, 7, 16, false, 4),
-    E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3),
+    E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3), E_D1(16, 10, 8, false, 3), E_D1(8, 7, 8, false, 3),
 #endif
 };
 
@@ -126,6 +130,11 @@ cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes
 
 cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
   void* args[] = {const_cast<SweepParams*>(&p)};
+  return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, s);
+}
+
+cudaError_t launch_h2_kernel(const void* fn, const H2Params& p, int grid, int threads, size_t smem, cudaStream_t s) {
+  void* args[] = {const_cast<H2Params*>(&p)};
   return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, s);
 }
 

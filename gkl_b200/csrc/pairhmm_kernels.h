@@ -5,10 +5,11 @@
 #include <stddef.h>
 
 #include "pairhmm_device.cuh"
+#include "pairhmm_h2.cuh"
 
 namespace gklb {
 
-enum Policy { POL_F2 = 0, POL_F1 = 1, POL_D1 = 2 };
+enum Policy { POL_F2 = 0, POL_F1 = 1, POL_D1 = 2, POL_H2 = 3 };
 
 struct KernelEntry {
   int policy, G, K, warps, multi, var;
@@ -26,6 +27,7 @@ cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int thr
 const void* mega_kernel(int policy, int list_mode, int warps = 8);
 cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes, int list_mode, int grid, int threads,
                         size_t smem, cudaStream_t s);
+cudaError_t launch_h2_kernel(const void* fn, const H2Params& p, int grid, int threads, size_t smem, cudaStream_t s);
 cudaError_t launch_pack(const PackParams& p, cudaStream_t s);
 cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,
                               cudaStream_t s);
