@@ -20,8 +20,8 @@ sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 import oracle  # noqa: E402  (measurement harness: the oracle is the checker only)
 from gkl_b200 import native, synth  # noqa: E402
 
-VARIANTS_H2 = ["f2,16,7,12,5", "h2,8,13,8,5", "h2,8,13,10,5", "h2,8,13,12,5", "h2,16,7,12,5", "h2,16,7,16,5",
-               "h2,16,10,12,5", "h2,16,10,8,5", "h2,8,7,16,5", "h2,32,5,12,5", "h2,32,5,16,5"]
+VARIANTS_H2 = ["f2,16,7,12,5", "h2,8,13,8,5", "h2,8,13,12,5", "h2,16,7,12,5", "h2,16,7,16,5", "h2,16,10,12,5",
+               "h2,16,10,8,5", "h2,8,14,8,5", "h2,8,16,8,5", "h2,4,16,8,5"]
 VARIANTS = [
     "f2,16,7,8,4", "f2,16,7,12,5", "f2,16,7,8,5", "f2,16,7,8,3", "f2,16,7,8,2", "f2,16,7,8,1", "f2,16,7,8,0", "f2,16,8,8,4", "f2,16,7,10,4", "f2,16,7,12,4",
     "f2,32,4,12,4", "f2,32,4,16,4", "f2,32,5,8,4",

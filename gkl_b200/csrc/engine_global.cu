@@ -1,0 +1,345 @@
+// engine_global.cu -- the process-global surface of the PairHMM engine: what the JNI layer (and GKL's Java
+// shim above it) sees.  Replaces the native state of pairhmm/IntelPairHmm.cc:41-48 (g_use_double, g_max_threads,
+// function pointers) and the bodies of initNative / computeLikelihoodsNative / doneNative (:55-118,125-181,189-192).
+//
+// GKL's native state is read-only after init, so several IntelPairHmm instances and several Java threads (Spark
+// executors) may call computeLikelihoods concurrently, and doneNative is empty.  Here the state is a POOL of
+// engines: every compute call borrows an idle engine (or creates one, up to GKLB_ENGINES_PER_DEVICE per device),
+// on the least busy of the configured devices, so concurrent callers run on different GPUs when there are
+// several and never wait on one global lock.  init/done are reference counted: done of the last instance frees
+// the idle engines' device memory, and a later compute simply creates engines again.
+// Large batches (more than ~4e9 cells per device) are sharded over reads across the configured devices inside
+// the one call (GKLB_SHARD=direct: one host thread per device, each device copies its shard over its own PCIe
+// link and writes its slab of the caller's array; GKLB_SHARD=nccl: see engine_nccl.cu).
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <thread>
+
+#include "engine_internal.h"
+
+using namespace gklb;
+
+namespace {
+
+struct Slot {
+  gklb_engine* e = nullptr;
+  int device = 0;
+  bool use_double = false;
+  bool busy = false;
+};
+
+std::mutex g_mu;
+std::condition_variable g_cv;
+bool g_inited = false;
+int g_refs = 0;
+bool g_use_double = false;
+std::vector<int> g_devices;  // as configured (a device may be listed twice: two shards on one GPU)
+std::vector<Slot*> g_pool;
+unsigned g_rr = 0;
+gklb_pairhmm_stats g_last_stats{};
+
+int max_engines_per_device() {
+  static const int v = [] {
+    const char* s = getenv("GKLB_ENGINES_PER_DEVICE");
+    return s && atoi(s) > 0 ? atoi(s) : 4;
+  }();
+  return v;
+}
+
+std::vector<int> configured_devices() {
+  // GKLB_DEVICES = "all" | "0,1,2,..." ; GKLB_DEVICE = n : a single device (default 0)
+  std::vector<int> devices;
+  const char* many = getenv("GKLB_DEVICES");
+  if (many && *many) {
+    if (!strcmp(many, "all")) {
+      int n = 0;
+      cudaGetDeviceCount(&n);
+      for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) devices.push_back(i);
+      }
+    } else {
+      for (const char* q = many; *q;) {
+        devices.push_back(atoi(q));
+        while (*q && *q != ',') q++;
+        if (*q == ',') q++;
+      }
+    }
+  }
+  if (devices.empty()) {
+    const char* dev = getenv("GKLB_DEVICE");
+    devices.push_back(dev ? atoi(dev) : 0);
+  }
+  return devices;
+}
+
+// Borrow an engine.  device_hint < 0: the least busy configured device.
+int acquire(int device_hint, gklb_engine** out) {
+  std::unique_lock<std::mutex> lk(g_mu);
+  if (!g_inited) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
+  for (;;) {
+    int d = device_hint;
+    if (d < 0) {
+      int best = -1, best_busy = 1 << 30;
+      const size_t n = g_devices.size();
+      for (size_t k = 0; k < n; k++) {
+        const int cand = g_devices[(g_rr + k) % n];
+        int busy = 0;
+        for (Slot* s : g_pool) busy += (s->device == cand && s->busy);
+        if (busy < best_busy) { best_busy = busy; best = cand; }
+      }
+      g_rr++;
+      d = best;
+    }
+    Slot* idle_other = nullptr;
+    int on_device = 0;
+    for (Slot* s : g_pool) {
+      if (s->device != d) continue;
+      on_device++;
+      if (s->busy) continue;
+      if (s->use_double == g_use_double) {
+        s->busy = true;
+        *out = s->e;
+        return GKLB_OK;
+      }
+      idle_other = s;
+    }
+    if (on_device < max_engines_per_device() || idle_other) {
+      // create outside the lock (context creation takes a while); an idle engine of the other precision is replaced
+      Slot* s = idle_other;
+      gklb_engine* old = nullptr;
+      const bool use_double = g_use_double;
+      if (s) { old = s->e; s->e = nullptr; } else { s = new Slot; s->device = d; g_pool.push_back(s); }
+      s->busy = true;
+      s->use_double = use_double;
+      lk.unlock();
+      if (old) destroy_engine(old);
+      gklb_engine* e = nullptr;
+      const int rc = create_engine(&e, d, use_double);
+      lk.lock();
+      if (rc) {
+        g_pool.erase(std::find(g_pool.begin(), g_pool.end(), s));
+        delete s;
+        g_cv.notify_all();
+        return rc;
+      }
+      s->e = e;
+      *out = e;
+      return GKLB_OK;
+    }
+    g_cv.wait(lk);
+  }
+}
+
+void release(gklb_engine* e) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (Slot* s : g_pool)
+    if (s->e == e) s->busy = false;
+  g_cv.notify_all();
+}
+
+void free_idle_engines_locked() {
+  for (size_t i = 0; i < g_pool.size();) {
+    Slot* s = g_pool[i];
+    if (!s->busy) {
+      destroy_engine(s->e);
+      delete s;
+      g_pool.erase(g_pool.begin() + i);
+    } else {
+      i++;
+    }
+  }
+}
+
+// Batches below this many cells per device are not worth splitting: one GPU finishes them in about a millisecond.
+const long long kMinCellsPerDevice = 4000000000LL;
+
+}  // namespace
+
+namespace gklb {
+int sharded_compute_nccl(const std::vector<gklb_engine*>& engines, const gklb_pairhmm_batch* batch, const std::vector<int>& cut,
+                         double* likelihoods, gklb_pairhmm_stats* stats);
+bool nccl_available();
+}  // namespace gklb
+
+extern "C" {
+
+int gklb_pairhmm_init(int use_double, int max_threads) {
+  (void)max_threads;  // GKL's non-OpenMP library ignores it as well (IntelPairHmm.cc:85-89)
+  std::vector<int> devices = configured_devices();
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_devices = devices;
+    g_use_double = use_double != 0;
+    g_inited = true;
+    g_refs++;
+  }
+  // one engine per configured device now, so that a missing or unsupported device fails initialize(), not the
+  // first computeLikelihoods (create_engine is the only place that can say GKLB_ERR_NO_DEVICE)
+  std::vector<int> distinct = devices;
+  std::sort(distinct.begin(), distinct.end());
+  distinct.erase(std::unique(distinct.begin(), distinct.end()), distinct.end());
+  for (int d : distinct) {
+    gklb_engine* e = nullptr;
+    const int rc = acquire(d, &e);
+    if (rc) {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_refs--;
+      if (g_refs == 0) { free_idle_engines_locked(); g_inited = false; }
+      return rc;
+    }
+    release(e);
+  }
+  return GKLB_OK;
+}
+
+int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_inited) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
+  }
+  int rc = validate_batch(batch);
+  if (rc) return rc;
+  std::vector<int> devices;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    devices = g_devices;
+  }
+  int n_dev = (int)devices.size();
+  if (batch->n_reads > 0 && batch->n_haps > 0) {
+    const long long cells = (long long)batch->read_off[batch->n_reads] * (long long)batch->hap_off[batch->n_haps];
+    n_dev = (int)std::max(1LL, std::min<long long>(n_dev, cells / kMinCellsPerDevice));
+    n_dev = std::min(n_dev, batch->n_reads);
+  } else {
+    n_dev = 1;
+  }
+  if (n_dev <= 1) {
+    gklb_engine* e = nullptr;
+    if ((rc = acquire(-1, &e))) return rc;
+    {
+      std::lock_guard<std::mutex> lk(e->mu);
+      rc = do_compute(e, batch, likelihoods);
+    }
+    {
+      std::lock_guard<std::mutex> lk(g_mu);
+      g_last_stats = e->stats;
+    }
+    release(e);
+    return rc;
+  }
+  // Reads are sharded into contiguous ranges balanced by total length (every read meets every haplotype, so
+  // cells are proportional to read length); range g gets a contiguous slab of the read-major output
+  // (JavaData.h:94-105).
+  const int64_t total = batch->read_off[batch->n_reads];
+  std::vector<int> cut(n_dev + 1, 0);
+  {
+    int r = 0;
+    for (int g = 1; g < n_dev; g++) {
+      const int64_t target = total * g / n_dev;
+      while (r < batch->n_reads && batch->read_off[r] < target) r++;
+      cut[g] = std::max(r, cut[g - 1]);
+    }
+    cut[n_dev] = batch->n_reads;
+  }
+  std::vector<gklb_engine*> engines(n_dev, nullptr);
+  for (int g = 0; g < n_dev; g++) {
+    if ((rc = acquire(devices[g], &engines[g]))) {
+      for (int k = 0; k < g; k++) release(engines[k]);
+      return rc;
+    }
+  }
+  gklb_pairhmm_stats total_stats{};
+  const char* mode = getenv("GKLB_SHARD");
+  if (mode && !strcmp(mode, "nccl")) {
+    rc = sharded_compute_nccl(engines, batch, cut, likelihoods, &total_stats);
+  } else {
+    // direct: each device copies its shard and the panel over its own PCIe link and writes its slab straight into
+    // the caller's array; the shards never meet on one GPU
+    std::vector<std::vector<int64_t>> offs(n_dev);
+    std::vector<gklb_pairhmm_batch> sub(n_dev);
+    std::vector<int> rcs(n_dev, GKLB_OK);
+    std::vector<std::string> errs(n_dev);
+    std::vector<std::thread> th;
+    for (int g = 0; g < n_dev; g++) {
+      const int lo = cut[g], hi = cut[g + 1];
+      const int64_t base = batch->read_off[lo];
+      offs[g].resize((size_t)(hi - lo) + 1);
+      for (int r = lo; r <= hi; r++) offs[g][r - lo] = batch->read_off[r] - base;
+      sub[g] = *batch;
+      sub[g].n_reads = hi - lo;
+      sub[g].read_off = offs[g].data();
+      sub[g].read_bases = batch->read_bases + base;
+      sub[g].read_quals = batch->read_quals + base;
+      sub[g].ins_gop = batch->ins_gop + base;
+      sub[g].del_gop = batch->del_gop + base;
+      sub[g].gcp = batch->gcp + base;
+    }
+    for (int g = 0; g < n_dev; g++) {
+      th.emplace_back([&, g] {
+        if (sub[g].n_reads == 0) return;
+        std::lock_guard<std::mutex> lk(engines[g]->mu);
+        rcs[g] = do_compute(engines[g], &sub[g], likelihoods + (size_t)cut[g] * batch->n_haps);
+        if (rcs[g]) errs[g] = last_error_string();  // the last error is thread-local: carry it to the caller's thread
+      });
+    }
+    for (auto& t : th) t.join();
+    for (int g = 0; g < n_dev && rc == GKLB_OK; g++) {
+      if (rcs[g]) { set_last_error(errs[g]); rc = rcs[g]; break; }
+      const gklb_pairhmm_stats& st = engines[g]->stats;
+      total_stats.pairs += st.pairs;
+      total_stats.cells += st.cells;
+      total_stats.fallback_pairs += st.fallback_pairs;
+      total_stats.kernel_launches += st.kernel_launches;
+      total_stats.n_classes = std::max(total_stats.n_classes, st.n_classes);
+      total_stats.h2d_ms = std::max(total_stats.h2d_ms, st.h2d_ms);
+      total_stats.kernel_ms = std::max(total_stats.kernel_ms, st.kernel_ms);
+      total_stats.d2h_ms = std::max(total_stats.d2h_ms, st.d2h_ms);
+    }
+  }
+  for (auto* e : engines) release(e);
+  if (rc == GKLB_OK) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_last_stats = total_stats;
+  }
+  return rc;
+}
+
+int gklb_pairhmm_done(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_refs > 0) g_refs--;
+  if (g_refs == 0) free_idle_engines_locked();  // engines in use by a concurrent call are freed by a later done
+  return GKLB_OK;
+}
+
+int gklb_pairhmm_devices_in_use(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return g_inited ? (int)g_devices.size() : 0;
+}
+
+int gklb_pairhmm_engines_alive(void) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  return (int)g_pool.size();
+}
+
+int gklb_pairhmm_last_stats(gklb_pairhmm_stats* out) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (!out) return fail(GKLB_ERR_INVALID, "out is null");
+  *out = g_last_stats;
+  return GKLB_OK;
+}
+
+int gklb_pairhmm_acquire_engine(int device, gklb_engine** out) {
+  if (!out) return fail(GKLB_ERR_INVALID, "out is null");
+  return acquire(device, out);
+}
+
+int gklb_pairhmm_release_engine(gklb_engine* e) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  release(e);
+  return GKLB_OK;
+}
+
+}  // extern "C"

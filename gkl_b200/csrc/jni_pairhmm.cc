@@ -78,24 +78,14 @@ int append_field(JNIEnv* env, jobjectArray array, int index, jfieldID fid, Arena
 }
 
 // Large calls are pipelined: reads are marshalled in blocks, and while block k+1 is being copied out of the Java
-// heap, block k is already on the GPU (two engines on the same device take turns).  In a JVM the 5R+H array
-// accesses of this binding cost as much as the kernels once those run at TCUPS rates.
-struct Pipeline {
-  gklb_engine* eng[2] = {nullptr, nullptr};
-  int use_double = 0;
-};
-Pipeline g_pipe;
-std::mutex g_pipe_mu;
-
+// heap, block k is already on the GPU (two engines borrowed from the pool, on the same device, take turns).  In a
+// JVM the 5R+H array accesses of this binding cost as much as the kernels once those run at TCUPS rates
+// (SURVEY.md 8(f) N1).  The engines come from the global pool (gklb_pairhmm_acquire_engine), so the pipeline runs
+// on whatever device the pool was configured with and concurrent Java threads each get their own pair.
 int pipeline_block_reads() {
   const char* v = getenv("GKLB_JNI_BLOCK_READS");
   const int n = v ? atoi(v) : 2048;
   return n > 0 ? n : 2048;
-}
-
-void pipeline_reset() {
-  for (auto& e : g_pipe.eng)
-    if (e) { gklb_engine_destroy(e); e = nullptr; }
 }
 
 }  // namespace
@@ -133,11 +123,6 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_initNative(JNIEnv
     std::lock_guard<std::mutex> lk(g_fid_mu);
     g_fid = f;
   }
-  {
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    pipeline_reset();
-    g_pipe.use_double = use_double ? 1 : 0;
-  }
   const int rc = gklb_pairhmm_init(use_double ? 1 : 0, (int)max_threads);
   if (rc != GKLB_OK) throw_status(env, rc);
 }
@@ -166,15 +151,19 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihood
       throw_java(env, "java/lang/IllegalArgumentException", "likelihood array is shorter than reads x haplotypes");
       return;
     }
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    const char* dev = getenv("GKLB_DEVICE");
-    for (auto& e : g_pipe.eng)
-      if (!e) {
-        const int rc = gklb_engine_create(&e, dev ? atoi(dev) : 0, g_pipe.use_double);
-        if (rc != GKLB_OK) { throw_status(env, rc); return; }
-      }
+    gklb_engine* eng[2] = {nullptr, nullptr};
+    int rc0 = gklb_pairhmm_acquire_engine(-1, &eng[0]);
+    if (rc0 == GKLB_OK) {
+      rc0 = gklb_pairhmm_acquire_engine(gklb_engine_device(eng[0]), &eng[1]);
+      if (rc0 != GKLB_OK) gklb_pairhmm_release_engine(eng[0]);
+    }
+    if (rc0 != GKLB_OK) { throw_status(env, rc0); return; }
     jdouble* out = env->GetDoubleArrayElements(likelihoodArray, nullptr);
-    if (!out) { throw_java(env, "java/lang/OutOfMemoryError", "Unable to access jdoubleArray"); return; }
+    if (!out) {
+      for (auto* e : eng) gklb_pairhmm_release_engine(e);
+      throw_java(env, "java/lang/OutOfMemoryError", "Unable to access jdoubleArray");
+      return;
+    }
     Arena blk[2][5];
     int rc = GKLB_OK;
     bool thrown = false;
@@ -184,7 +173,7 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihood
       Arena* a = blk[k & 1];
       // the engine that used these arenas two blocks ago must be done with them (pinned staging is per engine,
       // pageable sources are consumed at submit; waiting also bounds the pinned output buffers)
-      if (k >= 2) rc = gklb_engine_wait(g_pipe.eng[k & 1]);
+      if (k >= 2) rc = gklb_engine_wait(eng[k & 1]);
       if (rc != GKLB_OK) break;
       for (int i = 0; i < 5; i++) { a[i].bytes.clear(); a[i].off.assign(1, 0); }
       for (int r = r0; r < r1 && !thrown; r++) {
@@ -208,11 +197,12 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihood
       b.gcp = a[4].bytes.data();
       b.hap_off = hap.off.data();
       b.hap_bases = hap.bytes.data();
-      rc = gklb_engine_submit(g_pipe.eng[k & 1], &b, out + (size_t)r0 * n_haps);
+      rc = gklb_engine_submit(eng[k & 1], &b, out + (size_t)r0 * n_haps);
     }
-    for (auto& e : g_pipe.eng) {
+    for (auto* e : eng) {
       const int w = gklb_engine_wait(e);
       if (rc == GKLB_OK) rc = w;
+      gklb_pairhmm_release_engine(e);
     }
     env->ReleaseDoubleArrayElements(likelihoodArray, out, (rc == GKLB_OK && !thrown) ? 0 : JNI_ABORT);
     if (rc != GKLB_OK && !thrown) throw_status(env, rc);
@@ -256,11 +246,7 @@ JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihood
 JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_doneNative(JNIEnv* env, jobject obj) {
   (void)env;
   (void)obj;
-  {
-    std::lock_guard<std::mutex> lk(g_pipe_mu);
-    pipeline_reset();
-  }
-  gklb_pairhmm_done();  // GKL's is empty; ours releases device memory, streams and events.  Idempotent.
+  gklb_pairhmm_done();  // GKL's is empty; ours drops a reference, the last one frees the idle engines.  Idempotent.
 }
 
 }  // extern "C"

@@ -254,8 +254,12 @@ __device__ __forceinline__ int mm_index(int ins_q, int del_q) {  // Context.h:15
 template <class P, int K, int VAR>
 __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const uint8_t* rec, int stride, int n_rows,
                                                int row0, int n_pad, bool top_is_row0, const typename P::S* __restrict__ ph2pr,
-                                               const typename P::S* __restrict__ mm, typename P::S* tbl = nullptr) {
+                                               const typename P::S* __restrict__ mm, typename P::S* tbl = nullptr,
+                                               int shift = 0) {
+  // shift: the record holds n_rows - shift rows (it was packed for a class with fewer rows than this kernel
+  // sweeps); kernel row `row` is record row `row - shift`, rows below n_pad >= shift are padding either way
   typedef typename P::S S;
+  rec -= shift;
   uint32_t pm = 0;
 #pragma unroll
   for (int w = 0; w < (K + 7) / 8; w++) L.rbm[x][w] = 0;
@@ -263,8 +267,9 @@ __device__ __forceinline__ void load_lane_rows(LaneRows<P, K>& L, int x, const u
   for (int j = 0; j < K; j++) {
     const int row = row0 + j;
     const bool pad = row < n_pad;
-    const uint32_t nib = rec[row];
-    const int q = rec[stride + row], ig = rec[2 * stride + row], dg = rec[3 * stride + row], cg = rec[4 * stride + row];
+    const int ri = max(row, shift);  // padding rows read a valid byte and ignore it
+    const uint32_t nib = rec[ri];
+    const int q = rec[stride + ri], ig = rec[2 * stride + ri], dg = rec[3 * stride + ri], cg = rec[4 * stride + ri];
     S e = ph2pr[q];
     S om = (S)1 - e;    // stripeINITIALIZATION: _1_distm = 1 - distm
     S th = e / (S)3;    //                       distm = distm / 3
@@ -776,12 +781,14 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
     ctx.slot_parity ^= 1;
   }
 
+  const int krows = MULTI ? p.cls.rows : cap;    // rows this kernel sweeps; the records may hold fewer (see load_lane_rows)
+  const int shift = krows - p.cls.rows;
   int rid[P::NR], npad[P::NR];
 #pragma unroll
   for (int x = 0; x < P::NR; x++) {
     const int rec = rec0 + g * P::NR + x;
     rid[x] = p.cls.rec_rid[rec];
-    npad[x] = p.cls.rows - p.cls.rec_len[rec];
+    npad[x] = krows - p.cls.rec_len[rec];
   }
   const int h_begin = chunk * p.hap_chunk, h_end = min(p.panel.n_haps, h_begin + p.hap_chunk);
 
@@ -789,8 +796,8 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
   if (!MULTI) {
 #pragma unroll
     for (int x = 0; x < P::NR; x++)
-      load_lane_rows<P, K, VAR>(L, x, recs + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows, t * K,
-                                npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs);
+      load_lane_rows<P, K, VAR>(L, x, recs + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, krows, t * K,
+                                npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs, shift);
   }
   for (int h = h_begin; h < h_end; h++) {
     const int haplen = ctx.hlen[h];
@@ -859,8 +866,10 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   const int rec = (int)it.x;
   const int haplen = mine ? ctx.hlen[h] : 0;
   const uint8_t* hap = ctx.panel_s + (mine ? ctx.hpos[h] : ctx.hpos[0]);
+  const int krows = MULTI ? p.cls.rows : cap;
+  const int shift = krows - p.cls.rows;
   const int rid = mine ? p.cls.rec_rid[rec] : -1;
-  const int npad = mine ? p.cls.rows - p.cls.rec_len[rec] : 0;
+  const int npad = mine ? krows - p.cls.rec_len[rec] : 0;
   const S initY = (S)p.init_const / (S)max(haplen, 1);
   int n_steps = mine ? haplen + G - 1 : 0;
 #pragma unroll
@@ -873,8 +882,8 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   LaneRows<P, K> L;
   V sum = P::splat(0);
   if (!MULTI) {
-    load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
-                              reinterpret_cast<const S*>(p.mm), tbs);
+    load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, krows, t * K, npad, t == 0, ctx.ph2pr_s,
+                              reinterpret_cast<const S*>(p.mm), tbs, shift);
     sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0, tbv);
   } else {
     V* cg = carry + (size_t)g * 6 * carry_pitch;
@@ -935,7 +944,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
 // configuration, so a HaplotypeCaller-shaped batch with a dozen length classes of ~25 reads each
 // fills the GPU with a single launch instead of a dozen serialised under-filled ones.
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxMegaClasses = 14;
+constexpr int kMaxMegaClasses = 32;
 constexpr int kCfgMulti = 13;  // configuration index of the multi-pass class (32 x 8 rows per pass)
 
 struct MegaParams {
@@ -943,7 +952,7 @@ struct MegaParams {
   int cfg[kMaxMegaClasses];        // index into the class table (G, K), kCfgMulti for multi-pass
   int task_end[kMaxMegaClasses];   // exclusive prefix of tasks in the unified queue (task mode)
   unsigned int* queue;             // the unified work counter
-  SweepParams cls[kMaxMegaClasses];
+  const SweepParams* cls;          // [n_classes] in device memory (uploaded with the batch's meta block)
 };
 
 // product variants: fp32 uses the W form, fp64 must not (2^1020 leaves no headroom for X / pMX).  With 12 warps

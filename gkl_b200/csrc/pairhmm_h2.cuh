@@ -27,27 +27,52 @@ namespace gklb {
 
 struct PairPanelRef {      // one haplotype tile as a pair image, bulk-copied to shared memory:
   const uint8_t* image;    //   int32 ppos[n]   byte offset of column 0 of pair i inside the image
-  uint32_t bytes;          //   int32 lenA[n], lenB[n]   (lenA >= lenB; lenB == 0: no second haplotype)
-  int n_pairs;             //   int32 idxA[n], idxB[n]   haplotype index in the batch
+  uint32_t bytes;          //   int32 lenA[n], lenB[n]   (lenA >= lenB)
+  int n_pairs;             //   int32 idxA[n], idxB[n]   haplotype index in the batch (idxB -1: B repeats A, drop it)
   int n_haps_total;        //   pad to 16, then per pair: left margin | bytes | right margin
   int max_hap_len;
 };
 
-struct H2Params {
+struct H2Class {           // the reads of one length class (rows = G * K of its kernel), packed by k_pack_reads
+  const uint8_t* records;  // [n_rec][5 planes][stride]
+  const int32_t* rec_rid;  // [n_rec] read index in the batch, -1 for filler records
+  const int32_t* rec_len;  // [n_rec]
+  uint2* fb_items;         // (record, haplotype) of pairs whose scaled sum is < 1e-28f or not finite
+  unsigned int* fb_count;
+  int n_rec;               // multiple of 32 / G
+  int rows;                // G * K
+  int stride;              // bytes per plane
+  int pair_chunk;          // haplotype pairs per task
+  int n_chunks;
+  int n_tasks;             // (n_rec / (32 / G)) * n_chunks
+};
+
+struct H2Common {
   PairPanelRef panel;
-  ClassRef cls;
   const float* ph2pr;
   const float* mm;
   double* out;
-  int pair_chunk;          // haplotype pairs per task
-  int n_chunks;
-  int n_tasks;
-  unsigned int* task_counter;
-  uint2* fb_items;         // (record, haplotype) of pairs whose scaled sum is < 1e-28f or not finite
-  unsigned int* fb_count;
   float init_const;        // 2^120
   float log10_init;
   uint32_t slot_bytes;
+};
+
+struct H2Params {          // single-class launch
+  H2Common com;
+  H2Class cls;
+  unsigned int* task_counter;
+};
+
+// Multi-class launch: one queue that concatenates the classes' tasks, longest class first (see k_mega_tasks in
+// pairhmm_device.cuh for why).  cfg = gi * 9 + (K - 8) with G = 4 << gi.
+constexpr int kMaxH2Classes = 27;
+struct H2MegaParams {
+  H2Common com;
+  int n_classes;
+  unsigned int* queue;
+  int cfg[kMaxH2Classes];
+  int task_end[kMaxH2Classes];
+  H2Class cls[kMaxH2Classes];
 };
 
 __device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
@@ -244,30 +269,30 @@ __device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const PairPanel
 
 // One task = (block of 32/G records) x (chunk of haplotype pairs), executed by one warp.
 template <int G, int K>
-__device__ __forceinline__ void run_task_h2(const H2Params& p, unsigned int task, WarpCtxH2& ctx) {
+__device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cls, unsigned int task, WarpCtxH2& ctx) {
   constexpr int GPW = 32 / G;
   const int lane = ctx.lane;
   const int t = lane % G, g = lane / G;
-  const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
-  const int blk = task / p.n_chunks, chunk = task - blk * p.n_chunks;
+  const uint32_t rec_bytes = 5u * (uint32_t)cls.stride;
+  const int blk = task / cls.n_chunks, chunk = task - blk * cls.n_chunks;
   const int rec0 = blk * GPW;
   float* tbs = reinterpret_cast<float*>(ctx.slot + ((GPW * rec_bytes + 127u) & ~127u)) + lane;
   __syncwarp();
   if (lane == 0) {
     fence_proxy_async();
     mbar_expect_tx(ctx.slot_bar, GPW * rec_bytes);
-    tma_bulk_g2s(ctx.slot, p.cls.records + (size_t)rec0 * rec_bytes, GPW * rec_bytes, ctx.slot_bar);
+    tma_bulk_g2s(ctx.slot, cls.records + (size_t)rec0 * rec_bytes, GPW * rec_bytes, ctx.slot_bar);
   }
   mbar_wait(ctx.slot_bar, ctx.slot_parity);
   ctx.slot_parity ^= 1;
 
   const int rec = rec0 + g;
-  const int rid = p.cls.rec_rid[rec];
-  const int npad = p.cls.rows - p.cls.rec_len[rec];
+  const int rid = cls.rec_rid[rec];
+  const int npad = cls.rows - cls.rec_len[rec];
   LaneRowsH2<K> L;
-  load_lane_rows_h2<K>(L, ctx.slot + (size_t)g * rec_bytes, p.cls.stride, p.cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
+  load_lane_rows_h2<K>(L, ctx.slot + (size_t)g * rec_bytes, cls.stride, cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
                        p.mm, tbs);
-  const int q_begin = chunk * p.pair_chunk, q_end = min(p.panel.n_pairs, q_begin + p.pair_chunk);
+  const int q_begin = chunk * cls.pair_chunk, q_end = min(p.panel.n_pairs, q_begin + cls.pair_chunk);
   for (int q = q_begin; q < q_end; q++) {
     const int lenA = ctx.lenA[q], lenB = ctx.lenB[q];
     const uint8_t* hap = ctx.panel_s + ctx.ppos[q];
@@ -279,12 +304,12 @@ __device__ __forceinline__ void run_task_h2(const H2Params& p, unsigned int task
 #pragma unroll
       for (int x = 0; x < 2; x++) {
         const int h = x == 0 ? ctx.idxA[q] : ctx.idxB[q];
-        if (x == 1 && lenB == 0) continue;
+        if (h < 0) continue;   // an odd haplotype out is paired with itself; its second result is dropped
         double* o = p.out + (size_t)rid * p.panel.n_haps_total + h;
         if (!finish_pair<VF1>(x == 0 ? sum.x : sum.y, (double)p.log10_init, o)) {
           *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the rerun
-          const unsigned int k = atomicAdd(p.fb_count, 1u);
-          p.fb_items[k] = make_uint2((unsigned)rec, (unsigned)h);
+          const unsigned int k = atomicAdd(cls.fb_count, 1u);
+          cls.fb_items[k] = make_uint2((unsigned)rec, (unsigned)h);
         }
       }
     }
@@ -292,15 +317,53 @@ __device__ __forceinline__ void run_task_h2(const H2Params& p, unsigned int task
 }
 
 template <int G, int K, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 1) k_h2_tasks(const H2Params p) {
+__global__ void __launch_bounds__(WARPS * 32, 1) k_h2_tasks(const __grid_constant__ H2Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtxH2 ctx = setup_cta_h2(smem, p.panel, p.ph2pr, WARPS, p.slot_bytes);
+  WarpCtxH2 ctx = setup_cta_h2(smem, p.com.panel, p.com.ph2pr, WARPS, p.com.slot_bytes);
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
-    if (task >= (unsigned)p.n_tasks) break;
-    run_task_h2<G, K>(p, task, ctx);
+    if (task >= (unsigned)p.cls.n_tasks) break;
+    run_task_h2<G, K>(p.com, p.cls, task, ctx);
+  }
+}
+
+template <int G, int K>
+__device__ __noinline__ void mega_task_h2(const H2Common& com, const H2Class& cls, unsigned int task, WarpCtxH2& ctx) {
+  run_task_h2<G, K>(com, cls, task, ctx);
+}
+
+#define GKLB_H2_ROW(G, B)                                                   \
+  case B + 0: mega_task_h2<G, 8>(m.com, m.cls[c], local, ctx); break;       \
+  case B + 1: mega_task_h2<G, 9>(m.com, m.cls[c], local, ctx); break;       \
+  case B + 2: mega_task_h2<G, 10>(m.com, m.cls[c], local, ctx); break;      \
+  case B + 3: mega_task_h2<G, 11>(m.com, m.cls[c], local, ctx); break;      \
+  case B + 4: mega_task_h2<G, 12>(m.com, m.cls[c], local, ctx); break;      \
+  case B + 5: mega_task_h2<G, 13>(m.com, m.cls[c], local, ctx); break;      \
+  case B + 6: mega_task_h2<G, 14>(m.com, m.cls[c], local, ctx); break;      \
+  case B + 7: mega_task_h2<G, 15>(m.com, m.cls[c], local, ctx); break;      \
+  case B + 8: mega_task_h2<G, 16>(m.com, m.cls[c], local, ctx); break;
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_h2_mega(const __grid_constant__ H2MegaParams m) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  WarpCtxH2 ctx = setup_cta_h2(smem, m.com.panel, m.com.ph2pr, WARPS, m.com.slot_bytes);
+  const unsigned int total = (unsigned)m.task_end[m.n_classes - 1];
+  for (;;) {
+    unsigned int task = 0;
+    if (ctx.lane == 0) task = atomicAdd(m.queue, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= total) break;
+    int c = 0;
+    while (task >= (unsigned)m.task_end[c]) c++;
+    const unsigned int local = task - (c ? (unsigned)m.task_end[c - 1] : 0u);
+    switch (m.cfg[c]) {
+      GKLB_H2_ROW(4, 0)
+      GKLB_H2_ROW(8, 9)
+      GKLB_H2_ROW(16, 18)
+      default: break;
+    }
   }
 }
 

@@ -1,10 +1,10 @@
-// pairhmm_kernels.cu -- instantiations of the sweep kernels and their registry.
+// pairhmm_kernels.cu -- the small kernels (read packing, panel refill), the multi-pass packed-read sweep, the
+// measurement-only variants, and the registry of all compiled sweep kernels.
 //
-// Product instantiations: packed-fp32 (VF2) and fp64 (VD1) for every length class of
-// engine.cu's class table, plus the multi-pass variants for reads longer than 256 rows.
-// The remaining entries (VF1, VAR 0, alternative warp counts) exist so that the design choices
-// can be re-measured on the GPU (bench/sweep.py); the engine only uses them when told to
-// through GKLB_FORCE_KERNEL.
+// Product instantiations: H2 (two haplotypes per lane, kernels_h2_*.cu) for every single-pass length class,
+// packed-read VF2 multi-pass for reads longer than 256 rows, fp64 VD1 (kernels_d1.cu).  The remaining entries
+// (VF2/VF1 single-pass variants) exist so that the design choices can be re-measured on the GPU (bench/sweep.py,
+// make EXPERIMENTAL=1); the engine only uses them when told to through GKLB_FORCE_KERNEL.
 #include "pairhmm_kernels.h"
 
 namespace gklb {
@@ -57,6 +57,23 @@ __global__ void k_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t
   for (int c = threadIdx.x; c < hlen[i]; c += blockDim.x) dst[c] = panel_byte(bases[o + c]);
 }
 
+// The same for a pair image (pairhmm_h2.cuh): one block per pair.
+__global__ void k_fill_pair_panel(uint8_t* image, int n_pairs, const int64_t* hap_off, const uint8_t* bases) {
+  const int q = blockIdx.x;
+  if (q >= n_pairs) return;
+  const int32_t* ppos = reinterpret_cast<const int32_t*>(image);
+  const int32_t* lenA = ppos + n_pairs;
+  const int32_t* lenB = lenA + n_pairs;
+  const int32_t* idxA = lenB + n_pairs;
+  const int32_t* idxB = idxA + n_pairs;
+  const int a = idxA[q], b = idxB[q] >= 0 ? idxB[q] : a;
+  const int64_t oa = hap_off[a], ob = hap_off[b];
+  const int la = lenA[q], lb = lenB[q];
+  uint8_t* dst = image + ppos[q] + 1;
+  for (int c = threadIdx.x; c < la; c += blockDim.x)
+    dst[c] = (uint8_t)(base_index(bases[oa + c]) | (c < lb ? base_index(bases[ob + c]) << 3 : 0));
+}
+
 cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,
                               cudaStream_t s) {
   if (n_haps <= 0) return cudaSuccess;
@@ -64,43 +81,50 @@ cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_
   return cudaGetLastError();
 }
 
+cudaError_t launch_fill_pair_panel(uint8_t* image, int n_pairs, const int64_t* hap_off, const uint8_t* bases, cudaStream_t s) {
+  if (n_pairs <= 0) return cudaSuccess;
+  k_fill_pair_panel<<<n_pairs, 128, 0, s>>>(image, n_pairs, hap_off, bases);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_pack(const PackParams& p, cudaStream_t s) {
+  const int threads = 256;
+  const long long total = (long long)p.n_rec_total * 32;
+  const int grid = (int)((total + threads - 1) / threads);
+  if (grid == 0) return cudaSuccess;
+  k_pack_reads<<<grid, threads, 0, s>>>(p);
+  return cudaGetLastError();
+}
+
 #define GKLB_TASKS(P, G, K, W, M, V) reinterpret_cast<const void*>(&k_sweep_tasks<P, G, K, W, M, V>)
-#define GKLB_LIST(P, G, K, W, M, V) reinterpret_cast<const void*>(&k_sweep_list<P, G, K, W, M, V>)
-#define E_F2(G, K, W, M, V) {POL_F2, G, K, W, M, V, 2, GKLB_TASKS(VF2, G, K, W, M, V), nullptr}
-#define E_F1(G, K, W, M, V) {POL_F1, G, K, W, M, V, 1, GKLB_TASKS(VF1, G, K, W, M, V), nullptr}
-#define E_D1(G, K, W, M, V) {POL_D1, G, K, W, M, V, 1, GKLB_TASKS(VD1, G, K, W, M, V), GKLB_LIST(VD1, G, K, W, M, V)}
+#define E_F2(G, K, W, M, V) KernelEntry{POL_F2, G, K, W, M, V, 2, GKLB_TASKS(VF2, G, K, W, M, V), nullptr}
+#define E_F1(G, K, W, M, V) KernelEntry{POL_F1, G, K, W, M, V, 1, GKLB_TASKS(VF1, G, K, W, M, V), nullptr}
 
-#define E_H2(G, K, W) {POL_H2, G, K, W, false, 5, 1, reinterpret_cast<const void*>(&k_h2_tasks<G, K, W>), nullptr}
-
-static const KernelEntry g_table[] = {
-    // ---- product: packed fp32, folded recurrence with the shared-memory prior table (VAR 3) ----
-    // 12 warps per SM in 168 registers without the prior prefetch (VAR 5); K = 8 spills ~60 bytes outside the steady
-    // loop and is still 1-2 % faster than 8 warps with the prefetch (VAR 4); the multi-pass kernel keeps 8 warps
-    E_F2(8, 4, 12, false, 5),  E_F2(8, 5, 12, false, 5),  E_F2(8, 6, 12, false, 5),  E_F2(8, 7, 12, false, 5),
-    E_F2(8, 8, 12, false, 5),  E_F2(16, 5, 12, false, 5), E_F2(16, 6, 12, false, 5), E_F2(16, 7, 12, false, 5),
-    E_F2(16, 8, 12, false, 5), E_F2(32, 5, 12, false, 5), E_F2(32, 6, 12, false, 5), E_F2(32, 7, 12, false, 5),
-    E_F2(32, 8, 12, false, 5), E_F2(32, 8, 8, true, 4),
-    // ---- product: fp64 (useDoublePrecision and the rerun of flagged pairs) ----
-    E_D1(8, 4, 8, false, 3),  E_D1(8, 5, 8, false, 3),  E_D1(8, 6, 8, false, 3),  E_D1(8, 7, 8, false, 3),
-    E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 8, false, 3), E_D1(16, 6, 8, false, 3), E_D1(16, 7, 8, false, 3),
-    E_D1(16, 8, 8, false, 3), E_D1(32, 5, 8, false, 3), E_D1(32, 6, 8, false, 3), E_D1(32, 7, 8, false, 3),
-    E_D1(32, 8, 8, false, 3), E_D1(32, 8, 8, true, 3),
+void kernel_entries_misc(std::vector<KernelEntry>& v) {
+  // product: reads of more than 256 rows, two reads per lane, 32 x 8 rows per pass, carry line in global memory
+  v.push_back(E_F2(32, 8, 8, true, 4));
 #ifdef GKLB_EXPERIMENTAL
-    // ---- measurement only ----
-    E_H2(8, 13, 8), E_H2(8, 13, 10), E_H2(8, 13, 12), E_H2(16, 7, 12), E_H2(16, 7, 16), E_H2(16, 10, 12), E_H2(16, 10, 8),
-    E_H2(8, 7, 16), E_H2(32, 5, 12), E_H2(32, 5, 16),
-    E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2), E_F2(16, 7, 8, false, 1), E_F2(16, 7, 8, false, 0),
-    E_F2(16, 7, 8, false, 4), E_F2(16, 7, 12, false, 4), E_F2(16, 7, 8, false, 5), E_F2(32, 5, 8, false, 4), E_F2(16, 8, 8, false, 3), E_F2(16, 8, 8, false, 2), E_F2(32, 4, 12, false, 5), E_F2(8, 4, 16, false, 5),
-    E_F2(16, 8, 8, false, 4), E_F2(32, 8, 8, false, 4), E_F2(8, 8, 8, false, 4),
-    E_F2(16, 7, 12, false, 6), E_F2(16, 7, 8, false, 6), E_F2(16, 7, 10, false, 6), E_F2(16, 7, 10, false, 5),
-    E_F1(8, 13, 8, false, 4), E_F1(8, 13, 8, false, 3), E_F1(8, 13, 12, false, 4), E_F1(16, 7, 16, false, 4),
-    E_D1(16, 7, 8, false, 2), E_D1(8, 13, 8, false, 3), E_D1(32, 4, 8, false, 3), E_D1(16, 10, 8, false, 3), E_D1(8, 7, 8, false, 3),
+  // measurement only: the round-1 packed-read kernel (two reads per lane) and its variants
+  const KernelEntry e[] = {
+      E_F2(16, 7, 12, false, 5), E_F2(16, 7, 8, false, 4), E_F2(16, 7, 8, false, 3), E_F2(16, 7, 8, false, 2),
+      E_F2(16, 7, 8, false, 1),  E_F2(16, 7, 8, false, 0), E_F2(32, 5, 12, false, 5), E_F1(8, 13, 8, false, 4),
+  };
+  for (const auto& x : e) v.push_back(x);
 #endif
-};
+}
 
 const KernelEntry* kernel_table(int* n) {
-  *n = (int)(sizeof(g_table) / sizeof(g_table[0]));
-  return g_table;
+  static const std::vector<KernelEntry> table = [] {
+    std::vector<KernelEntry> v;
+    kernel_entries_h2_g4(v);
+    kernel_entries_h2_g8(v);
+    kernel_entries_h2_g16(v);
+    kernel_entries_d1(v);
+    kernel_entries_misc(v);
+    return v;
+  }();
+  *n = (int)table.size();
+  return table.data();
 }
 
 const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, int var) {
@@ -111,40 +135,6 @@ const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, i
         t[i].multi == multi && (var < 0 || t[i].var == var))
       return &t[i];
   return nullptr;
-}
-
-const void* mega_kernel(int policy, int list_mode, int warps) {
-  if (policy == POL_F2 && !list_mode && warps == 12) return reinterpret_cast<const void*>(&k_mega_tasks<VF2, 12>);
-  if (policy == POL_F2 && !list_mode) return reinterpret_cast<const void*>(&k_mega_tasks<VF2, 8>);
-  if (policy == POL_D1 && !list_mode) return reinterpret_cast<const void*>(&k_mega_tasks<VD1, 8>);
-  if (policy == POL_D1 && list_mode) return reinterpret_cast<const void*>(&k_mega_list<VD1, 8>);
-  return nullptr;
-}
-
-cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes, int list_mode, int grid, int threads,
-                        size_t smem, cudaStream_t s) {
-  void* args_tasks[] = {const_cast<MegaParams*>(&m), &slot_bytes};
-  void* args_list[] = {const_cast<MegaParams*>(&m), &slot_bytes};
-  return cudaLaunchKernel(fn, dim3(grid), dim3(threads), list_mode ? args_list : args_tasks, smem, s);
-}
-
-cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s) {
-  void* args[] = {const_cast<SweepParams*>(&p)};
-  return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, s);
-}
-
-cudaError_t launch_h2_kernel(const void* fn, const H2Params& p, int grid, int threads, size_t smem, cudaStream_t s) {
-  void* args[] = {const_cast<H2Params*>(&p)};
-  return cudaLaunchKernel(fn, dim3(grid), dim3(threads), args, smem, s);
-}
-
-cudaError_t launch_pack(const PackParams& p, cudaStream_t s) {
-  const int threads = 256;
-  const long long total = (long long)p.n_rec_total * 32;
-  const int grid = (int)((total + threads - 1) / threads);
-  if (grid == 0) return cudaSuccess;
-  k_pack_reads<<<grid, threads, 0, s>>>(p);
-  return cudaGetLastError();
 }
 
 }  // namespace gklb

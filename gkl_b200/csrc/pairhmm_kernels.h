@@ -1,8 +1,11 @@
-// pairhmm_kernels.h -- host-side registry of the compiled sweep kernels.
+// pairhmm_kernels.h -- host-side registry of the compiled sweep kernels.  The instantiations are spread over
+// several translation units (kernels_*.cu) so that they compile in parallel.
 #pragma once
 
 #include <cuda_runtime.h>
 #include <stddef.h>
+
+#include <vector>
 
 #include "pairhmm_device.cuh"
 #include "pairhmm_h2.cuh"
@@ -14,22 +17,35 @@ enum Policy { POL_F2 = 0, POL_F1 = 1, POL_D1 = 2, POL_H2 = 3 };
 struct KernelEntry {
   int policy, G, K, warps, multi, var;
   int nr;                  // reads carried per lane
-  const void* fn_tasks;    // k_sweep_tasks instantiation
-  const void* fn_list;     // k_sweep_list instantiation (nullptr when nr != 1)
+  const void* fn_tasks;    // task kernel (k_sweep_tasks / k_h2_tasks instantiation)
+  const void* fn_list;     // k_sweep_list instantiation (fp64 only)
 };
 
 // All compiled instantiations.
 const KernelEntry* kernel_table(int* n);
 const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, int var);
 
-cudaError_t launch_sweep(const void* fn, const SweepParams& p, int grid, int threads, size_t smem, cudaStream_t s);
-// Multi-class kernels (8 warps per CTA): POL_F2 / POL_D1 task kernels and the POL_D1 rerun-list kernel.
-const void* mega_kernel(int policy, int list_mode, int warps = 8);
-cudaError_t launch_mega(const void* fn, const MegaParams& m, uint32_t slot_bytes, int list_mode, int grid, int threads,
-                        size_t smem, cudaStream_t s);
-cudaError_t launch_h2_kernel(const void* fn, const H2Params& p, int grid, int threads, size_t smem, cudaStream_t s);
+// Multi-class kernels (8 warps per CTA): the fp64 task kernel (list_mode 0) and rerun-list kernel (1); the H2 sweep.
+const void* mega_kernel(int policy, int list_mode);
+const void* h2_mega_kernel();
+
 cudaError_t launch_pack(const PackParams& p, cudaStream_t s);
 cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,
                               cudaStream_t s);
+cudaError_t launch_fill_pair_panel(uint8_t* image, int n_pairs, const int64_t* hap_off, const uint8_t* bases, cudaStream_t s);
+
+// per translation unit
+void kernel_entries_h2_g4(std::vector<KernelEntry>& v);
+void kernel_entries_h2_g8(std::vector<KernelEntry>& v);
+void kernel_entries_h2_g16(std::vector<KernelEntry>& v);
+void kernel_entries_d1(std::vector<KernelEntry>& v);
+void kernel_entries_misc(std::vector<KernelEntry>& v);
+
+#define GKLB_E_H2(G, K, W) \
+  KernelEntry { POL_H2, G, K, W, 0, 5, 1, reinterpret_cast<const void*>(&k_h2_tasks<G, K, W>), nullptr }
+#define GKLB_H2_ROW_ENTRIES(v, G)                                                                             \
+  v.push_back(GKLB_E_H2(G, 8, 8)); v.push_back(GKLB_E_H2(G, 9, 8)); v.push_back(GKLB_E_H2(G, 10, 8));          \
+  v.push_back(GKLB_E_H2(G, 11, 8)); v.push_back(GKLB_E_H2(G, 12, 8)); v.push_back(GKLB_E_H2(G, 13, 8));        \
+  v.push_back(GKLB_E_H2(G, 14, 8)); v.push_back(GKLB_E_H2(G, 15, 8)); v.push_back(GKLB_E_H2(G, 16, 8));
 
 }  // namespace gklb

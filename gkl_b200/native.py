@@ -41,7 +41,8 @@ class Stats(C.Structure):
 
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_pairhmm_devices_in_use",
-           "gklb_pairhmm_last_stats", "gklb_engine_create",
+           "gklb_pairhmm_last_stats", "gklb_pairhmm_engines_alive", "gklb_pairhmm_acquire_engine",
+           "gklb_pairhmm_release_engine", "gklb_engine_device", "gklb_engine_sweep_kernel", "gklb_engine_create",
            "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_submit", "gklb_engine_wait", "gklb_engine_stage",
            "gklb_engine_stage_device", "gklb_engine_update_haps_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
            "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
@@ -86,6 +87,11 @@ def lib() -> C.CDLL:
         l.gklb_pairhmm_init.argtypes = [C.c_int, C.c_int]
         l.gklb_pairhmm_compute.argtypes = [C.POINTER(_Batch), C.c_void_p]
         l.gklb_pairhmm_last_stats.argtypes = [C.POINTER(Stats)]
+        l.gklb_engine_sweep_kernel.restype = C.c_char_p
+        l.gklb_engine_sweep_kernel.argtypes = [C.c_void_p]
+        l.gklb_engine_device.argtypes = [C.c_void_p]
+        l.gklb_pairhmm_acquire_engine.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        l.gklb_pairhmm_release_engine.argtypes = [C.c_void_p]
         _lib = l
     return _lib
 
@@ -209,6 +215,10 @@ class Engine:
         s = Stats()
         _check(lib().gklb_engine_stats(self._h, C.byref(s)))
         return s
+
+    def sweep_kernel(self) -> str:
+        """Name of the forward-sweep kernel the staged batch launches."""
+        return lib().gklb_engine_sweep_kernel(self._h).decode()
 
 
 def device_count() -> int:

@@ -94,29 +94,41 @@ typedef struct gklb_engine gklb_engine;
 /* initNative.  use_double mirrors PairHMMNativeArguments.useDoublePrecision; max_threads is
  * accepted for signature compatibility and ignored (GKL's non-OpenMP library ignores it too,
  * IntelPairHmm.cc:85-89).  Device selection: env GKLB_DEVICE (one device, default 0) or GKLB_DEVICES
- * ("all" or "0,1,..."): with several devices, batches of more than ~4e9 cells per device are sharded over
- * reads inside this process (one host thread and one engine per GPU; each GPU copies its shard and the
- * haplotype panel over its own PCIe link and writes its contiguous slab of the read-major output
- * directly).  May be called again; re-initialises with the new arguments. */
+ * ("all" or "0,1,...").  The state behind this surface is a pool of engines (engine_global.cu): init and done
+ * are reference counted -- GKL's native state is read-only after initNative and its doneNative is empty
+ * (IntelPairHmm.cc:41-48,189-192), so several IntelPairHmm instances may initialise and close independently --
+ * and a repeated init is cheap: engines are kept.  The precision of the last init wins, as with GKL's
+ * g_use_double. */
 GKLB_API int gklb_pairhmm_init(int use_double, int max_threads);
 
 /* computeLikelihoodsNative.  Host arenas in, likelihoods[r * n_haps + h] (log10) out; synchronous.
- * n_reads == 0 or n_haps == 0 is a no-op returning GKLB_OK, like GKL.  Thread-safe: concurrent
- * callers are serialised on the engine. */
+ * n_reads == 0 or n_haps == 0 is a no-op returning GKLB_OK, like GKL.  Thread-safe and concurrent: every call
+ * borrows its own engine from the pool, on the least busy configured device (Spark executors call
+ * computeLikelihoods from several threads, IntelPairHmm.java:65 synchronises only load()).  With several
+ * devices, batches of more than ~4e9 cells per device are sharded over reads inside the call (env GKLB_SHARD =
+ * direct | nccl, see engine_global.cu / engine_nccl.cu). */
 GKLB_API int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods);
 
-/* doneNative.  Frees the device state of the global engine; idempotent; init may follow. */
+/* doneNative.  Drops one reference; the last one frees the idle engines (device memory, streams, events).
+ * Idempotent; a later compute creates engines again. */
 GKLB_API int gklb_pairhmm_done(void);
 
-/* Number of devices the global surface was initialised with, and the counters of its last compute call
- * (summed over devices; phase times are the maximum over devices). */
+/* Number of devices the global surface was initialised with, engines currently alive in the pool, and the
+ * counters of the last compute call that finished (summed over devices; phase times are the maximum). */
 GKLB_API int gklb_pairhmm_devices_in_use(void);
+GKLB_API int gklb_pairhmm_engines_alive(void);
 GKLB_API int gklb_pairhmm_last_stats(gklb_pairhmm_stats* out);
+
+/* Borrow an engine of the pool for a sequence of gklb_engine_* calls (the JNI layer pipelines large calls over two
+ * engines of one device); device < 0: the least busy configured device.  Must be given back. */
+GKLB_API int gklb_pairhmm_acquire_engine(int device, gklb_engine** out);
+GKLB_API int gklb_pairhmm_release_engine(gklb_engine* e);
 
 /* ---- explicit engines: one per (host thread | device); used by the benchmark and multi-GPU host ---- */
 
 GKLB_API int gklb_engine_create(gklb_engine** out, int device, int use_double);
 GKLB_API int gklb_engine_destroy(gklb_engine* e);
+GKLB_API int gklb_engine_device(gklb_engine* e);
 
 /* Run all work of this engine on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
  * the caller's current stream so that caller-side CUDA events bracket the kernels.  NULL restores
@@ -155,6 +167,8 @@ GKLB_API int gklb_engine_result_device(gklb_engine* e, void** dev_ptr);
 GKLB_API int gklb_engine_synchronize(gklb_engine* e);
 
 GKLB_API int gklb_engine_stats(gklb_engine* e, gklb_pairhmm_stats* out);
+/* Name of the forward-sweep kernel the staged batch's plan launches (for bench reports). */
+GKLB_API const char* gklb_engine_sweep_kernel(gklb_engine* e);
 
 /* Time `iters` back-to-back runs of the staged batch with CUDA events recorded on the engine's
  * stream; returns the mean milliseconds per run in *ms_per_run. */
