@@ -13,12 +13,15 @@ NCCL broadcast of the haplotype panel and an NCCL gather of the likelihood slabs
 Printed keys (one JSON line, rank 0):
   value        GCUPS with the batch already resident in HBM (CUDA events around K steps, L2 flushed
                between steps, max over ranks)
-  e2e          the same metric through the operator interface with HOST buffers: per step the packed
-               arenas are copied host->device, kernels run, likelihoods come back device->host
+  e2e          the same metric through the C-ABI with HOST buffers: per step the packed arenas are copied
+               host->device, kernels run, likelihoods come back device->host
   roofline     the forward-sweep kernel against the measured fp32 FMA rate of this GPU (the recurrence is
                CUDA-core fp32 bound: 12 flop and ~4e-4 HBM bytes per cell), with the HBM view beside it
   cpu_baseline GKL's own AVX-512/AVX PairHMM (oracle/_ref) or the oracle port, all host threads
-  --impl reference  times only that CPU arm and prints it in the same shape.
+  configs      the other BASELINE.json configurations, each with value / e2e / parity / roofline / cpu_baseline:
+               c3 (32 HaplotypeCaller-shaped regions) and c5 (PDHMM) at N=1, c4 (1 M x 256 through the
+               in-process multi-GPU product path) at N=8 (bench/configs.py)
+  --impl reference  times only the CPU arm and prints it in the same shape.
 """
 from __future__ import annotations
 
@@ -43,6 +46,12 @@ FLOP_PER_CELL = 12  # 8 mul + 4 add, avx-pairhmm-template.h:213-222 (SURVEY.md 8
 
 def env_int(name, default):
     return int(os.environ.get(name, default))
+
+
+def workload_name(n_reads: int, n_haps: int) -> str:
+    """One string for both arms (the driver compares them)."""
+    return (f"configs[1]: {n_reads} reads (len 101) x {n_haps} haplotypes (len 200-400) per GPU, empirical quals; "
+            "fp32 forward sweep + fp64 rerun of pairs under 1e-28 (IntelPairHmm.cc:150-169)")
 
 
 def workload(rank: int, n_reads: int, n_haps: int):
@@ -98,21 +107,32 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def fp32_peak_tflops():
-    """Measured fp32 FMA peak of this GPU (bench/micro/fp32_peak, built by __graft_entry__.build)."""
-    exe = ROOT / "bench" / "micro" / "fp32_peak"
+def _micro_peak(exe_name: str, fallback_file: str, nominal: float, nominal_src: str):
+    exe = ROOT / "bench" / "micro" / exe_name
     try:
         out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60).stdout
         rows = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
         best = max(r["tflops"] for r in rows if "tflops" in r)
-        return best, "measured live: bench/micro/fp32_peak (best FFMA variant)"
+        return best, f"measured live: bench/micro/{exe_name} (best variant)"
     except Exception:
         pass
     try:
-        rows = [json.loads(l) for l in (ROOT / "profiles" / "r1_fp32_peak.jsonl").read_text().splitlines()]
-        return max(r["tflops"] for r in rows if "tflops" in r), "profiles/r1_fp32_peak.jsonl (measured on this pool)"
+        rows = [json.loads(l) for l in (ROOT / "profiles" / fallback_file).read_text().splitlines()]
+        return max(r["tflops"] for r in rows if "tflops" in r), f"profiles/{fallback_file} (measured on this pool)"
     except Exception:
-        return 148 * 128 * 2 * 1.965e9 / 1e12, "nominal 148 SM x 128 lanes x 2 x 1.965 GHz"
+        return nominal, nominal_src
+
+
+def fp32_peak_tflops():
+    """Measured fp32 FMA peak of this GPU (bench/micro/fp32_peak, built by __graft_entry__.build)."""
+    return _micro_peak("fp32_peak", "r2_fp32_peak.jsonl", 148 * 128 * 2 * 1.965e9 / 1e12,
+                       "nominal 148 SM x 128 lanes x 2 x 1.965 GHz")
+
+
+def fp64_peak_tflops():
+    """Measured fp64 FMA peak of this GPU (bench/micro/fp64_peak)."""
+    return _micro_peak("fp64_peak", "r2_fp64_peak.jsonl", 148 * 64 * 2 * 1.965e9 / 1e12,
+                       "nominal 148 SM x 64 lanes x 2 x 1.965 GHz")
 
 
 def measured_hbm_gbs():
@@ -122,9 +142,19 @@ def measured_hbm_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def dram_traffic_record():
+    """DRAM bytes per launch of the dominant kernel: an ncu-derived constant (ncu cannot run inside a timed bench), so
+    it carries the commit and the capture it came from."""
+    try:
+        return json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+    except Exception:
+        return None
+
+
 def cpu_arm(b, steps: int, warmup: int):
     """GKL's own compiled PairHMM (or the oracle port) on all host threads; returns (gcups, info).
-    info["out"] holds the CPU likelihoods of the batch (the parity reference of the same run)."""
+    info["out"] holds the CPU likelihoods of the batch (the parity reference of the same run).  The figure is the
+    best of `steps` timed passes after warm-up."""
     import oracle
     threads = oracle.host_threads()
     if oracle.ref_available():
@@ -137,12 +167,10 @@ def cpu_arm(b, steps: int, warmup: int):
         kind, detail = "port", "oracle/pairhmm_oracle.c"
     for _ in range(max(0, warmup - 1)):
         fn()
-    secs = []
-    for _ in range(steps):
-        secs.append(fn()[2])
-    total = sum(secs)
-    return b.cells() * steps / total / 1e9, {"kind": kind, "cores": threads, "detail": detail,
-                                            "seconds_per_step": total / steps, "out": out}
+    secs = [fn()[2] for _ in range(steps)]
+    best = min(secs)
+    return b.cells() / best / 1e9, {"kind": kind, "cores": threads, "detail": detail, "seconds_per_step": best,
+                                    "seconds_mean": sum(secs) / len(secs), "out": out}
 
 
 def run_reference(args):
@@ -156,11 +184,12 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": gcups, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": info["seconds_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"configs[1]: {b.n_reads} reads (len 101) x {b.n_haps} haplotypes (len 200-400), "
-                               "empirical quals", "cells_per_step": b.cells()},
+        "config": {"workload": workload_name(b.n_reads, b.n_haps)},
+        "cells_per_step": b.cells(),
         "cpu_baseline": {"value": gcups, "unit": UNIT, "cores": info["cores"], "kind": info["kind"],
-                         "sample": f"the full batch, {args.steps} passes ({info['detail']}, OpenMP schedule(dynamic,1), "
-                                   f"pair loop only); wall {time.time() - t0:.1f} s"},
+                         "sample": f"the full batch, best of {args.steps} passes ({info['detail']}, OpenMP "
+                                   f"schedule(dynamic,1), pair loop only; mean {info['seconds_mean'] * 1e3:.1f} ms); "
+                                   f"wall {time.time() - t0:.1f} s"},
         "e2e": {"value": gcups, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -170,8 +199,19 @@ def run_reference(args):
 class _DevArray:
     """__cuda_array_interface__ view of an engine-owned device buffer (so torch can gather it)."""
 
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+    def __init__(self, ptr, n, typestr="<f8"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+
+
+def parity_all_pairs(gpu: np.ndarray, cpu: np.ndarray) -> float:
+    """max_i |gpu - cpu| / |cpu| over every pair; a non-finite GPU value where the CPU value is finite (or the other
+    way round) is a failure, reported as inf."""
+    fin = np.isfinite(cpu)
+    if not np.array_equal(np.isfinite(gpu), fin):
+        return float("inf")
+    if not fin.any():
+        return 0.0
+    return float(np.max(np.abs(gpu[fin] - cpu[fin]) / np.abs(cpu[fin])))
 
 
 def run_ours(args):
@@ -185,8 +225,10 @@ def run_ours(args):
     torch.cuda.set_device(local)
     distributed = world > 1
     dev = torch.device("cuda", local)
+    cpu_group = None
     if distributed:
         dist.init_process_group("nccl", device_id=dev)
+        cpu_group = dist.new_group(backend="gloo")  # host-side barriers that do not occupy the GPUs
 
     b = workload(rank, args.reads, args.haps)
     cells = b.cells()
@@ -200,19 +242,23 @@ def run_ours(args):
     hap_dev = torch.from_numpy(b.hap_bases).to(dev)
     arenas_dev = [torch.from_numpy(x).to(dev) for x in (b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp)]
     eng.stage(b, arenas=arenas_dev, hap=hap_dev, device=True)
+    sweep_kernel = eng.sweep_kernel()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     from gkl_b200 import multi
+    panel_buf = hap_dev if rank == 0 else torch.empty_like(hap_dev)
+    gather_bufs = [torch.empty(pairs, dtype=torch.float64, device=dev) for _ in range(world)] if (distributed and rank == 0) else None
 
     def step():
         if distributed:
-            # the haplotype panel travels from GPU 0 over NVLink and is consumed by this step's sweep
-            _, panel = multi.broadcast_panel(b.hap_off if rank == 0 else None, hap_dev if rank == 0 else None, 0, dev)
-            eng.update_haps_device(panel)
+            # the haplotype panel travels from GPU 0 over NVLink (one broadcast of the packed bases; the lengths are
+            # part of the staged batch) and is consumed by this step's sweep; the likelihood slabs go back to GPU 0
+            dist.broadcast(panel_buf, src=0)
+            eng.update_haps_device(panel_buf)
         eng.run()
         if distributed:
             res = torch.as_tensor(_DevArray(eng.result_device_ptr(), pairs), device=dev)
-            multi.gather_slabs(res, [pairs] * world, 0)  # likelihood slabs back to GPU 0
+            dist.gather(res, gather_bufs, dst=0)
 
     for _ in range(args.warmup):
         step()
@@ -237,7 +283,6 @@ def run_ours(args):
         dist.barrier()
     dev_ms = sum(a.elapsed_time(c) for a, c in ev)
     clocks = sampler.result()
-    st = eng.stats()
     resident_out = eng.fetch(pairs)
     fallback = int(eng.stats().fallback_pairs)
 
@@ -257,17 +302,29 @@ def run_ours(args):
         eng.compute(b, arenas=host_arenas, hap=host_hap, out_ptr=host_out.data_ptr())
     e2e_s = time.perf_counter() - t0
     e2e_stats = eng.stats()
+    # the same with pageable buffers (what a JNI caller's std::vector arenas and a JVM-pinned double[] look like)
+    page_out = np.empty(pairs, dtype=np.float64)
+    eng.compute(b, out=page_out)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.compute(b, out=page_out)
+    e2e_page_s = time.perf_counter() - t0
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3, float(cells)], dtype=torch.float64, device=dev)
+    times = torch.tensor([dev_ms, e2e_s * 1e3, float(cells), e2e_page_s * 1e3], dtype=torch.float64, device=dev)
     if distributed:
         tmax = times.clone()
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = times.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms_total, total_cells = float(tmax[0]), float(tmax[1]), float(tsum[2])
+        dev_ms, e2e_ms_total, total_cells, e2e_page_ms = float(tmax[0]), float(tmax[1]), float(tsum[2]), float(tmax[3])
     else:
-        e2e_ms_total, total_cells = e2e_s * 1e3, float(cells)
+        e2e_ms_total, total_cells, e2e_page_ms = e2e_s * 1e3, float(cells), e2e_page_s * 1e3
+    torch.cuda.synchronize()
+    eng.close()
+    del flush, arenas_dev
+    torch.cuda.empty_cache()
 
+    line = None
     if rank == 0:
         value = total_cells * args.steps / (dev_ms * 1e-3) / 1e9
         e2e_value = total_cells * e2e_steps / (e2e_ms_total * 1e-3) / 1e9
@@ -276,11 +333,7 @@ def run_ours(args):
         sweep_per_launch_ms = sweep_ms / max(1, args.steps)
         ach_tf = cells * FLOP_PER_CELL / (sweep_per_launch_ms * 1e-3) / 1e12
         ach_gbs = algorithmic_bytes(b) / (sweep_per_launch_ms * 1e-3) / 1e9
-        try:
-            prof = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
-            traffic = prof.get("dram_bytes_per_launch")
-        except Exception:
-            traffic = None
+        traffic = dram_traffic_record()
         cpu_gcups, cpu_info = cpu_arm(b, 1, 1)
         cpu_out = cpu_info["out"]
         import oracle  # the CPU arm: one more figure, a single host thread on a 300-read slice of the same batch
@@ -288,31 +341,34 @@ def run_ours(args):
         fn1 = oracle.ref_pairhmm if oracle.ref_available() else oracle.port_pairhmm
         fn1(one, False, threads=1)
         cpu_1t = one.cells() / fn1(one, False, threads=1)[2] / 1e9
-        ok = np.isfinite(cpu_out)
-        parity = float(np.max(np.abs(resident_out[ok] - cpu_out[ok]) / np.abs(cpu_out[ok])))
-        parity_e2e = float(np.max(np.abs(host_out.numpy()[ok] - cpu_out[ok]) / np.abs(cpu_out[ok])))
+        parity = max(parity_all_pairs(resident_out, cpu_out), parity_all_pairs(host_out.numpy(), cpu_out),
+                     parity_all_pairs(page_out, cpu_out))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"configs[1] per GPU: {b.n_reads} reads (len 101) x {b.n_haps} haplotypes "
-                                   "(len 200-400), empirical quals; fp32 sweep + fp64 rerun of pairs under 1e-28",
-                       "cells_per_step": total_cells, "pairs_per_gpu": pairs, "fallback_pairs_rank0": fallback,
-                       "l2": "flushed between steps (256 MiB write)",
-                       "parallelism": f"reads sharded over {world} GPU(s); NCCL broadcast of the haplotype panel + "
-                                      "gather of likelihood slabs per step" if world > 1 else "single GPU",
-                       "parity_max_rel_err_all_pairs_vs_cpu_baseline": max(parity, parity_e2e)},
+            "config": {"workload": workload_name(b.n_reads, b.n_haps)},
+            "cells_per_step": total_cells, "pairs_per_gpu": pairs, "fallback_pairs_rank0": fallback,
+            "l2": "flushed between steps (256 MiB write)",
+            "parallelism": (f"reads sharded over {world} GPUs, one process per GPU; per step one NCCL broadcast of the "
+                            "haplotype panel and one NCCL gather of the likelihood slabs to GPU 0") if world > 1
+                           else "single GPU",
+            "parity_max_rel_err_all_pairs_vs_cpu_baseline": parity,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(5 * int(b.read_off[-1]) + int(b.hap_off[-1]) + 8 * (b.n_reads + 1)
                                               + 8 * (b.n_haps + 1)) * world,
                     "d2h_bytes_per_step": 8 * pairs * world, "ms_per_step": e2e_ms_total / e2e_steps,
                     "phases_ms_rank0": {"h2d_pack": e2e_stats.h2d_ms, "kernels": e2e_stats.kernel_ms,
                                         "d2h": e2e_stats.d2h_ms},
-                    "api": "gklb_engine_compute (what computeLikelihoodsNative calls), pinned host buffers"},
+                    "api": "gklb_engine_compute (what computeLikelihoodsNative calls), pinned host buffers",
+                    "pageable_host_buffers": {"value": total_cells * e2e_steps / (e2e_page_ms * 1e-3) / 1e9,
+                                              "ms_per_step": e2e_page_ms / e2e_steps}},
             "gpu_launches": launches,
             "clocks": clocks,
-            "roofline": {"bound": "fp32", "kernel": "k_sweep_tasks<VF2,16,7,12,false,5>", "achieved": ach_tf, "peak": peak_tf,
-                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf, "traffic": traffic,
+            "roofline": {"bound": "fp32", "kernel": sweep_kernel, "achieved": ach_tf, "peak": peak_tf,
+                         "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                         "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                         "traffic_source": traffic,
                          "flop_per_cell": FLOP_PER_CELL, "ms_per_launch": sweep_per_launch_ms, "peak_source": peak_src,
                          "hbm": {"achieved": ach_gbs, "peak": hbm, "unit": "GB/s", "frac": ach_gbs / hbm,
                                  "peak_source": hbm_src, "algorithmic_bytes_per_launch": algorithmic_bytes(b)},
@@ -322,8 +378,29 @@ def run_ours(args):
                              "sample": f"the full rank-0 batch once ({cpu_info['detail']}, all host threads, pair loop only, "
                                        f"{cpu_info['seconds_per_step']:.2f} s)"},
         }
+
+    # ---- the other BASELINE configurations (rank 0; the other ranks idle on a host-side barrier) ----
+    if not args.no_configs:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("gklb_bench_configs", ROOT / "bench" / "configs.py")
+        extra = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(extra)
+        extra.PEAKS.update(fp32=fp32_peak_tflops, fp64=fp64_peak_tflops)
+        if rank == 0:
+            cfgs = {}
+            try:
+                if world == 1:
+                    cfgs["c3"] = extra.config3(local)
+                    cfgs["c5"] = extra.config5(local)
+                elif world == 8 or args.force_c4:
+                    cfgs["c4"] = extra.config4(world, reads=args.c4_reads)
+            except Exception as ex:  # the headline line must survive a failure here
+                cfgs["error"] = f"{type(ex).__name__}: {ex}"
+            line["configs"] = cfgs
+        if distributed:
+            dist.barrier(group=cpu_group)
+    if rank == 0:
         print(json.dumps(line), flush=True)
-    eng.close()
     if distributed:
         dist.destroy_process_group()
 
@@ -336,6 +413,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--reads", type=int, default=10_000, help="reads per GPU (BASELINE configs[1]: 10000)")
     ap.add_argument("--haps", type=int, default=128)
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs object (c3/c5 at N=1, c4 at N=8)")
+    ap.add_argument("--force-c4", action="store_true", help="run config 4 at any N > 1 (measurement)")
+    ap.add_argument("--c4-reads", type=int, default=1_000_000)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -153,15 +153,15 @@ class IntelPDHMM:
         if len(likelihoodArray) != len(readDataArray) * len(haplotypeDataArray):
             raise IllegalArgumentException("likelihoodArray length must be equal to readDataArray length * haplotypeDataArray length")
         # operands once (haplotype h at h * max_hap, read r at r * max_read); the cross product is device-side
-        ops = PdhmmBatch.from_pairs(
-            [(h.haplotypeBases, h.haplotypePDBases, b"", b"", b"", b"", b"") for h in haplotypeDataArray])
-        rds = PdhmmBatch.from_pairs(
-            [(b"", b"", r.readBases, r.readQuals, r.insertionGOP, r.deletionGOP, r.overallGCP) for r in readDataArray])
-        b = PdhmmBatch(ops.hap_bases, ops.hap_pdbases, rds.read_bases, rds.read_qual, rds.read_ins_qual, rds.read_del_qual,
-                       rds.gcp, ops.hap_lengths, rds.read_lengths, ops.max_hap, rds.max_read)
+        b = PdhmmBatch.operands(
+            [(r.readBases, r.readQuals, r.insertionGOP, r.deletionGOP, r.overallGCP) for r in readDataArray],
+            [(h.haplotypeBases, h.haplotypePDBases) for h in haplotypeDataArray])
+        self.compute_cross(b, likelihoodArray)
+
+    def compute_cross(self, b: PdhmmBatch, out: np.ndarray) -> None:
+        """gklb_pdhmm_compute_cross on prepared operands (PdhmmBatch.operands): out[r * H + h]."""
         s = _struct(b, 0)
-        rc = _lib().gklb_pdhmm_compute_cross(C.byref(s), len(readDataArray), len(haplotypeDataArray),
-                                             likelihoodArray.ctypes.data)
+        rc = _lib().gklb_pdhmm_compute_cross(C.byref(s), len(b.read_lengths), len(b.hap_lengths), out.ctypes.data)
         if rc:
             _raise(rc)
 

@@ -63,6 +63,25 @@ class PdhmmBatch:
         return PdhmmBatch(hb, pd, rb, q, i, d, c, hl, rl, max_hap, max_read)
 
     @staticmethod
+    def operands(reads, haps) -> "PdhmmBatch":
+        """The operands of IntelPDHMM.computeLikelihoods once each (what gklb_pdhmm_compute_cross takes): haplotype h
+        at h * max_hap (hap_lengths[H]), read r at r * max_read (read_lengths[R]); the cross product is device-side."""
+        ops = PdhmmBatch.from_pairs([(h[0], h[1], b"", b"", b"", b"", b"") for h in haps])
+        rds = PdhmmBatch.from_pairs([(b"", b"", r[0], r[1], r[2], r[3], r[4]) for r in reads])
+        return PdhmmBatch(ops.hap_bases, ops.hap_pdbases, rds.read_bases, rds.read_qual, rds.read_ins_qual,
+                          rds.read_del_qual, rds.gcp, ops.hap_lengths, rds.read_lengths, ops.max_hap, rds.max_read)
+
+    def expand_cross(self, r0: int, r1: int) -> "PdhmmBatch":
+        """Flat batch of reads [r0, r1) x all haplotypes of an `operands` object, pair index (r - r0) * H + h
+        (the expansion of pdhmm/JavaData.h:177-242, vectorised)."""
+        H, nr = len(self.hap_lengths), r1 - r0
+        hap = lambda a: np.tile(a.reshape(H, self.max_hap), (nr, 1)).ravel()
+        rd = lambda a: np.repeat(a.reshape(-1, self.max_read)[r0:r1], H, axis=0).ravel()
+        return PdhmmBatch(hap(self.hap_bases), hap(self.hap_pdbases), rd(self.read_bases), rd(self.read_qual),
+                          rd(self.read_ins_qual), rd(self.read_del_qual), rd(self.gcp), np.tile(self.hap_lengths, nr),
+                          np.repeat(self.read_lengths[r0:r1], H), self.max_hap, self.max_read)
+
+    @staticmethod
     def cross(reads, haps) -> "PdhmmBatch":
         """reads: list of (bases, qual, ins, del, gcp); haps: list of (bases, pd).  Pair index r * H + h."""
         return PdhmmBatch.from_pairs([(h[0], h[1], r[0], r[1], r[2], r[3], r[4]) for r in reads for h in haps])

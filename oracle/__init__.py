@@ -122,6 +122,26 @@ def ref_pairhmm(batch, use_double: bool = False, threads: int = 1, engine: int =
     return out, bool(used.value), secs.value
 
 
+def ref_pairhmm_pairs(batch, pair_r: np.ndarray, pair_h: np.ndarray, threads: int = 1):
+    """GKL's own compiled PairHMM (fp32, fp64 rerun under 1e-28, as IntelPairHmm.cc:150-169) on an explicit list of
+    (read, haplotype) pairs of `batch`.  Returns (log10 likelihoods[len(pair_r)], seconds)."""
+    lib = _load_ref()
+    _i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    lib.gklref_pairhmm_pairs.restype = C.c_int
+    lib.gklref_pairhmm_pairs.argtypes = [C.c_long, _i32, _i32, _i64p, _u8p, _u8p, _u8p, _u8p, _u8p, _i64p, _u8p, C.c_int,
+                                         _f64p, C.POINTER(C.c_double)]
+    pr = np.ascontiguousarray(pair_r, dtype=np.int32)
+    ph = np.ascontiguousarray(pair_h, dtype=np.int32)
+    out = np.empty(len(pr), dtype=np.float64)
+    secs = C.c_double(0)
+    rc = lib.gklref_pairhmm_pairs(len(pr), pr, ph, batch.read_off, batch.read_bases, batch.read_quals, batch.ins_gop,
+                                  batch.del_gop, batch.gcp, batch.hap_off, batch.hap_bases, int(threads), out,
+                                  C.byref(secs))
+    if rc != 0:
+        raise RuntimeError(f"gklref_pairhmm_pairs failed: {rc}")
+    return out, secs.value
+
+
 def ref_avx512_supported() -> bool:
     return bool(_load_ref().gklref_avx512_supported())
 

@@ -112,6 +112,50 @@ int gklref_pairhmm(int n_reads, int n_haps, const int64_t* read_off, const uint8
   return 0;
 }
 
+// The same arithmetic for an explicit list of (read, haplotype) pairs: out[k] is the value
+// computeLikelihoods would write at index pair_r[k] * n_haps + pair_h[k].  Used to check every fp64-rerun pair of
+// a batch too large to recompute in full on the host (BASELINE configs[3]).
+int gklref_pairhmm_pairs(long n_pairs, const int32_t* pair_r, const int32_t* pair_h, const int64_t* read_off,
+                         const uint8_t* read_bases, const uint8_t* read_quals, const uint8_t* ins_gop,
+                         const uint8_t* del_gop, const uint8_t* gcp, const int64_t* hap_off, const uint8_t* hap_bases,
+                         int n_threads, double* out, double* seconds) {
+  _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+  ConvertChar::init();
+  const bool avx512 = is_avx512_supported();
+  float (*fp_float)(testcase*) = avx512 ? compute_fp_avx512s : compute_fp_avxs;
+  double (*fp_double)(testcase*) = avx512 ? compute_fp_avx512d : compute_fp_avxd;
+  const int max_threads = n_threads < 1 ? 1 : n_threads;
+  double t0 = now_s();
+#ifdef _OPENMP
+#pragma omp parallel num_threads(max_threads)
+#endif
+  {
+    _MM_SET_FLUSH_ZERO_MODE(_MM_FLUSH_ZERO_ON);
+#ifdef _OPENMP
+#pragma omp for schedule(dynamic, 64)
+#endif
+    for (long k = 0; k < n_pairs; k++) {
+      const int r = pair_r[k], h = pair_h[k];
+      testcase tc;
+      tc.hap = (const char*)hap_bases + hap_off[h];
+      tc.haplen = (int)(hap_off[h + 1] - hap_off[h]);
+      tc.rs = (const char*)read_bases + read_off[r];
+      tc.rslen = (int)(read_off[r + 1] - read_off[r]);
+      tc.i = (const char*)ins_gop + read_off[r];
+      tc.d = (const char*)del_gop + read_off[r];
+      tc.c = (const char*)gcp + read_off[r];
+      tc.q = (const char*)read_quals + read_off[r];
+      float result_float = fp_float(&tc);
+      if (result_float < MIN_ACCEPTED)
+        out[k] = log10(fp_double(&tc)) - g_ctxd.LOG10_INITIAL_CONSTANT;
+      else
+        out[k] = (double)(log10f(result_float) - g_ctxf.LOG10_INITIAL_CONSTANT);
+    }
+  }
+  if (seconds) *seconds = now_s() - t0;
+  return 0;
+}
+
 int gklref_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
