@@ -171,9 +171,8 @@ int set_kernel_attrs() {
   return GKLB_OK;
 }
 
-// Build the class instances for this batch.
-int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
-  e->classes.clear();
+// Build the class instances of one region (appended to e->classes).
+int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b, int region, int read_base) {
   const bool h2 = !e->use_double && !e->forced;
   const int n_single = h2 ? kNumClassesH2 : kNumClassesD1;
   std::vector<std::vector<int32_t>> rid(n_single), len(n_single);  // single-pass classes, by configuration
@@ -185,7 +184,7 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
     if (len64 > (1 << 24)) return fail(GKLB_ERR_INVALID, "read %d is too long (%lld)", r, (long long)len64);
     const int L = (int)len64;
     if (e->forced && L <= e->f_G * e->f_K) {
-      forced.rid.push_back(r);
+      forced.rid.push_back(read_base + r);
       forced.len.push_back(L);
     } else if (L <= kSinglePassMax) {
       int ci = 0;
@@ -195,7 +194,7 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
       } else {
         while (kClassesD1[ci].G * kClassesD1[ci].K < L) ci++;
       }
-      rid[ci].push_back(r);
+      rid[ci].push_back(read_base + r);
       len[ci].push_back(L);
     } else {
       const int cap = kMultiG * kMultiK;
@@ -213,7 +212,7 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
         multi_inst.push_back({n_pass, inst});
         multi.push_back(c);
       }
-      multi[inst].rid.push_back(r);
+      multi[inst].rid.push_back(read_base + r);
       multi[inst].len.push_back(L);
     }
   }
@@ -243,6 +242,7 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
       len[ci].swap(keep_l);
     }
   }
+  const size_t first = e->classes.size();
   for (int ci = 0; ci < n_single; ci++) {
     if (rid[ci].empty()) continue;
     ClassInst c;
@@ -271,8 +271,10 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b) {
     e->classes.push_back(std::move(forced));
   }
   for (auto& c : multi) e->classes.push_back(std::move(c));
-  for (auto& c : e->classes) {
+  for (size_t i = first; i < e->classes.size(); i++) {
+    ClassInst& c = e->classes[i];
     if (!c.kf || !c.kd) return fail(GKLB_ERR_STATE, "kernel for class G=%d K=%d is not compiled", c.G, c.K);
+    c.region = region;
     c.rows = c.n_pass * c.G * c.K;
     c.stride = (int)align_up((size_t)c.rows, 16);
     const int rpw = (32 / c.G) * c.kf->nr;
@@ -296,24 +298,29 @@ uint32_t slot_bytes_total(const ClassInst& c, const KernelEntry* k, bool list_mo
   return (uint32_t)k->warps * (uint32_t)align_up((size_t)warp_slot_bytes(c, k, list_mode), 128);
 }
 
-// Split the haplotypes into tiles whose panel image fits beside the largest slot area.
-int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, size_t* meta_bytes) {
+// Shared memory left for the resident image(s) beside the largest slot area any launch of this job uses.
+long long image_budget(gklb_engine* e) {
   uint32_t worst_slots = 0;
   for (auto& c : e->classes) {
     worst_slots = std::max(worst_slots, slot_bytes_total(c, c.kf, false));
     worst_slots = std::max(worst_slots, slot_bytes_total(c, c.kd, !e->use_double));
   }
-  const long long budget = (long long)kSmemMax - 4096 - worst_slots;
-  e->tiles.clear();
-  int h = 0;
+  return (long long)kSmemMax - 8192 - worst_slots;  // 8 KB: mbarriers, ph2pr table, task prefix of multi-class launches
+}
+
+// Split one region's haplotypes into tiles whose images fit in `budget` bytes (appended to e->tiles).
+int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, int region, long long budget) {
+  int h = 0, index = 0;
   while (h < b->n_haps) {
     Tile t;
+    t.region = region;
+    t.index_in_region = index++;
     t.hap0 = h;
     size_t data = 0;
     while (h < b->n_haps) {
       const size_t len = (size_t)(b->hap_off[h + 1] - b->hap_off[h]);
       const size_t add = kHapLeftMargin + len + kHapRightMargin;
-      const size_t header = align_up((size_t)20 * (t.n + 1), 16);   // the pair image's header is the larger one
+      const size_t header = align_up((size_t)20 * (t.n + 1), 16);  // the pair image's header is the larger one
       if (t.n > 0 && (long long)(header + data + add + 16) > budget) break;
       if (t.n == 0 && (long long)(header + add + 16) > budget)
         return fail(GKLB_ERR_INVALID, "haplotype %d (%zu bases) does not fit in shared memory", h, len);
@@ -323,8 +330,6 @@ int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, size_t* meta_bytes) 
       h++;
     }
     t.bytes = (uint32_t)align_up(align_up((size_t)8 * t.n, 16) + data, 16);
-    t.meta_off = *meta_bytes;
-    *meta_bytes += align_up(t.bytes, 128);
     // pair image: haplotypes by decreasing length, adjacent ones share a byte column
     t.order.resize(t.n);
     for (int i = 0; i < t.n; i++) t.order[i] = t.hap0 + i;
@@ -338,16 +343,60 @@ int plan_tiles(gklb_engine* e, const gklb_pairhmm_batch* b, size_t* meta_bytes) 
       pdata += kHapLeftMargin + (size_t)(b->hap_off[a + 1] - b->hap_off[a]) + kHapRightMargin;
     }
     t.pbytes = (uint32_t)align_up(align_up((size_t)20 * t.n_pairs, 16) + pdata, 16);
-    t.pmeta_off = *meta_bytes;
-    *meta_bytes += align_up(t.pbytes, 128);
-    // device-resident class parameter arrays of the multi-class fp64 launches
-    t.cls_list_off = *meta_bytes;
-    *meta_bytes += align_up(sizeof(SweepParams) * e->classes.size(), 128);
-    t.cls_tasks_off = *meta_bytes;
-    *meta_bytes += align_up(sizeof(SweepParams) * e->classes.size(), 128);
-    e->tiles.push_back(t);
+    e->tiles.push_back(std::move(t));
   }
   return GKLB_OK;
+}
+
+int classes_of_region(const gklb_engine* e, int region) {
+  int n = 0;
+  for (auto& c : e->classes) n += (c.region == region);
+  return n;
+}
+
+// Pack consecutive tiles into launch groups (their images resident together) and lay everything out in the meta block.
+void plan_groups(gklb_engine* e, long long budget, size_t* meta_bytes) {
+  e->groups.clear();
+  const int max_entries = kMaxMegaClasses;
+  size_t i = 0;
+  while (i < e->tiles.size()) {
+    Group g;
+    g.tile0 = (int)i;
+    while (i < e->tiles.size()) {
+      Tile& t = e->tiles[i];
+      const int ent = classes_of_region(e, t.region);
+      if (g.n_tiles > 0 && ((long long)(g.bytes + t.bytes) > budget || (long long)(g.pbytes + t.pbytes) > budget ||
+                            g.n_entries + ent > max_entries))
+        break;
+      t.img_off = g.bytes;
+      t.pimg_off = g.pbytes;
+      g.bytes += t.bytes;    // multiples of 16: every image stays 16-byte aligned for the bulk copy
+      g.pbytes += t.pbytes;
+      g.n_entries += ent;
+      g.n_tiles++;
+      i++;
+    }
+    g.meta_off = *meta_bytes;
+    *meta_bytes += align_up(g.bytes, 128);
+    g.pmeta_off = *meta_bytes;
+    *meta_bytes += align_up(g.pbytes, 128);
+    for (int k = 0; k < g.n_tiles; k++) {
+      Tile& t = e->tiles[g.tile0 + k];
+      t.meta_off = g.meta_off + t.img_off;
+      t.pmeta_off = g.pmeta_off + t.pimg_off;
+    }
+    const size_t n = (size_t)g.n_entries;
+    auto take = [&](size_t bytes) { const size_t o = *meta_bytes; *meta_bytes += align_up(bytes, 128); return o; };
+    g.h2_cls_off = take(sizeof(H2Class) * n);
+    g.h2_cfg_off = take(sizeof(int) * n);
+    g.h2_end_off = take(sizeof(int) * n);
+    g.dl_cls_off = take(sizeof(SweepParams) * n);
+    g.dl_cfg_off = take(sizeof(int) * n);
+    g.dt_cls_off = take(sizeof(SweepParams) * n);
+    g.dt_cfg_off = take(sizeof(int) * n);
+    g.dt_end_off = take(sizeof(int) * n);
+    e->groups.push_back(g);
+  }
 }
 
 void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) {
@@ -405,13 +454,21 @@ int tasks_per_warp_target() {
 
 // ---- launch plan ---------------------------------------------------------------------------------------------
 
+// The region's likelihoods, biased by the region's first read so that kernels index rows by job-wide read index.
+double* region_out(gklb_engine* e, const Region& r) {
+  return static_cast<double*>(e->d_out.p) + r.out_base - (int64_t)r.read_base * r.n_haps;
+}
+
 struct Sizing { int grid; size_t smem; uint32_t slot_bytes; };
 
-// Parameters of one fp64 / packed-read (class, tile, kernel) combination.
-Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, int tile_index,
-                   SweepParams* out) {
+// Parameters of one fp64 / packed-read (class, tile, kernel) combination.  resident: the panel is part of a group
+// image (multi-class launch); otherwise the launch loads the tile's own image.  work_scale: how many warp slots the
+// launch can count on for this entry (the whole GPU for a single-class launch, a share of it in a group).
+Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, bool resident,
+                   long long group_units, SweepParams* out) {
   const bool dbl = (k->policy == POL_D1);
   const HostTables& ht = host_tables();
+  const Region& reg = e->regions[c.region];
   SweepParams& p = *out;
   memset(&p, 0, sizeof(p));
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
@@ -419,8 +476,9 @@ Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kern
   p.panel.bytes = t.bytes;
   p.panel.n_haps = t.n;
   p.panel.hap0 = t.hap0;
-  p.panel.n_haps_total = e->n_haps;
+  p.panel.n_haps_total = reg.n_haps;
   p.panel.max_hap_len = t.max_len;
+  p.panel.smem_off = resident ? t.img_off : 0u;
   p.cls.records = static_cast<const uint8_t*>(e->d_records.p) + c.rec_off;
   p.cls.rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
   p.cls.rec_len = reinterpret_cast<const int32_t*>(dm + c.meta_len);
@@ -430,11 +488,11 @@ Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kern
   p.cls.n_pass = c.n_pass;
   p.ph2pr = dbl ? (const void*)e->d_ph2pr_d : (const void*)e->d_ph2pr_f;
   p.mm = dbl ? (const void*)e->d_mm_d : (const void*)e->d_mm_f;
-  p.out = static_cast<double*>(e->d_out.p);
+  p.out = region_out(e, reg);
   unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
   p.fb_count = counters + c.counter0;
   p.fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + c.fb_off : nullptr;
-  p.task_counter = counters + c.counter0 + 1 + 2 * tile_index + (list_mode ? 1 : 0);
+  p.task_counter = counters + c.counter0 + 1 + 2 * t.index_in_region + (list_mode ? 1 : 0);
   p.carry = c.multi ? static_cast<uint8_t*>(e->d_carry.p) + c.carry_off : nullptr;
   p.carry_stride_bytes = c.carry_stride;
   p.init_const = dbl ? ht.init_d : (double)ht.init_f;
@@ -445,7 +503,8 @@ Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kern
     const int rpw = (32 / k->G) * k->nr;
     const int n_blocks = c.n_rec / rpw;
     const int slots = e->num_sms * k->warps;
-    long long chunk = ((long long)n_blocks * t.n) / ((long long)tasks_per_warp_target() * slots);
+    const long long units = std::max<long long>(group_units, (long long)n_blocks * t.n);
+    long long chunk = units / ((long long)tasks_per_warp_target() * slots);
     chunk = std::max(1LL, std::min(chunk, 32LL));
     if (c.multi) chunk = 1;
     chunk = std::min<long long>(chunk, t.n);
@@ -464,24 +523,21 @@ Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kern
   return z;
 }
 
-void fill_h2_common(gklb_engine* e, const Tile& t, H2Common* com) {
+void fill_h2_common(gklb_engine* e, const uint8_t* image, uint32_t bytes, H2Common* com) {
   const HostTables& ht = host_tables();
   memset(com, 0, sizeof(*com));
-  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
-  com->panel.image = dm + t.pmeta_off;
-  com->panel.bytes = t.pbytes;
-  com->panel.n_pairs = t.n_pairs;
-  com->panel.n_haps_total = e->n_haps;
-  com->panel.max_hap_len = t.max_len;
+  com->image = image;
+  com->image_bytes = bytes;
   com->ph2pr = e->d_ph2pr_f;
   com->mm = e->d_mm_f;
-  com->out = static_cast<double*>(e->d_out.p);
   com->init_const = ht.init_f;
   com->log10_init = ht.log10_init_f;
 }
 
-void fill_h2_class(gklb_engine* e, const ClassInst& c, const Tile& t, int warps, H2Class* cls) {
+void fill_h2_class(gklb_engine* e, const ClassInst& c, const Tile& t, int warps, bool resident, long long group_units,
+                   H2Class* cls) {
   memset(cls, 0, sizeof(*cls));
+  const Region& reg = e->regions[c.region];
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
   cls->records = static_cast<const uint8_t*>(e->d_records.p) + c.rec_off;
   cls->rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
@@ -492,9 +548,14 @@ void fill_h2_class(gklb_engine* e, const ClassInst& c, const Tile& t, int warps,
   cls->n_rec = c.n_rec;
   cls->rows = c.rows;
   cls->stride = c.stride;
+  cls->panel_off = resident ? t.pimg_off : 0u;
+  cls->n_pairs = t.n_pairs;
+  cls->n_haps_total = reg.n_haps;
+  cls->out = region_out(e, reg);
   const int n_blocks = c.n_rec / (32 / c.G);
   const int slots = e->num_sms * warps;
-  long long chunk = ((long long)n_blocks * t.n_pairs) / ((long long)tasks_per_warp_target() * slots);
+  const long long units = std::max<long long>(group_units, (long long)n_blocks * t.n_pairs);
+  long long chunk = units / ((long long)tasks_per_warp_target() * slots);
   chunk = std::max(1LL, std::min(chunk, 32LL));
   chunk = std::min<long long>(chunk, t.n_pairs);
   cls->pair_chunk = (int)chunk;
@@ -514,13 +575,14 @@ int push_launch(gklb_engine* e, Launch&& l) {
   return GKLB_OK;
 }
 
-Launch h2_single_launch(gklb_engine* e, const ClassInst& c, const Tile& t, int ti) {
+Launch h2_single_launch(gklb_engine* e, const ClassInst& c, const Tile& t) {
   H2Params p;
   memset(&p, 0, sizeof(p));
-  fill_h2_common(e, t, &p.com);
-  fill_h2_class(e, c, t, c.kf->warps, &p.cls);
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  fill_h2_common(e, dm + t.pmeta_off, t.pbytes, &p.com);
+  fill_h2_class(e, c, t, c.kf->warps, false, 0, &p.cls);
   p.com.slot_bytes = warp_slot_bytes(c, c.kf, false);
-  p.task_counter = static_cast<unsigned int*>(e->d_counters.p) + c.counter0 + 1 + 2 * ti;
+  p.task_counter = static_cast<unsigned int*>(e->d_counters.p) + c.counter0 + 1 + 2 * t.index_in_region;
   Launch l;
   l.fn = c.kf->fn_tasks;
   l.threads = c.kf->warps * 32;
@@ -532,8 +594,10 @@ Launch h2_single_launch(gklb_engine* e, const ClassInst& c, const Tile& t, int t
   return l;
 }
 
-// Build the launches of the staged batch.  hm: host image of the meta block (the device-resident class arrays of the
-// multi-class fp64 kernels are written into it before it is uploaded).
+struct Entry { const ClassInst* c; const Tile* t; };
+
+// Build the launches of the staged job.  hm: host image of the meta block (the device-resident class arrays of the
+// multi-class kernels are written into it before it is uploaded).
 int build_plan(gklb_engine* e, uint8_t* hm) {
   e->plan.clear();
   e->sweep_kernel[0] = 0;
@@ -542,52 +606,66 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
   unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
   int rc;
-  for (size_t ti = 0; ti < e->tiles.size(); ti++) {
-    const Tile& t = e->tiles[ti];
-    std::vector<const ClassInst*> order;  // longest classes first: their tasks are the most expensive
-    for (auto& c : e->classes) order.push_back(&c);
-    std::stable_sort(order.begin(), order.end(), [](const ClassInst* a, const ClassInst* b) { return a->rows > b->rows; });
+  for (size_t gi = 0; gi < e->groups.size(); gi++) {
+    const Group& g = e->groups[gi];
+    // (class, tile) entries of the group, longest classes first: their tasks are the most expensive
+    std::vector<Entry> entries;
+    for (int k = 0; k < g.n_tiles; k++) {
+      const Tile& t = e->tiles[g.tile0 + k];
+      for (auto& c : e->classes)
+        if (c.region == t.region) entries.push_back({&c, &t});
+    }
+    std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.c->rows > b.c->rows; });
+    unsigned int* queue = counters + e->mega_counter0 + 2 * gi;
 
     if (e->use_double) {  // ---- fp64 over all pairs ----
-      if (mega_ok && e->classes.size() > 1) {
+      if (mega_ok && entries.size() > 1) {
+        long long units = 0;
+        for (auto& en : entries) units += (long long)(en.c->n_rec / ((32 / en.c->kd->G) * en.c->kd->nr)) * en.t->n;
         MegaParams mp;
         memset(&mp, 0, sizeof(mp));
-        SweepParams* arr = reinterpret_cast<SweepParams*>(hm + t.cls_tasks_off);
+        SweepParams* arr = reinterpret_cast<SweepParams*>(hm + g.dt_cls_off);
+        int* cfg = reinterpret_cast<int*>(hm + g.dt_cfg_off);
+        int* ends = reinterpret_cast<int*>(hm + g.dt_end_off);
         uint32_t slot_bytes = 0;
         int tasks = 0;
-        for (const ClassInst* c : order) {
+        for (auto& en : entries) {
           const int i = mp.n_classes++;
-          const Sizing z = fill_params(e, *c, t, c->kd, false, (int)ti, &arr[i]);
-          mp.cfg[i] = c->cfg_d;
+          const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, false, true, units, &arr[i]);
+          cfg[i] = en.c->cfg_d;
           tasks += arr[i].n_tasks;
-          mp.task_end[i] = tasks;
+          ends[i] = tasks;
           slot_bytes = std::max(slot_bytes, z.slot_bytes);
         }
-        mp.queue = counters + e->mega_counter0 + 2 * ti;
-        mp.cls = reinterpret_cast<const SweepParams*>(dm + t.cls_tasks_off);
+        mp.cfg = reinterpret_cast<const int*>(dm + g.dt_cfg_off);
+        mp.task_end = reinterpret_cast<const int*>(dm + g.dt_end_off);
+        mp.cls = reinterpret_cast<const SweepParams*>(dm + g.dt_cls_off);
+        mp.queue = queue;
+        mp.image = dm + g.meta_off;
+        mp.image_bytes = g.bytes;
         Launch l;
         l.fn = mega_kernel(POL_D1, 0);
         l.threads = 8 * 32;
-        l.smem = smem_layout(8, t.bytes, slot_bytes, 8).total;
+        l.smem = smem_layout(8, g.bytes, slot_bytes, 8, (uint32_t)mp.n_classes).total;
         l.grid = std::min(e->num_sms, (tasks + 7) / 8);
         l.extra = slot_bytes;
         l.sweep = true;
         set_params(l, mp);
-        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_mega_tasks<VD1,8> (%d classes)", mp.n_classes);
+        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_mega_tasks<VD1,8> (%d class x tile entries)", mp.n_classes);
         if ((rc = push_launch(e, std::move(l)))) return rc;
       } else {
-        for (auto& c : e->classes) {
+        for (auto& en : entries) {
           SweepParams p;
-          const Sizing z = fill_params(e, c, t, c.kd, false, (int)ti, &p);
+          const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, false, false, 0, &p);
           Launch l;
-          l.fn = c.kd->fn_tasks;
-          l.threads = c.kd->warps * 32;
+          l.fn = en.c->kd->fn_tasks;
+          l.threads = en.c->kd->warps * 32;
           l.smem = z.smem;
           l.grid = z.grid;
           l.sweep = true;
           set_params(l, p);
-          snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<VD1,%d,%d,%d,%s>", c.kd->G, c.kd->K, c.kd->warps,
-                   c.multi ? "multi" : "single");
+          snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<VD1,%d,%d,%d,%s>", en.c->kd->G, en.c->kd->K,
+                   en.c->kd->warps, en.c->multi ? "multi" : "single");
           if ((rc = push_launch(e, std::move(l)))) return rc;
         }
       }
@@ -595,87 +673,100 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
     }
 
     // ---- fp32 forward sweep ----
-    std::vector<const ClassInst*> h2cls, other;
-    for (const ClassInst* c : order) (c->kf->policy == POL_H2 && !e->forced ? h2cls : other).push_back(c);
-    if (mega_ok && h2cls.size() > 1) {
-      std::vector<uint8_t> buf(sizeof(H2MegaParams), 0);
-      H2MegaParams& mp = *reinterpret_cast<H2MegaParams*>(buf.data());
-      fill_h2_common(e, t, &mp.com);
+    std::vector<Entry> h2, other;
+    for (auto& en : entries) (en.c->kf->policy == POL_H2 && !e->forced ? h2 : other).push_back(en);
+    if (mega_ok && h2.size() > 1) {
+      long long units = 0;
+      for (auto& en : h2) units += (long long)(en.c->n_rec / (32 / en.c->G)) * en.t->n_pairs;
+      H2MegaParams mp;
+      memset(&mp, 0, sizeof(mp));
+      fill_h2_common(e, dm + g.pmeta_off, g.pbytes, &mp.com);
+      H2Class* arr = reinterpret_cast<H2Class*>(hm + g.h2_cls_off);
+      int* cfg = reinterpret_cast<int*>(hm + g.h2_cfg_off);
+      int* ends = reinterpret_cast<int*>(hm + g.h2_end_off);
       int tasks = 0;
       uint32_t slot_bytes = 0;
-      for (const ClassInst* c : h2cls) {
+      for (auto& en : h2) {
         const int i = mp.n_classes++;
-        fill_h2_class(e, *c, t, kH2Warps, &mp.cls[i]);
-        mp.cfg[i] = c->cfg_f;
-        tasks += mp.cls[i].n_tasks;
-        mp.task_end[i] = tasks;
-        slot_bytes = std::max(slot_bytes, warp_slot_bytes(*c, c->kf, false));
+        fill_h2_class(e, *en.c, *en.t, kH2Warps, true, units, &arr[i]);
+        cfg[i] = en.c->cfg_f;
+        tasks += arr[i].n_tasks;
+        ends[i] = tasks;
+        slot_bytes = std::max(slot_bytes, warp_slot_bytes(*en.c, en.c->kf, false));
       }
       mp.com.slot_bytes = slot_bytes;
-      mp.queue = counters + e->mega_counter0 + 2 * ti;
+      mp.cfg = reinterpret_cast<const int*>(dm + g.h2_cfg_off);
+      mp.task_end = reinterpret_cast<const int*>(dm + g.h2_end_off);
+      mp.cls = reinterpret_cast<const H2Class*>(dm + g.h2_cls_off);
+      mp.queue = queue;
       Launch l;
       l.fn = h2_mega_kernel();
       l.threads = kH2Warps * 32;
-      l.smem = smem_layout(kH2Warps, t.pbytes, slot_bytes, 4).total;
+      l.smem = smem_layout(kH2Warps, g.pbytes, slot_bytes, 4, (uint32_t)mp.n_classes).total;
       l.grid = std::min(e->num_sms, (tasks + kH2Warps - 1) / kH2Warps);
       l.sweep = true;
-      snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_h2_mega<8> (%d classes)", mp.n_classes);
-      l.params.swap(buf);
+      set_params(l, mp);
+      snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_h2_mega<8> (%d class x tile entries, %d tiles)", mp.n_classes,
+               g.n_tiles);
       if ((rc = push_launch(e, std::move(l)))) return rc;
     } else {
-      for (const ClassInst* c : h2cls)
-        if ((rc = push_launch(e, h2_single_launch(e, *c, t, (int)ti)))) return rc;
+      for (auto& en : h2)
+        if ((rc = push_launch(e, h2_single_launch(e, *en.c, *en.t)))) return rc;
     }
-    for (const ClassInst* c : other) {  // multi-pass classes and forced measurement kernels: one launch each
-      if (c->kf->policy == POL_H2) {
-        if ((rc = push_launch(e, h2_single_launch(e, *c, t, (int)ti)))) return rc;
+    for (auto& en : other) {  // multi-pass classes and forced measurement kernels: one launch each
+      if (en.c->kf->policy == POL_H2) {
+        if ((rc = push_launch(e, h2_single_launch(e, *en.c, *en.t)))) return rc;
         continue;
       }
       SweepParams p;
-      const Sizing z = fill_params(e, *c, t, c->kf, false, (int)ti, &p);
+      const Sizing z = fill_params(e, *en.c, *en.t, en.c->kf, false, false, 0, &p);
       Launch l;
-      l.fn = c->kf->fn_tasks;
-      l.threads = c->kf->warps * 32;
+      l.fn = en.c->kf->fn_tasks;
+      l.threads = en.c->kf->warps * 32;
       l.smem = z.smem;
       l.grid = z.grid;
       l.sweep = true;
       set_params(l, p);
       if (!e->sweep_kernel[0] || e->forced)
-        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<pol%d,%d,%d,%d,%s,var%d>", c->kf->policy, c->G,
-                 c->K, c->kf->warps, c->multi ? "multi" : "single", c->kf->var);
+        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<pol%d,%d,%d,%d,%s,var%d>", en.c->kf->policy,
+                 en.c->G, en.c->K, en.c->kf->warps, en.c->multi ? "multi" : "single", en.c->kf->var);
       if ((rc = push_launch(e, std::move(l)))) return rc;
     }
 
     // ---- fp64 rerun of the flagged pairs ----
-    if (mega_ok && e->classes.size() > 1) {
+    if (mega_ok && entries.size() > 1) {
       MegaParams mp;
       memset(&mp, 0, sizeof(mp));
-      SweepParams* arr = reinterpret_cast<SweepParams*>(hm + t.cls_list_off);
+      SweepParams* arr = reinterpret_cast<SweepParams*>(hm + g.dl_cls_off);
+      int* cfg = reinterpret_cast<int*>(hm + g.dl_cfg_off);
       uint32_t slot_bytes = 0;
-      for (const ClassInst* c : order) {
+      for (auto& en : entries) {
         const int i = mp.n_classes++;
-        const Sizing z = fill_params(e, *c, t, c->kd, true, (int)ti, &arr[i]);
-        mp.cfg[i] = c->cfg_d;
+        const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, true, true, 0, &arr[i]);
+        cfg[i] = en.c->cfg_d;
         slot_bytes = std::max(slot_bytes, z.slot_bytes);
       }
-      mp.queue = counters + e->mega_counter0 + 2 * ti + 1;
-      mp.cls = reinterpret_cast<const SweepParams*>(dm + t.cls_list_off);
+      mp.cfg = reinterpret_cast<const int*>(dm + g.dl_cfg_off);
+      mp.cls = reinterpret_cast<const SweepParams*>(dm + g.dl_cls_off);
+      mp.queue = queue + 1;
+      mp.image = dm + g.meta_off;
+      mp.image_bytes = g.bytes;
       Launch l;
       l.fn = mega_kernel(POL_D1, 1);
       l.threads = 8 * 32;
-      l.smem = smem_layout(8, t.bytes, slot_bytes, 8).total;
+      l.smem = smem_layout(8, g.bytes, slot_bytes, 8, (uint32_t)mp.n_classes).total;
       l.grid = e->num_sms;
       l.extra = slot_bytes;
       set_params(l, mp);
       if ((rc = push_launch(e, std::move(l)))) return rc;
     } else {
-      for (auto& c : e->classes) {
-        if (c.kf->policy == POL_D1) continue;  // forced fp64 sweep: nothing to rerun
+      for (auto& en : entries) {
+        if (en.c->kf->policy == POL_D1) continue;  // forced fp64 sweep: nothing to rerun
         SweepParams p;
-        const Sizing z = fill_params(e, c, t, c.kd, true, (int)ti, &p);
+        const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, true, false, 0, &p);
         Launch l;
-        l.fn = c.kd->fn_list;
-        l.threads = c.kd->warps * 32;
+        l.fn = en.c->kd->fn_list;
+        l.threads = en.c->kd->warps * 32;
         l.smem = z.smem;
         l.grid = z.grid;
         set_params(l, p);
@@ -710,46 +801,76 @@ int validate_batch(const gklb_pairhmm_batch* b) {
   return GKLB_OK;
 }
 
-int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
-  if (e->pending_out)
+int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_on_device) {
+  if (!e->pending_out.empty())
     return fail(GKLB_ERR_STATE, "a submitted batch is still in flight on this engine: call gklb_engine_wait first");
   e->staged = false;
-  int rc = validate_batch(b);
-  if (rc) return rc;
+  if (k < 0 || (k > 0 && !batches)) return fail(GKLB_ERR_INVALID, "bad region array");
+  if (hap_on_device && k != 1) return fail(GKLB_ERR_INVALID, "device-resident staging takes one region");
+  int rc;
+  for (int r = 0; r < k; r++)
+    if ((rc = validate_batch(&batches[r]))) return rc;
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));  // the pinned staging buffers are about to be rewritten
-  e->n_reads = b->n_reads;
-  e->n_haps = b->n_haps;
   e->stats = gklb_pairhmm_stats{};
   e->plan.clear();
-  if (b->n_reads == 0 || b->n_haps == 0) {
-    e->classes.clear();
-    e->tiles.clear();
+  e->classes.clear();
+  e->tiles.clear();
+  e->groups.clear();
+  e->regions.assign((size_t)k, Region{});
+  // regions, in one job-wide numbering of reads, haplotypes and result slots; empty regions keep their slot
+  int64_t total_read = 0, total_hap = 0, total_pairs = 0, n_reads_all = 0, n_haps_all = 0;
+  for (int r = 0; r < k; r++) {
+    const gklb_pairhmm_batch& b = batches[r];
+    Region& reg = e->regions[r];
+    const bool empty = b.n_reads == 0 || b.n_haps == 0;
+    reg.n_reads = empty ? 0 : b.n_reads;
+    reg.n_haps = empty ? 0 : b.n_haps;
+    reg.read_base = (int)n_reads_all;
+    reg.arena_base = total_read;
+    reg.hap_base = (int)n_haps_all;
+    reg.hap_arena_base = total_hap;
+    reg.out_base = total_pairs;
+    if (empty) continue;
+    n_reads_all += b.n_reads;
+    n_haps_all += b.n_haps;
+    total_read += b.read_off[b.n_reads];
+    total_hap += b.hap_off[b.n_haps];
+    total_pairs += (int64_t)b.n_reads * b.n_haps;
+    e->stats.cells += b.read_off[b.n_reads] * b.hap_off[b.n_haps];
+    if (n_reads_all > 0x7fffffff || n_haps_all > 0x7fffffff) return fail(GKLB_ERR_INVALID, "job too large");
+  }
+  e->stats.pairs = total_pairs;
+  if (total_pairs == 0) {
     e->staged = true;
     return GKLB_OK;
   }
   if ((rc = parse_forced(e))) return rc;
-  const int64_t total_read = b->read_off[b->n_reads];
-  const int64_t total_hap = b->hap_off[b->n_haps];
-  e->stats.pairs = (int64_t)b->n_reads * b->n_haps;
-  e->stats.cells = total_read * total_hap;
 
   // the haplotype panel images are built on the host: fetch the bases if they live on the device
   std::vector<uint8_t> hap_host;
-  gklb_pairhmm_batch hb = *b;
+  std::vector<gklb_pairhmm_batch> hb(batches, batches + k);
   if (hap_on_device) {
     hap_host.resize((size_t)total_hap);
-    CU(cudaMemcpyAsync(hap_host.data(), b->hap_bases, (size_t)total_hap, cudaMemcpyDeviceToHost, e->stream));
+    CU(cudaMemcpyAsync(hap_host.data(), batches[0].hap_bases, (size_t)total_hap, cudaMemcpyDeviceToHost, e->stream));
     CU(cudaStreamSynchronize(e->stream));
-    hb.hap_bases = hap_host.data();
+    hb[0].hap_bases = hap_host.data();
   }
 
-  if ((rc = plan_classes(e, b))) return rc;
+  for (int r = 0; r < k; r++)
+    if (e->regions[r].n_reads && (rc = plan_classes(e, &batches[r], r, e->regions[r].read_base))) return rc;
+  const long long budget = image_budget(e);
+  for (int r = 0; r < k; r++)
+    if (e->regions[r].n_reads && (rc = plan_tiles(e, &hb[r], r, budget))) return rc;
   size_t meta_bytes = 0;
-  if ((rc = plan_tiles(e, &hb, &meta_bytes))) return rc;
+  plan_groups(e, budget, &meta_bytes);
+
+  std::vector<int> tiles_of_region((size_t)k, 0);
+  for (auto& t : e->tiles) tiles_of_region[t.region]++;
   size_t rec_bytes = 0, fb_items = 0, carry_bytes = 0;
   int counters = 0;
   for (auto& c : e->classes) {
+    const Region& reg = e->regions[c.region];
     c.meta_rid = meta_bytes;
     meta_bytes += align_up(sizeof(int32_t) * c.n_rec, 128);
     c.meta_len = meta_bytes;
@@ -757,12 +878,13 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
     c.rec_off = rec_bytes;
     rec_bytes += align_up((size_t)c.n_rec * 5 * c.stride, 128);
     c.fb_off = fb_items;
-    if (!e->use_double) fb_items += (size_t)c.n_rec * b->n_haps;
+    if (!e->use_double) fb_items += (size_t)c.n_rec * reg.n_haps;
     c.counter0 = counters;
-    counters += 1 + 2 * (int)e->tiles.size();
+    counters += 1 + 2 * tiles_of_region[c.region];
     if (c.multi) {
       int max_len = 0;
-      for (auto& t : e->tiles) max_len = std::max(max_len, t.max_len);
+      for (auto& t : e->tiles)
+        if (t.region == c.region) max_len = std::max(max_len, t.max_len);
       // per-warp scratch: sized for the widest CTA any kernel of this class may run with
       const int warps = std::max(12, std::max(c.kf->warps, c.kd->warps));
       c.carry_stride = (size_t)(32 / c.G) * 6 * (max_len + 2) * 8;
@@ -771,28 +893,31 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
     }
   }
   e->mega_counter0 = counters;
-  counters += 2 * (int)e->tiles.size();
+  counters += 2 * (int)e->groups.size();
   e->n_counters = counters;
 
-  // small host-resident batches: offsets + arenas are staged behind the meta block (see below)
+  // host-resident jobs of moderate size: offsets + arenas are staged behind the meta block -> one host->device copy
   e->arena_pitch = align_up((size_t)total_read, 256);
-  const bool consolidate = !hap_on_device && (size_t)total_read * 5 <= (4u << 20);
+  const bool consolidate = !hap_on_device && (k > 1 || (size_t)total_read * 5 <= (4u << 20));
+  const size_t off_bytes_r = sizeof(int64_t) * ((size_t)n_reads_all + 1), off_bytes_h = sizeof(int64_t) * ((size_t)n_haps_all + 1);
   size_t st_read_off = 0, st_hap_off = 0, st_arena = 0, staged_bytes = meta_bytes;
   if (consolidate) {
     st_read_off = staged_bytes;
-    staged_bytes += align_up(sizeof(int64_t) * ((size_t)b->n_reads + 1), 256);
+    staged_bytes += align_up(off_bytes_r, 256);
     st_hap_off = staged_bytes;
-    staged_bytes += align_up(sizeof(int64_t) * ((size_t)b->n_haps + 1), 256);
+    staged_bytes += align_up(off_bytes_h, 256);
     st_arena = staged_bytes;
     staged_bytes += 5 * e->arena_pitch;
   }
   CU(e->h_meta.ensure(staged_bytes));
   CU(e->d_meta.ensure(staged_bytes));
   CU(e->d_records.ensure(rec_bytes));
-  CU(e->d_read_off.ensure(sizeof(int64_t) * ((size_t)b->n_reads + 1)));
-  CU(e->d_hap_off.ensure(sizeof(int64_t) * ((size_t)b->n_haps + 1)));
-  if (!consolidate) CU(e->d_arenas.ensure(e->arena_pitch * 5));
-  CU(e->d_out.ensure(sizeof(double) * (size_t)e->stats.pairs));
+  if (!consolidate) {
+    CU(e->d_read_off.ensure(off_bytes_r));
+    CU(e->d_hap_off.ensure(off_bytes_h));
+    CU(e->d_arenas.ensure(e->arena_pitch * 5));
+  }
+  CU(e->d_out.ensure(sizeof(double) * (size_t)total_pairs));
   if (fb_items) CU(e->d_fb.ensure(sizeof(uint2) * fb_items));
   CU(e->d_counters.ensure(sizeof(unsigned int) * (size_t)counters));
   CU(e->h_counters.ensure(sizeof(unsigned int) * (size_t)counters));
@@ -800,8 +925,8 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
 
   uint8_t* hm = static_cast<uint8_t*>(e->h_meta.p);
   for (auto& t : e->tiles) {
-    build_tile_image(t, &hb, hm + t.meta_off);
-    build_pair_image(t, &hb, hm + t.pmeta_off);
+    build_tile_image(t, &hb[t.region], hm + t.meta_off);
+    build_pair_image(t, &hb[t.region], hm + t.pmeta_off);
   }
   for (auto& c : e->classes) {
     memcpy(hm + c.meta_rid, c.rid.data(), sizeof(int32_t) * c.n_rec);
@@ -810,22 +935,30 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device) {
   if ((rc = build_plan(e, hm))) return rc;  // every device buffer has its final address now
 
   cudaStream_t s = e->stream;
-  const size_t off_bytes_r = sizeof(int64_t) * ((size_t)b->n_reads + 1), off_bytes_h = sizeof(int64_t) * ((size_t)b->n_haps + 1);
-  const uint8_t* src[5] = {b->read_bases, b->read_quals, b->ins_gop, b->del_gop, b->gcp};
   uint8_t* dmw = static_cast<uint8_t*>(e->d_meta.p);
   if (consolidate) {
-    // small batch: offsets and arenas ride in the same pinned staging buffer -> one host->device copy
-    memcpy(hm + st_read_off, b->read_off, off_bytes_r);
-    memcpy(hm + st_hap_off, b->hap_off, off_bytes_h);
-    for (int i = 0; i < 5; i++) memcpy(hm + st_arena + i * e->arena_pitch, src[i], (size_t)total_read);
+    int64_t* ro = reinterpret_cast<int64_t*>(hm + st_read_off);
+    int64_t* ho = reinterpret_cast<int64_t*>(hm + st_hap_off);
+    for (int r = 0; r < k; r++) {
+      const Region& reg = e->regions[r];
+      if (!reg.n_reads) continue;
+      const gklb_pairhmm_batch& b = batches[r];
+      for (int i = 0; i <= b.n_reads; i++) ro[reg.read_base + i] = reg.arena_base + b.read_off[i];
+      for (int i = 0; i <= b.n_haps; i++) ho[reg.hap_base + i] = reg.hap_arena_base + b.hap_off[i];
+      const uint8_t* src[5] = {b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp};
+      for (int i = 0; i < 5; i++)
+        memcpy(hm + st_arena + i * e->arena_pitch + reg.arena_base, src[i], (size_t)b.read_off[b.n_reads]);
+    }
     CU(cudaMemcpyAsync(dmw, hm, staged_bytes, cudaMemcpyHostToDevice, s));
     e->p_read_off = reinterpret_cast<const int64_t*>(dmw + st_read_off);
     e->p_hap_off = reinterpret_cast<const int64_t*>(dmw + st_hap_off);
     e->p_arenas = dmw + st_arena;
-  } else {
+  } else {  // one large region: the arenas go straight from the caller's buffers (host or device)
+    const gklb_pairhmm_batch& b = batches[0];
     CU(cudaMemcpyAsync(dmw, hm, meta_bytes, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(e->d_read_off.p, b->read_off, off_bytes_r, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpyAsync(e->d_hap_off.p, b->hap_off, off_bytes_h, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->d_read_off.p, b.read_off, off_bytes_r, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(e->d_hap_off.p, b.hap_off, off_bytes_h, cudaMemcpyHostToDevice, s));
+    const uint8_t* src[5] = {b.read_bases, b.read_quals, b.ins_gop, b.del_gop, b.gcp};
     uint8_t* da = static_cast<uint8_t*>(e->d_arenas.p);
     for (int i = 0; i < 5; i++)
       CU(cudaMemcpyAsync(da + i * e->arena_pitch, src[i], (size_t)total_read, cudaMemcpyDefault, s));
@@ -890,35 +1023,52 @@ int do_run(gklb_engine* e) {
   return GKLB_OK;
 }
 
-int do_fetch(gklb_engine* e, double* out) {
+namespace {
+// The job's result buffer -> the callers' arrays, one per region.
+void scatter_results(gklb_engine* e, const uint8_t* host_src, double* const* outs) {
+  for (size_t r = 0; r < e->regions.size(); r++) {
+    const Region& reg = e->regions[r];
+    const size_t n = (size_t)reg.n_reads * reg.n_haps;
+    if (n) memcpy(outs[r], host_src + sizeof(double) * (size_t)reg.out_base, sizeof(double) * n);
+  }
+}
+}  // namespace
+
+int do_fetch(gklb_engine* e, double* const* outs) {
   if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
-  if (e->pending_out) return fail(GKLB_ERR_STATE, "a submitted batch is still in flight on this engine");
+  if (!e->pending_out.empty()) return fail(GKLB_ERR_STATE, "a submitted batch is still in flight on this engine");
   CU(cudaSetDevice(e->device));
   if (e->classes.empty()) return GKLB_OK;
-  if (!out) return fail(GKLB_ERR_INVALID, "likelihoods is null");
+  if (!outs) return fail(GKLB_ERR_INVALID, "likelihoods is null");
+  for (size_t r = 0; r < e->regions.size(); r++)
+    if (e->regions[r].n_reads && !outs[r]) return fail(GKLB_ERR_INVALID, "likelihoods is null");
   // Small results travel through the engine's pinned buffer: a device->host copy into the caller's (usually
   // pageable) array is staged by the driver and costs tens of microseconds more per call than the memcpy here.
   const size_t out_bytes = sizeof(double) * (size_t)e->stats.pairs;
-  const bool via_pinned = out_bytes <= ((size_t)2 << 20);
-  if (via_pinned) CU(e->h_out.ensure(out_bytes));
-  CU(cudaMemcpyAsync(via_pinned ? e->h_out.p : (void*)out, e->d_out.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  const bool via_pinned = e->regions.size() > 1 || out_bytes <= ((size_t)2 << 20);
+  if (via_pinned) {
+    CU(e->h_out.ensure(out_bytes));
+    CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  } else {
+    CU(cudaMemcpyAsync(outs[0], e->d_out.p, out_bytes, cudaMemcpyDeviceToHost, e->stream));
+  }
   CU(cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(unsigned int) * (size_t)e->n_counters,
                      cudaMemcpyDeviceToHost, e->stream));
   CU(cudaStreamSynchronize(e->stream));
-  if (via_pinned) memcpy(out, e->h_out.p, out_bytes);
+  if (via_pinned) scatter_results(e, static_cast<const uint8_t*>(e->h_out.p), outs);
   read_fallback_count(e);
   return GKLB_OK;
 }
 
-int do_compute(gklb_engine* e, const gklb_pairhmm_batch* b, double* out) {
+int do_compute(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs) {
   int rc;
   CU(cudaSetDevice(e->device));
   CU(cudaEventRecord(e->ev[0], e->stream));
-  if ((rc = do_stage(e, b, false))) return rc;
+  if ((rc = do_stage(e, batches, k, false))) return rc;
   CU(cudaEventRecord(e->ev[1], e->stream));
   if ((rc = do_run(e))) return rc;
   CU(cudaEventRecord(e->ev[2], e->stream));
-  if ((rc = do_fetch(e, out))) return rc;
+  if ((rc = do_fetch(e, outs))) return rc;
   CU(cudaEventRecord(e->ev[3], e->stream));
   CU(cudaEventSynchronize(e->ev[3]));
   cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]);
@@ -929,27 +1079,28 @@ int do_compute(gklb_engine* e, const gklb_pairhmm_batch* b, double* out) {
 
 // Asynchronous compute: everything is queued on the engine's stream and the likelihoods travel to a pinned
 // buffer (a device->host copy into pageable memory would block the host until the kernels are done).
-int do_submit(gklb_engine* e, const gklb_pairhmm_batch* b, double* out) {
+int do_submit(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs) {
   int rc;
-  if ((rc = do_stage(e, b, false))) return rc;  // refuses while a batch is in flight
+  if ((rc = do_stage(e, batches, k, false))) return rc;  // refuses while a job is in flight
   if ((rc = do_run(e))) return rc;
   if (e->classes.empty()) return GKLB_OK;
-  if (!out) return fail(GKLB_ERR_INVALID, "likelihoods is null");
+  if (!outs) return fail(GKLB_ERR_INVALID, "likelihoods is null");
+  for (int r = 0; r < k; r++)
+    if (e->regions[r].n_reads && !outs[r]) return fail(GKLB_ERR_INVALID, "likelihoods is null");
   CU(e->h_out.ensure(sizeof(double) * (size_t)e->stats.pairs));
   CU(cudaMemcpyAsync(e->h_out.p, e->d_out.p, sizeof(double) * (size_t)e->stats.pairs, cudaMemcpyDeviceToHost, e->stream));
   CU(cudaMemcpyAsync(e->h_counters.p, e->d_counters.p, sizeof(unsigned int) * (size_t)e->n_counters,
                      cudaMemcpyDeviceToHost, e->stream));
-  e->pending_out = out;
-  e->pending_pairs = e->stats.pairs;
+  e->pending_out.assign(outs, outs + k);
   return GKLB_OK;
 }
 
 int do_wait(gklb_engine* e) {
   CU(cudaSetDevice(e->device));
   CU(cudaStreamSynchronize(e->stream));
-  if (!e->pending_out) return GKLB_OK;
-  memcpy(e->pending_out, e->h_out.p, sizeof(double) * (size_t)e->pending_pairs);
-  e->pending_out = nullptr;
+  if (e->pending_out.empty()) return GKLB_OK;
+  scatter_results(e, static_cast<const uint8_t*>(e->h_out.p), e->pending_out.data());
+  e->pending_out.clear();
   read_fallback_count(e);
   return GKLB_OK;
 }
@@ -1025,14 +1176,22 @@ int gklb_engine_set_stream(gklb_engine* e, void* cuda_stream) {
 
 int gklb_engine_compute(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  if (!batch) return fail(GKLB_ERR_INVALID, "batch is null");
   std::lock_guard<std::mutex> lk(e->mu);
-  return do_compute(e, batch, likelihoods);
+  return do_compute(e, batch, 1, &likelihoods);
+}
+
+int gklb_engine_compute_multi(gklb_engine* e, const gklb_pairhmm_batch* batches, int n_batches, double* const* likelihoods) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_compute(e, batches, n_batches, likelihoods);
 }
 
 int gklb_engine_submit(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  if (!batch) return fail(GKLB_ERR_INVALID, "batch is null");
   std::lock_guard<std::mutex> lk(e->mu);
-  return do_submit(e, batch, likelihoods);
+  return do_submit(e, batch, 1, &likelihoods);
 }
 
 int gklb_engine_wait(gklb_engine* e) {
@@ -1043,14 +1202,16 @@ int gklb_engine_wait(gklb_engine* e) {
 
 int gklb_engine_stage(gklb_engine* e, const gklb_pairhmm_batch* batch) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  if (!batch) return fail(GKLB_ERR_INVALID, "batch is null");
   std::lock_guard<std::mutex> lk(e->mu);
-  return do_stage(e, batch, false);
+  return do_stage(e, batch, 1, false);
 }
 
 int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  if (!batch) return fail(GKLB_ERR_INVALID, "batch is null");
   std::lock_guard<std::mutex> lk(e->mu);
-  return do_stage(e, batch, true);
+  return do_stage(e, batch, 1, true);
 }
 
 int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_bases_dev) {
@@ -1058,6 +1219,7 @@ int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_bases_dev) {
   std::lock_guard<std::mutex> lk(e->mu);
   if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
   CU(cudaSetDevice(e->device));
+  if (e->regions.size() != 1) return fail(GKLB_ERR_STATE, "the staged job must have one region");
   uint8_t* dm = static_cast<uint8_t*>(e->d_meta.p);
   for (auto& t : e->tiles) {
     CU(launch_fill_panel(dm + t.meta_off, t.n, t.hap0, e->p_hap_off, static_cast<const uint8_t*>(hap_bases_dev), e->stream));
@@ -1076,7 +1238,8 @@ int gklb_engine_run(gklb_engine* e) {
 int gklb_engine_fetch(gklb_engine* e, double* likelihoods) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
   std::lock_guard<std::mutex> lk(e->mu);
-  return do_fetch(e, likelihoods);
+  if (e->regions.size() > 1) return fail(GKLB_ERR_STATE, "the staged job has several regions: use gklb_engine_compute_multi");
+  return do_fetch(e, &likelihoods);
 }
 
 int gklb_engine_result_device(gklb_engine* e, void** dev_ptr) {

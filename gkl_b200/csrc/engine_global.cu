@@ -221,7 +221,7 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
     if ((rc = acquire(-1, &e))) return rc;
     {
       std::lock_guard<std::mutex> lk(e->mu);
-      rc = do_compute(e, batch, likelihoods);
+      rc = do_compute(e, batch, 1, &likelihoods);
     }
     {
       std::lock_guard<std::mutex> lk(g_mu);
@@ -281,7 +281,8 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
       th.emplace_back([&, g] {
         if (sub[g].n_reads == 0) return;
         std::lock_guard<std::mutex> lk(engines[g]->mu);
-        rcs[g] = do_compute(engines[g], &sub[g], likelihoods + (size_t)cut[g] * batch->n_haps);
+        double* slab = likelihoods + (size_t)cut[g] * batch->n_haps;
+        rcs[g] = do_compute(engines[g], &sub[g], 1, &slab);
         if (rcs[g]) errs[g] = last_error_string();  // the last error is thread-local: carry it to the caller's thread
       });
     }
@@ -304,6 +305,32 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
     std::lock_guard<std::mutex> lk(g_mu);
     g_last_stats = total_stats;
   }
+  return rc;
+}
+
+// Several regions (active regions of HaplotypeCaller) in one call: the caller-side coalescing of SURVEY.md 8(f) N2.
+// All regions are staged with one host->device copy and served by launches that pull from one task queue per
+// launch group (engine.cu: plan_groups), so that a dozen small regions fill the GPU like one large batch;
+// likelihoods[r] receives region r's matrix.  Results are bit-identical to one gklb_pairhmm_compute per region.
+int gklb_pairhmm_compute_multi(const gklb_pairhmm_batch* batches, int n_batches, double* const* likelihoods) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_inited) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
+  }
+  if (n_batches < 0 || (n_batches > 0 && (!batches || !likelihoods))) return fail(GKLB_ERR_INVALID, "bad region array");
+  if (n_batches == 0) return GKLB_OK;
+  gklb_engine* e = nullptr;
+  int rc = acquire(-1, &e);
+  if (rc) return rc;
+  {
+    std::lock_guard<std::mutex> lk(e->mu);
+    rc = do_compute(e, batches, n_batches, likelihoods);
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_last_stats = e->stats;
+  }
+  release(e);
   return rc;
 }
 

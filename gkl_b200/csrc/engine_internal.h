@@ -42,15 +42,27 @@ struct HostBuf {  // pinned
   void release();
 };
 
-// One length class of a staged batch: its reads, packed as records of `rows` rows, and the kernels that serve it.
+// One region of a staged job: one read x haplotype batch (one active region of HaplotypeCaller = one
+// computeLikelihoods call).  A job is one or several regions that share the launches.
+struct Region {
+  int n_reads = 0, n_haps = 0;
+  int read_base = 0;        // index of the region's first read in the job's global read numbering
+  int64_t arena_base = 0;   // byte offset of its reads in the job's arenas
+  int hap_base = 0;         // index of its first haplotype in the job's global haplotype offsets
+  int64_t hap_arena_base = 0;
+  int64_t out_base = 0;     // offset of its likelihoods (doubles) in the job's result buffer
+};
+
+// One length class of one region: its reads, packed as records of `rows` rows, and the kernels that serve it.
 struct ClassInst {
+  int region = 0;
   int G = 0, K = 0, n_pass = 1, rows = 0, stride = 0;
   bool multi = false;
   const KernelEntry* kf = nullptr;  // forward sweep: H2 (fp32, single pass), F2 multi-pass, or fp64 tasks in use_double mode
   const KernelEntry* kd = nullptr;  // fp64: rerun-list kernel (and task kernel in use_double mode)
   int cfg_f = -1;                   // configuration index in the H2 multi-class kernel
   int cfg_d = -1;                   // configuration index in the fp64 multi-class kernels
-  std::vector<int32_t> rid, len;    // record order
+  std::vector<int32_t> rid, len;    // record order; rid is the read's index in the job
   int n_rec = 0;
   size_t meta_rid = 0, meta_len = 0;  // offsets into the meta block
   size_t rec_off = 0;                 // into d_records
@@ -59,17 +71,29 @@ struct ClassInst {
   int counter0 = 0;  // index of this class's first counter (rerun count), then per tile: task counter, list counter
 };
 
+// A tile: as many haplotypes of one region as fit in shared memory beside the record slots, as two images.
 struct Tile {
-  int hap0 = 0, n = 0, max_len = 0;
-  size_t meta_off = 0;
-  uint32_t bytes = 0;
+  int region = 0, index_in_region = 0;
+  int hap0 = 0, n = 0, max_len = 0;  // haplotypes [hap0, hap0 + n) of the region
+  size_t meta_off = 0;               // per-haplotype image (fp64 and multi-pass kernels)
+  uint32_t bytes = 0, img_off = 0;   // ... its size and its offset inside the group's resident image
   // the same haplotypes as a pair image (pairhmm_h2.cuh): sorted by length, two per byte column
   int n_pairs = 0;
   size_t pmeta_off = 0;
-  uint32_t pbytes = 0;
-  std::vector<int> order;  // haplotype indices by decreasing length; pair q = order[2q], order[2q+1]
-  size_t cls_list_off = 0;   // meta offset of the SweepParams array of the multi-class rerun launch
-  size_t cls_tasks_off = 0;  // ... and of the multi-class fp64 task launch (use_double)
+  uint32_t pbytes = 0, pimg_off = 0;
+  std::vector<int> order;  // haplotype indices (in the region) by decreasing length; pair q = order[2q], order[2q+1]
+};
+
+// A launch group: consecutive tiles (of one or several regions) whose images are resident together, so that one
+// multi-class launch serves all of them from a single task queue.
+struct Group {
+  int tile0 = 0, n_tiles = 0;
+  size_t meta_off = 0, pmeta_off = 0;  // start of the group's contiguous per-haplotype / pair images in the meta block
+  uint32_t bytes = 0, pbytes = 0;
+  int n_entries = 0;                   // (class, tile) pairs
+  size_t h2_cls_off = 0, h2_cfg_off = 0, h2_end_off = 0;      // device-resident arrays of the multi-class launches
+  size_t dl_cls_off = 0, dl_cfg_off = 0;                       //   fp64 rerun list
+  size_t dt_cls_off = 0, dt_cfg_off = 0, dt_end_off = 0;      //   fp64 tasks (use_double)
 };
 
 // One kernel launch of the staged batch's plan (built once per stage, replayed by every run).
@@ -79,9 +103,7 @@ struct Launch {
   size_t smem = 0;
   std::vector<uint8_t> params;   // the kernel's single by-value parameter struct
   uint32_t extra = 0;            // second parameter of the multi-class fp64 kernels (slot bytes)
-  bool has_extra = false;
   bool sweep = false;            // a forward-sweep launch: bracketed by events, counted in stats.sweep_ms
-  const char* name = "";
 };
 
 }  // namespace gklb
@@ -100,20 +122,20 @@ struct gklb_engine {
   const double *d_ph2pr_d = nullptr, *d_mm_d = nullptr;
   // staged batch
   bool staged = false;
-  int n_reads = 0, n_haps = 0;
+  std::vector<gklb::Region> regions;
   std::vector<gklb::ClassInst> classes;
   std::vector<gklb::Tile> tiles;
+  std::vector<gklb::Group> groups;
   std::vector<gklb::Launch> plan;
   gklb::DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
   gklb::HostBuf h_meta, h_counters, h_out;
-  double* pending_out = nullptr;  // destination of the batch submitted with gklb_engine_submit, until gklb_engine_wait
-  int64_t pending_pairs = 0;
+  std::vector<double*> pending_out;  // destinations of the job submitted with gklb_engine_submit, until gklb_engine_wait
   size_t arena_pitch = 0;
   const int64_t* p_read_off = nullptr;  // where the staged offsets / arenas live on the device
   const int64_t* p_hap_off = nullptr;
   const uint8_t* p_arenas = nullptr;
   int n_counters = 0;
-  int mega_counter0 = 0;  // first of the per-tile unified queue counters
+  int mega_counter0 = 0;  // first of the per-group unified queue counters (two per group)
   gklb_pairhmm_stats stats{};
   char sweep_kernel[96] = {0};  // name of the (last) forward-sweep kernel of the plan
   // forced kernel (measurement): policy,G,K,warps,var
@@ -127,11 +149,12 @@ namespace gklb {
 int create_engine(gklb_engine** out, int device, int use_double);
 void destroy_engine(gklb_engine* e);
 int validate_batch(const gklb_pairhmm_batch* b);
-int do_stage(gklb_engine* e, const gklb_pairhmm_batch* b, bool hap_on_device);
+// A job is k regions (k >= 1); outs[r] receives region r's likelihoods (double[n_reads * n_haps], read-major).
+int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_on_device);
 int do_run(gklb_engine* e);
-int do_fetch(gklb_engine* e, double* out);
-int do_compute(gklb_engine* e, const gklb_pairhmm_batch* b, double* out);
-int do_submit(gklb_engine* e, const gklb_pairhmm_batch* b, double* out);
+int do_fetch(gklb_engine* e, double* const* outs);
+int do_compute(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs);
+int do_submit(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs);
 int do_wait(gklb_engine* e);
 
 }  // namespace gklb

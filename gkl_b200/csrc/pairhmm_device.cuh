@@ -145,8 +145,9 @@ struct PanelRef {          // one haplotype tile, as an image that is bulk-copie
   uint32_t bytes;          //   int32 hlen[n]
   int n_haps;              //   pad to 16, then per haplotype: left margin | nibbles | right margin
   int hap0;                // index of the tile's first haplotype in the batch
-  int n_haps_total;        // H of the batch (row pitch of the output)
+  int n_haps_total;        // H of the tile's region (row pitch of its output)
   int max_hap_len;         // longest haplotype in the tile
+  uint32_t smem_off;       // where this image sits inside the CTA's resident image (multi-panel launches; else 0)
 };
 
 struct ClassRef {          // the reads of one length class, packed by k_pack_reads
@@ -681,17 +682,19 @@ __device__ __forceinline__ bool finish_pair(typename P::S sum, double log10_init
 // Shared memory layout of the sweep kernels.
 struct SmemLayout {
   uint32_t bars;     // offset of mbarriers: [0] panel, [1 + w] slot of warp w
+  uint32_t ends;     // int[n_ends]: exclusive task prefix of the classes of a multi-class launch
   uint32_t ph2pr;    // S[128]
-  uint32_t panel;    // panel image
+  uint32_t panel;    // panel image(s)
   uint32_t slots;    // per-warp record slots
   uint32_t slot_bytes;
   uint32_t total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int warps, uint32_t panel_bytes, uint32_t slot_bytes,
-                                                  uint32_t scalar_bytes) {
+                                                  uint32_t scalar_bytes, uint32_t n_ends = 0) {
   SmemLayout l;
   l.bars = 0;
-  l.ph2pr = (uint32_t)((8 * (1 + warps) + 127) / 128 * 128);
+  l.ends = (uint32_t)((8 * (1 + warps) + 15) / 16 * 16);
+  l.ph2pr = (uint32_t)((l.ends + 4 * n_ends + 127) / 128 * 128);
   l.panel = l.ph2pr + 128 * scalar_bytes;
   l.slots = (l.panel + panel_bytes + 127) / 128 * 128;
   l.slot_bytes = (slot_bytes + 127) / 128 * 128;
@@ -708,17 +711,27 @@ struct WarpCtx {
   uint32_t slot_parity;
   uint8_t* slot;           // this warp's record slot
   const S* ph2pr_s;
-  const uint8_t* panel_s;
+  const uint8_t* image_s;  // the CTA's resident image (one panel, or the panels of a multi-region launch)
+  int* ends_s;             // multi-class launches: exclusive task prefix per class
+  const uint8_t* panel_s;  // the panel the current task works on
   const int32_t* hpos;
   const int32_t* hlen;
   int warp, lane;
   size_t warp_global;      // index of this warp in the grid
 };
 
+// Point a warp at one panel of the resident image.
 template <class S>
-__device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const PanelRef& panel, const void* ph2pr, int warps,
-                                                uint32_t slot_bytes) {
-  const SmemLayout lay = smem_layout(warps, panel.bytes, slot_bytes, sizeof(S));
+__device__ __forceinline__ void bind_panel(WarpCtx<S>& c, const uint8_t* image_s, const PanelRef& panel) {
+  c.panel_s = image_s + panel.smem_off;
+  c.hpos = reinterpret_cast<const int32_t*>(c.panel_s);
+  c.hlen = c.hpos + panel.n_haps;
+}
+
+template <class S>
+__device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const uint8_t* image, uint32_t image_bytes, const void* ph2pr,
+                                                int warps, uint32_t slot_bytes, uint32_t n_ends = 0) {
+  const SmemLayout lay = smem_layout(warps, image_bytes, slot_bytes, sizeof(S), n_ends);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
   S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
   if (threadIdx.x == 0) {
@@ -728,8 +741,8 @@ __device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const PanelRef& p
   for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = reinterpret_cast<const S*>(ph2pr)[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], panel.bytes);
-    tma_bulk_g2s(smem + lay.panel, panel.image, panel.bytes, &bars[0]);
+    mbar_expect_tx(&bars[0], image_bytes);
+    tma_bulk_g2s(smem + lay.panel, image, image_bytes, &bars[0]);
   }
   mbar_wait(&bars[0], 0);
   WarpCtx<S> c;
@@ -739,11 +752,23 @@ __device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const PanelRef& p
   c.slot_parity = 0;
   c.slot = smem + lay.slots + (size_t)c.warp * lay.slot_bytes;
   c.ph2pr_s = ph2pr_s;
-  c.panel_s = smem + lay.panel;
-  c.hpos = reinterpret_cast<const int32_t*>(c.panel_s);
-  c.hlen = c.hpos + panel.n_haps;
+  c.image_s = smem + lay.panel;
+  c.ends_s = reinterpret_cast<int*>(smem + lay.ends);
+  c.panel_s = c.image_s;
+  c.hpos = nullptr;
+  c.hlen = nullptr;
   c.warp_global = (size_t)blockIdx.x * warps + c.warp;
   return c;
+}
+
+// Class of a task in a multi-class queue: first c with task < ends[c] (ends is an exclusive prefix in shared memory).
+__device__ __forceinline__ int class_of_task(const int* ends, int n, unsigned int task) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (task < (unsigned)ends[mid]) hi = mid; else lo = mid + 1;
+  }
+  return lo;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -910,7 +935,8 @@ template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams p) {
   typedef typename P::S S;
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, p.slot_bytes);
+  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel.image, p.panel.bytes, p.ph2pr, WARPS, p.slot_bytes);
+  bind_panel(ctx, ctx.image_s, p.panel);
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
@@ -927,7 +953,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
   extern __shared__ __align__(128) uint8_t smem[];
   const unsigned int n_items = *p.list_count;
   if (n_items == 0) return;
-  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel, p.ph2pr, WARPS, p.slot_bytes);
+  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel.image, p.panel.bytes, p.ph2pr, WARPS, p.slot_bytes);
+  bind_panel(ctx, ctx.image_s, p.panel);
   const unsigned int n_warp_items = (n_items + GPW - 1) / GPW;
   for (;;) {
     unsigned int wi = 0;
@@ -944,15 +971,17 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
 // configuration, so a HaplotypeCaller-shaped batch with a dozen length classes of ~25 reads each
 // fills the GPU with a single launch instead of a dozen serialised under-filled ones.
 // ------------------------------------------------------------------------------------------
-constexpr int kMaxMegaClasses = 32;
+constexpr int kMaxMegaClasses = 1024;  // (class, panel) entries of one multi-class launch
 constexpr int kCfgMulti = 13;  // configuration index of the multi-pass class (32 x 8 rows per pass)
 
 struct MegaParams {
   int n_classes;
-  int cfg[kMaxMegaClasses];        // index into the class table (G, K), kCfgMulti for multi-pass
-  int task_end[kMaxMegaClasses];   // exclusive prefix of tasks in the unified queue (task mode)
+  const int* cfg;                  // [n_classes] index into the class table (G, K), kCfgMulti for multi-pass   (device)
+  const int* task_end;             // [n_classes] exclusive prefix of tasks in the unified queue (task mode)    (device)
   unsigned int* queue;             // the unified work counter
-  const SweepParams* cls;          // [n_classes] in device memory (uploaded with the batch's meta block)
+  const SweepParams* cls;          // [n_classes] (device memory, uploaded with the batch's meta block)
+  const uint8_t* image;            // the panels of the launch, contiguous; each class's panel.smem_off points into it
+  uint32_t image_bytes;
 };
 
 // product variants: fp32 uses the W form, fp64 must not (2^1020 leaves no headroom for X / pMX).  With 12 warps
@@ -990,18 +1019,21 @@ template <class P, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_tasks(const __grid_constant__ MegaParams m, uint32_t slot_bytes) {
   typedef typename P::S S;
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtx<S> ctx = setup_cta<S>(smem, m.cls[0].panel, m.cls[0].ph2pr, WARPS, slot_bytes);
-  const unsigned int total = (unsigned)m.task_end[m.n_classes - 1];
+  WarpCtx<S> ctx = setup_cta<S>(smem, m.image, m.image_bytes, m.cls[0].ph2pr, WARPS, slot_bytes, (uint32_t)m.n_classes);
+  for (int i = threadIdx.x; i < m.n_classes; i += blockDim.x) ctx.ends_s[i] = m.task_end[i];
+  __syncthreads();
+  const unsigned int total = (unsigned)ctx.ends_s[m.n_classes - 1];
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(m.queue, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= total) break;
-    int c = 0;
-    while (task >= (unsigned)m.task_end[c]) c++;
-    const unsigned int local = task - (c ? (unsigned)m.task_end[c - 1] : 0u);
+    const int c = class_of_task(ctx.ends_s, m.n_classes, task);
+    const unsigned int local = task - (c ? (unsigned)ctx.ends_s[c - 1] : 0u);
     const int cfg = m.cfg[c];
-    GKLB_MEGA_DISPATCH(mega_task, m.cls[c], local, ctx)
+    const SweepParams& p = m.cls[c];
+    bind_panel(ctx, ctx.image_s, p.panel);
+    GKLB_MEGA_DISPATCH(mega_task, p, local, ctx)
   }
 }
 
@@ -1010,26 +1042,36 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_consta
   typedef typename P::S S;
   extern __shared__ __align__(128) uint8_t smem[];
   // warp-items per class follow from the list lengths the fp32 kernel left in device memory
-  unsigned int end[kMaxMegaClasses];
-  unsigned int total = 0;
-  for (int c = 0; c < m.n_classes; c++) {
-    const unsigned int gpw = (m.cfg[c] <= 4) ? 4u : (m.cfg[c] <= 8) ? 2u : 1u;
-    total += (*m.cls[c].list_count + gpw - 1) / gpw;
-    end[c] = total;
+  unsigned int total;
+  {
+    const SmemLayout lay = smem_layout(WARPS, m.image_bytes, slot_bytes, sizeof(S), (uint32_t)m.n_classes);
+    int* ends = reinterpret_cast<int*>(smem + lay.ends);
+    for (int c = threadIdx.x; c < m.n_classes; c += blockDim.x) {
+      const unsigned int gpw = (m.cfg[c] <= 4) ? 4u : (m.cfg[c] <= 8) ? 2u : 1u;
+      ends[c] = (int)((*m.cls[c].list_count + gpw - 1) / gpw);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned int t = 0;
+      for (int c = 0; c < m.n_classes; c++) { t += (unsigned)ends[c]; ends[c] = (int)t; }
+    }
+    __syncthreads();
+    total = (unsigned)ends[m.n_classes - 1];
   }
   if (total == 0) return;
-  WarpCtx<S> ctx = setup_cta<S>(smem, m.cls[0].panel, m.cls[0].ph2pr, WARPS, slot_bytes);
+  WarpCtx<S> ctx = setup_cta<S>(smem, m.image, m.image_bytes, m.cls[0].ph2pr, WARPS, slot_bytes, (uint32_t)m.n_classes);
   for (;;) {
     unsigned int wi = 0;
     if (ctx.lane == 0) wi = atomicAdd(m.queue, 1u);
     wi = __shfl_sync(0xffffffffu, wi, 0);
     if (wi >= total) break;
-    int c = 0;
-    while (wi >= end[c]) c++;
-    const unsigned int local = wi - (c ? end[c - 1] : 0u);
+    const int c = class_of_task(ctx.ends_s, m.n_classes, wi);
+    const unsigned int local = wi - (c ? (unsigned)ctx.ends_s[c - 1] : 0u);
     const int cfg = m.cfg[c];
-    const unsigned int n_items = *m.cls[c].list_count;
-    GKLB_MEGA_DISPATCH(mega_item, m.cls[c], local, n_items, ctx)
+    const SweepParams& p = m.cls[c];
+    const unsigned int n_items = *p.list_count;
+    bind_panel(ctx, ctx.image_s, p.panel);
+    GKLB_MEGA_DISPATCH(mega_item, p, local, n_items, ctx)
   }
 }
 

@@ -25,16 +25,15 @@
 
 namespace gklb {
 
-struct PairPanelRef {      // one haplotype tile as a pair image, bulk-copied to shared memory:
-  const uint8_t* image;    //   int32 ppos[n]   byte offset of column 0 of pair i inside the image
-  uint32_t bytes;          //   int32 lenA[n], lenB[n]   (lenA >= lenB)
-  int n_pairs;             //   int32 idxA[n], idxB[n]   haplotype index in the batch (idxB -1: B repeats A, drop it)
-  int n_haps_total;        //   pad to 16, then per pair: left margin | bytes | right margin
-  int max_hap_len;
-};
+// One haplotype tile as a pair image:
+//   int32 ppos[n]            byte offset of column 0 of pair i inside the image
+//   int32 lenA[n], lenB[n]   (lenA >= lenB)
+//   int32 idxA[n], idxB[n]   haplotype index in its region (idxB -1: B repeats A, drop it)
+//   pad to 16, then per pair: left margin | bytes | right margin
+// A launch keeps one image resident in shared memory: one tile, or the tiles of several regions back to back.
 
-struct H2Class {           // the reads of one length class (rows = G * K of its kernel), packed by k_pack_reads
-  const uint8_t* records;  // [n_rec][5 planes][stride]
+struct H2Class {           // the reads of one length class of one region against one tile of its haplotypes
+  const uint8_t* records;  // [n_rec][5 planes][stride]   (rows = G * K of the class kernel, packed by k_pack_reads)
   const int32_t* rec_rid;  // [n_rec] read index in the batch, -1 for filler records
   const int32_t* rec_len;  // [n_rec]
   uint2* fb_items;         // (record, haplotype) of pairs whose scaled sum is < 1e-28f or not finite
@@ -45,13 +44,17 @@ struct H2Class {           // the reads of one length class (rows = G * K of its
   int pair_chunk;          // haplotype pairs per task
   int n_chunks;
   int n_tasks;             // (n_rec / (32 / G)) * n_chunks
+  uint32_t panel_off;      // the tile's pair image inside the resident image
+  int n_pairs;
+  int n_haps_total;        // H of the region (row pitch of its output)
+  double* out;             // the region's likelihoods, biased so that out[rid * n_haps_total + h] is read rid's row
 };
 
 struct H2Common {
-  PairPanelRef panel;
+  const uint8_t* image;    // resident image (bulk-copied to shared memory once per CTA)
+  uint32_t image_bytes;
   const float* ph2pr;
   const float* mm;
-  double* out;
   float init_const;        // 2^120
   float log10_init;
   uint32_t slot_bytes;
@@ -63,16 +66,16 @@ struct H2Params {          // single-class launch
   unsigned int* task_counter;
 };
 
-// Multi-class launch: one queue that concatenates the classes' tasks, longest class first (see k_mega_tasks in
-// pairhmm_device.cuh for why).  cfg = gi * 9 + (K - 8) with G = 4 << gi.
-constexpr int kMaxH2Classes = 27;
+// Multi-class launch: one queue that concatenates the tasks of every (class, tile) entry, longest class first (see
+// k_mega_tasks in pairhmm_device.cuh for why); the entries may belong to different regions (several active regions
+// in one launch).  cfg = gi * 9 + (K - 8) with G = 4 << gi.  The arrays live in device memory (meta block).
 struct H2MegaParams {
   H2Common com;
   int n_classes;
   unsigned int* queue;
-  int cfg[kMaxH2Classes];
-  int task_end[kMaxH2Classes];
-  H2Class cls[kMaxH2Classes];
+  const int* cfg;
+  const int* task_end;
+  const H2Class* cls;
 };
 
 __device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
@@ -230,14 +233,14 @@ struct WarpCtxH2 {
   uint32_t slot_parity;
   uint8_t* slot;
   const float* ph2pr_s;
-  const uint8_t* panel_s;
-  const int32_t *ppos, *lenA, *lenB, *idxA, *idxB;
+  const uint8_t* image_s;
+  int* ends_s;
   int warp, lane;
 };
 
-__device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const PairPanelRef& panel, const float* ph2pr, int warps,
-                                                  uint32_t slot_bytes) {
-  const SmemLayout lay = smem_layout(warps, panel.bytes, slot_bytes, sizeof(float));
+__device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const H2Common& com, int warps, uint32_t n_ends = 0) {
+  const SmemLayout lay = smem_layout(warps, com.image_bytes, com.slot_bytes, sizeof(float), n_ends);
+  const float* ph2pr = com.ph2pr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
   float* ph2pr_s = reinterpret_cast<float*>(smem + lay.ph2pr);
   if (threadIdx.x == 0) {
@@ -247,8 +250,8 @@ __device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const PairPanel
   for (int i = threadIdx.x; i < 128; i += blockDim.x) ph2pr_s[i] = ph2pr[i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    mbar_expect_tx(&bars[0], panel.bytes);
-    tma_bulk_g2s(smem + lay.panel, panel.image, panel.bytes, &bars[0]);
+    mbar_expect_tx(&bars[0], com.image_bytes);
+    tma_bulk_g2s(smem + lay.panel, com.image, com.image_bytes, &bars[0]);
   }
   mbar_wait(&bars[0], 0);
   WarpCtxH2 c;
@@ -258,12 +261,8 @@ __device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const PairPanel
   c.slot_parity = 0;
   c.slot = smem + lay.slots + (size_t)c.warp * lay.slot_bytes;
   c.ph2pr_s = ph2pr_s;
-  c.panel_s = smem + lay.panel;
-  c.ppos = reinterpret_cast<const int32_t*>(c.panel_s);
-  c.lenA = c.ppos + panel.n_pairs;
-  c.lenB = c.lenA + panel.n_pairs;
-  c.idxA = c.lenB + panel.n_pairs;
-  c.idxB = c.idxA + panel.n_pairs;
+  c.image_s = smem + lay.panel;
+  c.ends_s = reinterpret_cast<int*>(smem + lay.ends);
   return c;
 }
 
@@ -292,10 +291,16 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
   LaneRowsH2<K> L;
   load_lane_rows_h2<K>(L, ctx.slot + (size_t)g * rec_bytes, cls.stride, cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
                        p.mm, tbs);
-  const int q_begin = chunk * cls.pair_chunk, q_end = min(p.panel.n_pairs, q_begin + cls.pair_chunk);
+  const uint8_t* panel_s = ctx.image_s + cls.panel_off;
+  const int32_t* ppos = reinterpret_cast<const int32_t*>(panel_s);
+  const int32_t* plenA = ppos + cls.n_pairs;
+  const int32_t* plenB = plenA + cls.n_pairs;
+  const int32_t* pidxA = plenB + cls.n_pairs;
+  const int32_t* pidxB = pidxA + cls.n_pairs;
+  const int q_begin = chunk * cls.pair_chunk, q_end = min(cls.n_pairs, q_begin + cls.pair_chunk);
   for (int q = q_begin; q < q_end; q++) {
-    const int lenA = ctx.lenA[q], lenB = ctx.lenB[q];
-    const uint8_t* hap = ctx.panel_s + ctx.ppos[q];
+    const int lenA = plenA[q], lenB = plenB[q];
+    const uint8_t* hap = panel_s + ppos[q];
     const float2 initY = make_float2(p.init_const / (float)lenA, p.init_const / (float)max(lenB, 1));
     SweeperH2<G, K> sw(L);
     // steps G..min(lenA, lenB) need no guard: every lane is inside both haplotypes
@@ -303,9 +308,9 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
     if (t == G - 1 && rid >= 0) {
 #pragma unroll
       for (int x = 0; x < 2; x++) {
-        const int h = x == 0 ? ctx.idxA[q] : ctx.idxB[q];
+        const int h = x == 0 ? pidxA[q] : pidxB[q];
         if (h < 0) continue;   // an odd haplotype out is paired with itself; its second result is dropped
-        double* o = p.out + (size_t)rid * p.panel.n_haps_total + h;
+        double* o = cls.out + (size_t)rid * cls.n_haps_total + h;
         if (!finish_pair<VF1>(x == 0 ? sum.x : sum.y, (double)p.log10_init, o)) {
           *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the rerun
           const unsigned int k = atomicAdd(cls.fb_count, 1u);
@@ -319,7 +324,7 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
 template <int G, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_h2_tasks(const __grid_constant__ H2Params p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtxH2 ctx = setup_cta_h2(smem, p.com.panel, p.com.ph2pr, WARPS, p.com.slot_bytes);
+  WarpCtxH2 ctx = setup_cta_h2(smem, p.com, WARPS);
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
@@ -335,29 +340,31 @@ __device__ __noinline__ void mega_task_h2(const H2Common& com, const H2Class& cl
 }
 
 #define GKLB_H2_ROW(G, B)                                                   \
-  case B + 0: mega_task_h2<G, 8>(m.com, m.cls[c], local, ctx); break;       \
-  case B + 1: mega_task_h2<G, 9>(m.com, m.cls[c], local, ctx); break;       \
-  case B + 2: mega_task_h2<G, 10>(m.com, m.cls[c], local, ctx); break;      \
-  case B + 3: mega_task_h2<G, 11>(m.com, m.cls[c], local, ctx); break;      \
-  case B + 4: mega_task_h2<G, 12>(m.com, m.cls[c], local, ctx); break;      \
-  case B + 5: mega_task_h2<G, 13>(m.com, m.cls[c], local, ctx); break;      \
-  case B + 6: mega_task_h2<G, 14>(m.com, m.cls[c], local, ctx); break;      \
-  case B + 7: mega_task_h2<G, 15>(m.com, m.cls[c], local, ctx); break;      \
-  case B + 8: mega_task_h2<G, 16>(m.com, m.cls[c], local, ctx); break;
+  case B + 0: mega_task_h2<G, 8>(m.com, cls, local, ctx); break;            \
+  case B + 1: mega_task_h2<G, 9>(m.com, cls, local, ctx); break;            \
+  case B + 2: mega_task_h2<G, 10>(m.com, cls, local, ctx); break;           \
+  case B + 3: mega_task_h2<G, 11>(m.com, cls, local, ctx); break;           \
+  case B + 4: mega_task_h2<G, 12>(m.com, cls, local, ctx); break;           \
+  case B + 5: mega_task_h2<G, 13>(m.com, cls, local, ctx); break;           \
+  case B + 6: mega_task_h2<G, 14>(m.com, cls, local, ctx); break;           \
+  case B + 7: mega_task_h2<G, 15>(m.com, cls, local, ctx); break;           \
+  case B + 8: mega_task_h2<G, 16>(m.com, cls, local, ctx); break;
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_h2_mega(const __grid_constant__ H2MegaParams m) {
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtxH2 ctx = setup_cta_h2(smem, m.com.panel, m.com.ph2pr, WARPS, m.com.slot_bytes);
-  const unsigned int total = (unsigned)m.task_end[m.n_classes - 1];
+  WarpCtxH2 ctx = setup_cta_h2(smem, m.com, WARPS, (uint32_t)m.n_classes);
+  for (int i = threadIdx.x; i < m.n_classes; i += blockDim.x) ctx.ends_s[i] = m.task_end[i];
+  __syncthreads();
+  const unsigned int total = (unsigned)ctx.ends_s[m.n_classes - 1];
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(m.queue, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= total) break;
-    int c = 0;
-    while (task >= (unsigned)m.task_end[c]) c++;
-    const unsigned int local = task - (c ? (unsigned)m.task_end[c - 1] : 0u);
+    const int c = class_of_task(ctx.ends_s, m.n_classes, task);
+    const unsigned int local = task - (c ? (unsigned)ctx.ends_s[c - 1] : 0u);
+    const H2Class& cls = m.cls[c];
     switch (m.cfg[c]) {
       GKLB_H2_ROW(4, 0)
       GKLB_H2_ROW(8, 9)

@@ -42,7 +42,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_pairhmm_devices_in_use",
            "gklb_pairhmm_last_stats", "gklb_pairhmm_engines_alive", "gklb_pairhmm_acquire_engine",
-           "gklb_pairhmm_release_engine", "gklb_engine_device", "gklb_engine_sweep_kernel", "gklb_engine_create",
+           "gklb_pairhmm_release_engine", "gklb_pairhmm_compute_multi", "gklb_engine_compute_multi", "gklb_engine_device", "gklb_engine_sweep_kernel", "gklb_engine_create",
            "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_submit", "gklb_engine_wait", "gklb_engine_stage",
            "gklb_engine_stage_device", "gklb_engine_update_haps_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
            "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
@@ -92,6 +92,8 @@ def lib() -> C.CDLL:
         l.gklb_engine_device.argtypes = [C.c_void_p]
         l.gklb_pairhmm_acquire_engine.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.gklb_pairhmm_release_engine.argtypes = [C.c_void_p]
+        l.gklb_pairhmm_compute_multi.argtypes = [C.POINTER(_Batch), C.c_int, C.POINTER(C.c_void_p)]
+        l.gklb_engine_compute_multi.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_int, C.POINTER(C.c_void_p)]
         _lib = l
     return _lib
 
@@ -168,6 +170,12 @@ class Engine:
         _check(lib().gklb_engine_compute(self._h, C.byref(s), out_ptr if out_ptr is not None else _ptr(out)))
         return out
 
+    def compute_multi(self, batches, outs=None):
+        """Several regions as one job (gklb_engine_compute_multi): returns the list of likelihood arrays."""
+        arr, ptrs, outs = _multi_args(batches, outs)
+        _check(lib().gklb_engine_compute_multi(self._h, arr, len(batches), ptrs))
+        return outs
+
     def submit(self, b: PairHmmBatch, out: np.ndarray) -> None:
         """Asynchronous compute: returns once everything is queued; `out` is filled by wait()."""
         b.validate()
@@ -221,6 +229,16 @@ class Engine:
         return lib().gklb_engine_sweep_kernel(self._h).decode()
 
 
+def _multi_args(batches, outs):
+    for b in batches:
+        b.validate()
+    if outs is None:
+        outs = [np.empty(b.n_reads * b.n_haps, dtype=np.float64) for b in batches]
+    arr = (_Batch * len(batches))(*[make_batch(b) for b in batches])
+    ptrs = (C.c_void_p * len(batches))(*[_ptr(o) if o.size else 0 for o in outs])
+    return arr, ptrs, outs
+
+
 def device_count() -> int:
     return int(lib().gklb_device_count())
 
@@ -238,6 +256,13 @@ def global_compute(b: PairHmmBatch, out: np.ndarray | None = None) -> np.ndarray
     s = make_batch(b)
     _check(lib().gklb_pairhmm_compute(C.byref(s), _ptr(out)))
     return out
+
+
+def global_compute_multi(batches, outs=None):
+    """gklb_pairhmm_compute_multi: several regions in one call; returns the list of likelihood arrays."""
+    arr, ptrs, outs = _multi_args(batches, outs)
+    _check(lib().gklb_pairhmm_compute_multi(arr, len(batches), ptrs))
+    return outs
 
 
 def global_stats() -> Stats:

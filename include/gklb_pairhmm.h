@@ -109,6 +109,14 @@ GKLB_API int gklb_pairhmm_init(int use_double, int max_threads);
  * direct | nccl, see engine_global.cu / engine_nccl.cu). */
 GKLB_API int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods);
 
+/* Several regions in one call (what a GATK-side queue that coalesces active regions would call;
+ * IntelPairHmm.computeLikelihoods is one synchronous call per region, IntelPairHmm.java:130-147).  All regions
+ * are staged with one host->device copy and share the launches: the tasks of every region of a launch group are
+ * pulled from one queue, so many small regions fill the GPU like one large batch.  likelihoods[r] receives
+ * region r's matrix (double[n_reads * n_haps]); results are bit-identical to one gklb_pairhmm_compute per region.
+ * Regions with no reads or no haplotypes are skipped. */
+GKLB_API int gklb_pairhmm_compute_multi(const gklb_pairhmm_batch* batches, int n_batches, double* const* likelihoods);
+
 /* doneNative.  Drops one reference; the last one frees the idle engines (device memory, streams, events).
  * Idempotent; a later compute creates engines again. */
 GKLB_API int gklb_pairhmm_done(void);
@@ -136,6 +144,8 @@ GKLB_API int gklb_engine_device(gklb_engine* e);
 GKLB_API int gklb_engine_set_stream(gklb_engine* e, void* cuda_stream);
 
 GKLB_API int gklb_engine_compute(gklb_engine* e, const gklb_pairhmm_batch* batch, double* likelihoods);
+GKLB_API int gklb_engine_compute_multi(gklb_engine* e, const gklb_pairhmm_batch* batches, int n_batches,
+                                       double* const* likelihoods);
 
 /* Asynchronous form of compute, for callers that have host work to overlap with the GPU (the JNI layer marshals
  * the next block of reads while the previous one is being computed):

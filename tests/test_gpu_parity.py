@@ -293,3 +293,63 @@ def test_in_process_multi_device_sharding(monkeypatch):
         assert native.global_stats().pairs == 50 * 64 and np.all(np.isfinite(small))
     finally:
         native.global_done()
+
+
+def test_multi_region_call_is_bit_identical_to_one_call_per_region(eng):
+    """gklb_engine_compute_multi: several active regions share the launches (one task queue per launch group);
+    every region's matrix must equal what a call of its own returns, bit for bit, and match the reference."""
+    regions = synth.config3(6, seed=11) + [synth.random_batch(61, 40, 9, low_quality=0.1, unrelated=0.4),
+                                           synth.random_batch(62, 7, 3, read_len=(1, 12), hap_len=(1, 12)),
+                                           synth.random_batch(63, 12, 5, read_len=(250, 600), hap_len=(300, 700))]
+    single = [eng.compute(r) for r in regions]
+    multi = eng.compute_multi(regions)
+    for r, a, m in zip(regions, single, multi):
+        assert np.array_equal(a, m)
+        ref = checker(r)
+        ok = np.isfinite(ref)
+        assert rel(m[ok], ref[ok]).max() <= REL_TOL
+    assert eng.stats().pairs == sum(r.n_reads * r.n_haps for r in regions)
+    # the engine stays usable for single calls, and empty regions keep their slot
+    empty = fixtures.PairHmmBatch.from_lists([], [], [], [], [], [b"ACGT"])
+    outs = eng.compute_multi([regions[0], empty, regions[1]])
+    assert np.array_equal(outs[0], single[0]) and outs[1].size == 0 and np.array_equal(outs[2], single[1])
+
+
+def test_multi_region_call_through_the_global_surface():
+    native.global_init(False, 1)
+    try:
+        regions = synth.config3(40, seed=12)   # more regions than fit one launch group
+        outs = native.global_compute_multi(regions)
+        one = native.Engine(0, False)
+        for r, o in zip(regions, outs):
+            assert np.array_equal(one.compute(r), o)
+        one.close()
+        st = native.global_stats()
+        assert st.pairs == sum(r.n_reads * r.n_haps for r in regions)
+    finally:
+        native.global_done()
+
+
+def test_quality_bytes_above_127_are_masked_like_the_reference(eng, eng_d):
+    """avx-pairhmm-template.h:134-136,149: every quality byte is used `& 127`; bytes with the high bit set must give
+    the same likelihoods as their low seven bits (checked against GKL's own code on the raw bytes)."""
+    b = synth.random_batch(71, 60, 12, low_quality=0.05)
+    rng = np.random.default_rng(72)
+    for a in (b.read_quals, b.ins_gop, b.del_gop, b.gcp):
+        hi = rng.random(a.size) < 0.3
+        a[hi] |= 0x80
+    for e, dbl, tol in ((eng, False, REL_TOL), (eng_d, True, 1e-9)):
+        out, ref = e.compute(b), checker(b, dbl)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(out), ok)
+        assert rel(out[ok], ref[ok]).max() <= tol
+
+
+def test_config4_shape_at_reduced_size_all_pairs(eng):
+    """BASELINE configs[3] (150-base reads x 256 haplotypes) at 4 000 reads: every pair against the reference."""
+    b = synth.config4(4000, 256)
+    out = eng.compute(b)
+    ref = checker(b)
+    assert np.array_equal(np.isfinite(out), np.isfinite(ref))
+    assert rel(out, ref).max() <= REL_TOL
+    assert eng.stats().fallback_pairs > 0
