@@ -1207,6 +1207,12 @@ int gklb_engine_stage(gklb_engine* e, const gklb_pairhmm_batch* batch) {
   return do_stage(e, batch, 1, false);
 }
 
+int gklb_engine_stage_multi(gklb_engine* e, const gklb_pairhmm_batch* batches, int n_batches) {
+  if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
+  std::lock_guard<std::mutex> lk(e->mu);
+  return do_stage(e, batches, n_batches, false);
+}
+
 int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch) {
   if (!e) return fail(GKLB_ERR_INVALID, "engine is null");
   if (!batch) return fail(GKLB_ERR_INVALID, "batch is null");
@@ -1273,6 +1279,21 @@ int gklb_engine_stats(gklb_engine* e, gklb_pairhmm_stats* out) {
 }
 
 const char* gklb_engine_sweep_kernel(gklb_engine* e) { return e ? e->sweep_kernel : ""; }
+
+// Text description of the staged job's plan (regions, classes, tiles, launch groups, launches), for reports.
+int gklb_engine_plan_info(gklb_engine* e, char* buf, int n) {
+  if (!e || !buf || n <= 0) return fail(GKLB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  int at = snprintf(buf, n, "regions=%zu classes=%zu tiles=%zu groups=%zu launches=%zu\n", e->regions.size(),
+                    e->classes.size(), e->tiles.size(), e->groups.size(), e->plan.size());
+  for (size_t i = 0; i < e->groups.size() && at < n; i++)
+    at += snprintf(buf + at, n - at, "group %zu: tiles=%d entries=%d image=%u pair_image=%u\n", i, e->groups[i].n_tiles,
+                   e->groups[i].n_entries, e->groups[i].bytes, e->groups[i].pbytes);
+  for (size_t i = 0; i < e->plan.size() && at < n; i++)
+    at += snprintf(buf + at, n - at, "launch %zu: grid=%d threads=%d smem=%zu%s\n", i, e->plan[i].grid, e->plan[i].threads,
+                   e->plan[i].smem, e->plan[i].sweep ? " sweep" : "");
+  return GKLB_OK;
+}
 
 int gklb_engine_time_runs(gklb_engine* e, int iters, float* ms_per_run) {
   if (!e || !ms_per_run || iters <= 0) return fail(GKLB_ERR_INVALID, "bad argument");

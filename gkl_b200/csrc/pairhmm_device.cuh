@@ -705,32 +705,32 @@ __host__ __device__ inline SmemLayout smem_layout(int warps, uint32_t panel_byte
 // ------------------------------------------------------------------------------------------
 // Per-CTA setup shared by all sweep kernels: mbarriers, ph2pr table, panel image (one TMA bulk copy).
 // ------------------------------------------------------------------------------------------
+// The context holds OFFSETS into the dynamic shared memory, not pointers: device functions rebuild their pointers
+// from the `extern __shared__` symbol so that the compiler keeps emitting LDS/STS (a generic pointer that crosses
+// the call boundary of the multi-class kernels' task functions turns every table and symbol load into a generic LD).
 template <class S>
 struct WarpCtx {
-  uint64_t* slot_bar;      // this warp's record-slot mbarrier
+  uint32_t slot_bar;       // offset of this warp's record-slot mbarrier
   uint32_t slot_parity;
-  uint8_t* slot;           // this warp's record slot
-  const S* ph2pr_s;
-  const uint8_t* image_s;  // the CTA's resident image (one panel, or the panels of a multi-region launch)
-  int* ends_s;             // multi-class launches: exclusive task prefix per class
-  const uint8_t* panel_s;  // the panel the current task works on
-  const int32_t* hpos;
-  const int32_t* hlen;
+  uint32_t slot;           // offset of this warp's record slot
+  uint32_t ph2pr;          // offset of S[128]
+  uint32_t image;          // offset of the CTA's resident image (one panel, or the panels of a multi-region launch)
+  uint32_t ends;           // offset of int[n_ends]: exclusive task prefix per class (multi-class launches)
+  uint32_t panel;          // offset of the panel the current task works on
   int warp, lane;
   size_t warp_global;      // index of this warp in the grid
 };
 
 // Point a warp at one panel of the resident image.
 template <class S>
-__device__ __forceinline__ void bind_panel(WarpCtx<S>& c, const uint8_t* image_s, const PanelRef& panel) {
-  c.panel_s = image_s + panel.smem_off;
-  c.hpos = reinterpret_cast<const int32_t*>(c.panel_s);
-  c.hlen = c.hpos + panel.n_haps;
+__device__ __forceinline__ void bind_panel(WarpCtx<S>& c, const PanelRef& panel) {
+  c.panel = c.image + panel.smem_off;
 }
 
 template <class S>
-__device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const uint8_t* image, uint32_t image_bytes, const void* ph2pr,
-                                                int warps, uint32_t slot_bytes, uint32_t n_ends = 0) {
+__device__ __forceinline__ WarpCtx<S> setup_cta(const uint8_t* image, uint32_t image_bytes, const void* ph2pr, int warps,
+                                                uint32_t slot_bytes, uint32_t n_ends = 0) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout lay = smem_layout(warps, image_bytes, slot_bytes, sizeof(S), n_ends);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
   S* ph2pr_s = reinterpret_cast<S*>(smem + lay.ph2pr);
@@ -748,15 +748,13 @@ __device__ __forceinline__ WarpCtx<S> setup_cta(uint8_t* smem, const uint8_t* im
   WarpCtx<S> c;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
-  c.slot_bar = &bars[1 + c.warp];
+  c.slot_bar = lay.bars + 8u * (1 + c.warp);
   c.slot_parity = 0;
-  c.slot = smem + lay.slots + (size_t)c.warp * lay.slot_bytes;
-  c.ph2pr_s = ph2pr_s;
-  c.image_s = smem + lay.panel;
-  c.ends_s = reinterpret_cast<int*>(smem + lay.ends);
-  c.panel_s = c.image_s;
-  c.hpos = nullptr;
-  c.hlen = nullptr;
+  c.slot = lay.slots + (uint32_t)c.warp * lay.slot_bytes;
+  c.ph2pr = lay.ph2pr;
+  c.image = lay.panel;
+  c.ends = lay.ends;
+  c.panel = lay.panel;
   c.warp_global = (size_t)blockIdx.x * warps + c.warp;
   return c;
 }
@@ -778,8 +776,15 @@ template <class P, int G, int K, bool MULTI, int VAR>
 __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
   typedef typename P::V V;
   typedef typename P::S S;
+  extern __shared__ __align__(128) uint8_t smem[];
   constexpr int GPW = 32 / G;           // groups per warp
   constexpr int RPW = GPW * P::NR;      // records per warp-task
+  uint8_t* const slot = smem + ctx.slot;
+  uint64_t* const slot_bar = reinterpret_cast<uint64_t*>(smem + ctx.slot_bar);
+  const S* const ph2pr_s = reinterpret_cast<const S*>(smem + ctx.ph2pr);
+  const uint8_t* const panel_s = smem + ctx.panel;
+  const int32_t* const hpos = reinterpret_cast<const int32_t*>(panel_s);
+  const int32_t* const hlen = hpos + p.panel.n_haps;
   const int lane = ctx.lane;
   const int t = lane % G, g = lane / G;
   const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
@@ -791,18 +796,17 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
   const int rec0 = blk * RPW;
   // VAR >= 3: the warp's prior table sits behind the record slot; lane-private column.  Multi-pass classes
   // (reads of thousands of rows) do not stage their records: the rows are read from global memory pass by pass.
-  V* tbv = reinterpret_cast<V*>(ctx.slot + (MULTI ? 0u : ((RPW * rec_bytes + 127u) & ~127u))) + lane;
+  V* tbv = reinterpret_cast<V*>(slot + (MULTI ? 0u : ((RPW * rec_bytes + 127u) & ~127u))) + lane;
   S* tbs = reinterpret_cast<S*>(tbv);
-  const uint8_t* recs = MULTI ? p.cls.records + (size_t)rec0 * rec_bytes : ctx.slot;
   if (!MULTI) {
     // stage the block's packed records into this warp's slot
     __syncwarp();
     if (lane == 0) {
       fence_proxy_async();
-      mbar_expect_tx(ctx.slot_bar, RPW * rec_bytes);
-      tma_bulk_g2s(ctx.slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, ctx.slot_bar);
+      mbar_expect_tx(slot_bar, RPW * rec_bytes);
+      tma_bulk_g2s(slot, p.cls.records + (size_t)rec0 * rec_bytes, RPW * rec_bytes, slot_bar);
     }
-    mbar_wait(ctx.slot_bar, ctx.slot_parity);
+    mbar_wait(slot_bar, ctx.slot_parity);
     ctx.slot_parity ^= 1;
   }
 
@@ -821,12 +825,12 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
   if (!MULTI) {
 #pragma unroll
     for (int x = 0; x < P::NR; x++)
-      load_lane_rows<P, K, VAR>(L, x, recs + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, krows, t * K,
-                                npad[x], t == 0, ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs, shift);
+      load_lane_rows<P, K, VAR>(L, x, slot + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, krows, t * K,
+                                npad[x], t == 0, ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs, shift);
   }
   for (int h = h_begin; h < h_end; h++) {
-    const int haplen = ctx.hlen[h];
-    const uint8_t* hap = ctx.panel_s + ctx.hpos[h];
+    const int haplen = hlen[h];
+    const uint8_t* hap = panel_s + hpos[h];
     const S initY = (S)p.init_const / (S)haplen;
     const int n_steps = haplen + G - 1;
     const int steady_end = haplen;
@@ -838,8 +842,8 @@ __device__ __forceinline__ void run_task(const SweepParams& p, unsigned int task
       for (int pass = 0; pass < p.cls.n_pass; pass++) {
 #pragma unroll
         for (int x = 0; x < P::NR; x++)
-          load_lane_rows<P, K, VAR>(L, x, recs + (size_t)(g * P::NR + x) * rec_bytes, p.cls.stride, p.cls.rows,
-                                    pass * cap + t * K, npad[x], t == 0 && pass == 0, ctx.ph2pr_s,
+          load_lane_rows<P, K, VAR>(L, x, p.cls.records + (size_t)(rec0 + g * P::NR + x) * rec_bytes, p.cls.stride,
+                                    p.cls.rows, pass * cap + t * K, npad[x], t == 0 && pass == 0, ph2pr_s,
                                     reinterpret_cast<const S*>(p.mm), tbs);
         V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
         V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
@@ -873,7 +877,12 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   typedef typename P::V V;
   typedef typename P::S S;
   static_assert(P::NR == 1, "list items carry one read per lane");
+  extern __shared__ __align__(128) uint8_t smem[];
   constexpr int GPW = 32 / G;
+  const S* const ph2pr_s = reinterpret_cast<const S*>(smem + ctx.ph2pr);
+  const uint8_t* const panel_s = smem + ctx.panel;
+  const int32_t* const hpos = reinterpret_cast<const int32_t*>(panel_s);
+  const int32_t* const hlen = hpos + p.panel.n_haps;
   const int lane = ctx.lane;
   const int t = lane % G, g = lane / G;
   const uint32_t rec_bytes = 5u * (uint32_t)p.cls.stride;
@@ -881,7 +890,7 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   const int carry_pitch = p.panel.max_hap_len + 2;
   V* carry = MULTI ? reinterpret_cast<V*>(reinterpret_cast<uint8_t*>(p.carry) + ctx.warp_global * p.carry_stride_bytes)
                    : nullptr;
-  V* tbv = reinterpret_cast<V*>(ctx.slot) + lane;  // VAR 3: the slot holds only the prior table here
+  V* tbv = reinterpret_cast<V*>(smem + ctx.slot) + lane;  // VAR 3: the slot holds only the prior table here
   S* tbs = reinterpret_cast<S*>(tbv);
   const unsigned int item = wi * GPW + g;
   const bool valid = item < n_items;
@@ -889,8 +898,8 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   const int h = (int)it.y - p.panel.hap0;
   const bool mine = valid && h >= 0 && h < p.panel.n_haps;  // items of other tiles are skipped
   const int rec = (int)it.x;
-  const int haplen = mine ? ctx.hlen[h] : 0;
-  const uint8_t* hap = ctx.panel_s + (mine ? ctx.hpos[h] : ctx.hpos[0]);
+  const int haplen = mine ? hlen[h] : 0;
+  const uint8_t* hap = panel_s + (mine ? hpos[h] : hpos[0]);
   const int krows = MULTI ? p.cls.rows : cap;
   const int shift = krows - p.cls.rows;
   const int rid = mine ? p.cls.rec_rid[rec] : -1;
@@ -907,14 +916,14 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
   LaneRows<P, K> L;
   V sum = P::splat(0);
   if (!MULTI) {
-    load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, krows, t * K, npad, t == 0, ctx.ph2pr_s,
+    load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, krows, t * K, npad, t == 0, ph2pr_s,
                               reinterpret_cast<const S*>(p.mm), tbs, shift);
     sum = sweep<P, G, K, false, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, true, nullptr, nullptr, 0, tbv);
   } else {
     V* cg = carry + (size_t)g * 6 * carry_pitch;
     for (int pass = 0; pass < p.cls.n_pass; pass++) {
       load_lane_rows<P, K, VAR>(L, 0, recp, p.cls.stride, p.cls.rows, pass * cap + t * K, npad, t == 0 && pass == 0,
-                                ctx.ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs);
+                                ph2pr_s, reinterpret_cast<const S*>(p.mm), tbs);
       V* cin = cg + (size_t)(pass & 1) * 3 * carry_pitch;
       V* cout = cg + (size_t)((pass + 1) & 1) * 3 * carry_pitch;
       sum = sweep<P, G, K, true, VAR>(L, hap, haplen, steady_end, n_steps, t, initY, pass == 0, cin,
@@ -934,9 +943,8 @@ __device__ __forceinline__ void run_list_item(const SweepParams& p, unsigned int
 template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_tasks(const SweepParams p) {
   typedef typename P::S S;
-  extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel.image, p.panel.bytes, p.ph2pr, WARPS, p.slot_bytes);
-  bind_panel(ctx, ctx.image_s, p.panel);
+  WarpCtx<S> ctx = setup_cta<S>(p.panel.image, p.panel.bytes, p.ph2pr, WARPS, p.slot_bytes);
+  bind_panel(ctx, p.panel);
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
@@ -950,11 +958,10 @@ template <class P, int G, int K, int WARPS, bool MULTI, int VAR>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams p) {
   typedef typename P::S S;
   constexpr int GPW = 32 / G;
-  extern __shared__ __align__(128) uint8_t smem[];
   const unsigned int n_items = *p.list_count;
   if (n_items == 0) return;
-  WarpCtx<S> ctx = setup_cta<S>(smem, p.panel.image, p.panel.bytes, p.ph2pr, WARPS, p.slot_bytes);
-  bind_panel(ctx, ctx.image_s, p.panel);
+  WarpCtx<S> ctx = setup_cta<S>(p.panel.image, p.panel.bytes, p.ph2pr, WARPS, p.slot_bytes);
+  bind_panel(ctx, p.panel);
   const unsigned int n_warp_items = (n_items + GPW - 1) / GPW;
   for (;;) {
     unsigned int wi = 0;
@@ -987,52 +994,57 @@ struct MegaParams {
 // product variants: fp32 uses the W form, fp64 must not (2^1020 leaves no headroom for X / pMX).  With 12 warps
 // per CTA (168 registers) the fp32 kernels drop the one-column-ahead prior prefetch (VAR 5); with 8 they keep it.
 template <class P, int WARPS> struct ProductVar { static constexpr int value = P::kDouble ? 3 : (WARPS >= 12 ? 5 : 4); };
+// The task functions of the multi-class kernels take the context by value (no pointer into the caller's frame) and
+// return the slot barrier's phase.
 template <class P, int G, int K, bool MULTI, int WARPS>
-__device__ __noinline__ void mega_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S>& ctx) {
+__device__ __noinline__ uint32_t mega_task(const SweepParams& p, unsigned int task, WarpCtx<typename P::S> ctx) {
   run_task<P, G, K, MULTI, ProductVar<P, WARPS>::value>(p, task, ctx);
+  return ctx.slot_parity;
 }
 template <class P, int G, int K, bool MULTI, int WARPS>
-__device__ __noinline__ void mega_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
-                                       WarpCtx<typename P::S>& ctx) {
+__device__ __noinline__ uint32_t mega_item(const SweepParams& p, unsigned int wi, unsigned int n_items,
+                                           WarpCtx<typename P::S> ctx) {
   run_list_item<P, G, K, MULTI, ProductVar<P, WARPS>::value>(p, wi, n_items, ctx);
+  return ctx.slot_parity;
 }
 
 #define GKLB_MEGA_DISPATCH(FN, ...)                                   \
   switch (cfg) {                                                      \
-    case 0: FN<P, 8, 4, false, WARPS>(__VA_ARGS__); break;                   \
-    case 1: FN<P, 8, 5, false, WARPS>(__VA_ARGS__); break;                   \
-    case 2: FN<P, 8, 6, false, WARPS>(__VA_ARGS__); break;                   \
-    case 3: FN<P, 8, 7, false, WARPS>(__VA_ARGS__); break;                   \
-    case 4: FN<P, 8, 8, false, WARPS>(__VA_ARGS__); break;                   \
-    case 5: FN<P, 16, 5, false, WARPS>(__VA_ARGS__); break;                  \
-    case 6: FN<P, 16, 6, false, WARPS>(__VA_ARGS__); break;                  \
-    case 7: FN<P, 16, 7, false, WARPS>(__VA_ARGS__); break;                  \
-    case 8: FN<P, 16, 8, false, WARPS>(__VA_ARGS__); break;                  \
-    case 9: FN<P, 32, 5, false, WARPS>(__VA_ARGS__); break;                  \
-    case 10: FN<P, 32, 6, false, WARPS>(__VA_ARGS__); break;                 \
-    case 11: FN<P, 32, 7, false, WARPS>(__VA_ARGS__); break;                 \
-    case 12: FN<P, 32, 8, false, WARPS>(__VA_ARGS__); break;                 \
-    default: FN<P, 32, 8, true, WARPS>(__VA_ARGS__); break;                  \
+    case 0: ctx.slot_parity = FN<P, 8, 4, false, WARPS>(__VA_ARGS__); break;                   \
+    case 1: ctx.slot_parity = FN<P, 8, 5, false, WARPS>(__VA_ARGS__); break;                   \
+    case 2: ctx.slot_parity = FN<P, 8, 6, false, WARPS>(__VA_ARGS__); break;                   \
+    case 3: ctx.slot_parity = FN<P, 8, 7, false, WARPS>(__VA_ARGS__); break;                   \
+    case 4: ctx.slot_parity = FN<P, 8, 8, false, WARPS>(__VA_ARGS__); break;                   \
+    case 5: ctx.slot_parity = FN<P, 16, 5, false, WARPS>(__VA_ARGS__); break;                  \
+    case 6: ctx.slot_parity = FN<P, 16, 6, false, WARPS>(__VA_ARGS__); break;                  \
+    case 7: ctx.slot_parity = FN<P, 16, 7, false, WARPS>(__VA_ARGS__); break;                  \
+    case 8: ctx.slot_parity = FN<P, 16, 8, false, WARPS>(__VA_ARGS__); break;                  \
+    case 9: ctx.slot_parity = FN<P, 32, 5, false, WARPS>(__VA_ARGS__); break;                  \
+    case 10: ctx.slot_parity = FN<P, 32, 6, false, WARPS>(__VA_ARGS__); break;                 \
+    case 11: ctx.slot_parity = FN<P, 32, 7, false, WARPS>(__VA_ARGS__); break;                 \
+    case 12: ctx.slot_parity = FN<P, 32, 8, false, WARPS>(__VA_ARGS__); break;                 \
+    default: ctx.slot_parity = FN<P, 32, 8, true, WARPS>(__VA_ARGS__); break;                  \
   }
 
 template <class P, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_tasks(const __grid_constant__ MegaParams m, uint32_t slot_bytes) {
   typedef typename P::S S;
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtx<S> ctx = setup_cta<S>(smem, m.image, m.image_bytes, m.cls[0].ph2pr, WARPS, slot_bytes, (uint32_t)m.n_classes);
-  for (int i = threadIdx.x; i < m.n_classes; i += blockDim.x) ctx.ends_s[i] = m.task_end[i];
+  WarpCtx<S> ctx = setup_cta<S>(m.image, m.image_bytes, m.cls[0].ph2pr, WARPS, slot_bytes, (uint32_t)m.n_classes);
+  int* const ends_s = reinterpret_cast<int*>(smem + ctx.ends);
+  for (int i = threadIdx.x; i < m.n_classes; i += blockDim.x) ends_s[i] = m.task_end[i];
   __syncthreads();
-  const unsigned int total = (unsigned)ctx.ends_s[m.n_classes - 1];
+  const unsigned int total = (unsigned)ends_s[m.n_classes - 1];
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(m.queue, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= total) break;
-    const int c = class_of_task(ctx.ends_s, m.n_classes, task);
-    const unsigned int local = task - (c ? (unsigned)ctx.ends_s[c - 1] : 0u);
+    const int c = class_of_task(ends_s, m.n_classes, task);
+    const unsigned int local = task - (c ? (unsigned)ends_s[c - 1] : 0u);
     const int cfg = m.cfg[c];
     const SweepParams& p = m.cls[c];
-    bind_panel(ctx, ctx.image_s, p.panel);
+    bind_panel(ctx, p.panel);
     GKLB_MEGA_DISPATCH(mega_task, p, local, ctx)
   }
 }
@@ -1059,18 +1071,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_mega_list(const __grid_consta
     total = (unsigned)ends[m.n_classes - 1];
   }
   if (total == 0) return;
-  WarpCtx<S> ctx = setup_cta<S>(smem, m.image, m.image_bytes, m.cls[0].ph2pr, WARPS, slot_bytes, (uint32_t)m.n_classes);
+  WarpCtx<S> ctx = setup_cta<S>(m.image, m.image_bytes, m.cls[0].ph2pr, WARPS, slot_bytes, (uint32_t)m.n_classes);
+  const int* const ends_s = reinterpret_cast<const int*>(smem + ctx.ends);
   for (;;) {
     unsigned int wi = 0;
     if (ctx.lane == 0) wi = atomicAdd(m.queue, 1u);
     wi = __shfl_sync(0xffffffffu, wi, 0);
     if (wi >= total) break;
-    const int c = class_of_task(ctx.ends_s, m.n_classes, wi);
-    const unsigned int local = wi - (c ? (unsigned)ctx.ends_s[c - 1] : 0u);
+    const int c = class_of_task(ends_s, m.n_classes, wi);
+    const unsigned int local = wi - (c ? (unsigned)ends_s[c - 1] : 0u);
     const int cfg = m.cfg[c];
     const SweepParams& p = m.cls[c];
     const unsigned int n_items = *p.list_count;
-    bind_panel(ctx, ctx.image_s, p.panel);
+    bind_panel(ctx, p.panel);
     GKLB_MEGA_DISPATCH(mega_item, p, local, n_items, ctx)
   }
 }

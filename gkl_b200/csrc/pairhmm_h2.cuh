@@ -227,18 +227,22 @@ struct SweeperH2 {
   }
 };
 
-// Per-CTA setup for the H2 kernels: mbarriers, ph2pr table, pair image (one TMA bulk copy).
+// Per-CTA setup for the H2 kernels: mbarriers, ph2pr table, resident image (one TMA bulk copy).  The context holds
+// OFFSETS into the dynamic shared memory, not pointers: device functions rebuild their pointers from the
+// `extern __shared__` symbol, so that the compiler keeps emitting LDS/STS (a generic pointer that crosses the call
+// boundary of the multi-class kernel's task functions turns every table load into a generic LD).
 struct WarpCtxH2 {
-  uint64_t* slot_bar;
+  uint32_t slot_bar;     // offset of this warp's record-slot mbarrier
   uint32_t slot_parity;
-  uint8_t* slot;
-  const float* ph2pr_s;
-  const uint8_t* image_s;
-  int* ends_s;
+  uint32_t slot;         // offset of this warp's slot (records, then the prior table)
+  uint32_t ph2pr;        // offset of float[128]
+  uint32_t image;        // offset of the resident image
+  uint32_t ends;         // offset of int[n_ends] (multi-class launches)
   int warp, lane;
 };
 
-__device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const H2Common& com, int warps, uint32_t n_ends = 0) {
+__device__ __forceinline__ WarpCtxH2 setup_cta_h2(const H2Common& com, int warps, uint32_t n_ends = 0) {
+  extern __shared__ __align__(128) uint8_t smem[];
   const SmemLayout lay = smem_layout(warps, com.image_bytes, com.slot_bytes, sizeof(float), n_ends);
   const float* ph2pr = com.ph2pr;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bars);
@@ -257,47 +261,52 @@ __device__ __forceinline__ WarpCtxH2 setup_cta_h2(uint8_t* smem, const H2Common&
   WarpCtxH2 c;
   c.warp = threadIdx.x >> 5;
   c.lane = threadIdx.x & 31;
-  c.slot_bar = &bars[1 + c.warp];
+  c.slot_bar = lay.bars + 8u * (1 + c.warp);
   c.slot_parity = 0;
-  c.slot = smem + lay.slots + (size_t)c.warp * lay.slot_bytes;
-  c.ph2pr_s = ph2pr_s;
-  c.image_s = smem + lay.panel;
-  c.ends_s = reinterpret_cast<int*>(smem + lay.ends);
+  c.slot = lay.slots + (uint32_t)c.warp * lay.slot_bytes;
+  c.ph2pr = lay.ph2pr;
+  c.image = lay.panel;
+  c.ends = lay.ends;
   return c;
 }
 
-// One task = (block of 32/G records) x (chunk of haplotype pairs), executed by one warp.
+// One task = (block of 32/G records) x (chunk of haplotype pairs), executed by one warp.  Flips ctx.slot_parity.
 template <int G, int K>
 __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cls, unsigned int task, WarpCtxH2& ctx) {
+  extern __shared__ __align__(128) uint8_t smem[];
   constexpr int GPW = 32 / G;
   const int lane = ctx.lane;
   const int t = lane % G, g = lane / G;
   const uint32_t rec_bytes = 5u * (uint32_t)cls.stride;
   const int blk = task / cls.n_chunks, chunk = task - blk * cls.n_chunks;
   const int rec0 = blk * GPW;
-  float* tbs = reinterpret_cast<float*>(ctx.slot + ((GPW * rec_bytes + 127u) & ~127u)) + lane;
+  uint8_t* slot = smem + ctx.slot;
+  uint64_t* slot_bar = reinterpret_cast<uint64_t*>(smem + ctx.slot_bar);
+  const float* ph2pr_s = reinterpret_cast<const float*>(smem + ctx.ph2pr);
+  float* tbs = reinterpret_cast<float*>(slot + ((GPW * rec_bytes + 127u) & ~127u)) + lane;
   __syncwarp();
   if (lane == 0) {
     fence_proxy_async();
-    mbar_expect_tx(ctx.slot_bar, GPW * rec_bytes);
-    tma_bulk_g2s(ctx.slot, cls.records + (size_t)rec0 * rec_bytes, GPW * rec_bytes, ctx.slot_bar);
+    mbar_expect_tx(slot_bar, GPW * rec_bytes);
+    tma_bulk_g2s(slot, cls.records + (size_t)rec0 * rec_bytes, GPW * rec_bytes, slot_bar);
   }
-  mbar_wait(ctx.slot_bar, ctx.slot_parity);
+  mbar_wait(slot_bar, ctx.slot_parity);
   ctx.slot_parity ^= 1;
 
   const int rec = rec0 + g;
   const int rid = cls.rec_rid[rec];
   const int npad = cls.rows - cls.rec_len[rec];
   LaneRowsH2<K> L;
-  load_lane_rows_h2<K>(L, ctx.slot + (size_t)g * rec_bytes, cls.stride, cls.rows, t * K, npad, t == 0, ctx.ph2pr_s,
-                       p.mm, tbs);
-  const uint8_t* panel_s = ctx.image_s + cls.panel_off;
+  load_lane_rows_h2<K>(L, slot + (size_t)g * rec_bytes, cls.stride, cls.rows, t * K, npad, t == 0, ph2pr_s, p.mm, tbs);
+  const uint8_t* panel_s = smem + ctx.image + cls.panel_off;
   const int32_t* ppos = reinterpret_cast<const int32_t*>(panel_s);
   const int32_t* plenA = ppos + cls.n_pairs;
   const int32_t* plenB = plenA + cls.n_pairs;
   const int32_t* pidxA = plenB + cls.n_pairs;
   const int32_t* pidxB = pidxA + cls.n_pairs;
   const int q_begin = chunk * cls.pair_chunk, q_end = min(cls.n_pairs, q_begin + cls.pair_chunk);
+  double* const out = cls.out;
+  const int n_haps_total = cls.n_haps_total;
   for (int q = q_begin; q < q_end; q++) {
     const int lenA = plenA[q], lenB = plenB[q];
     const uint8_t* hap = panel_s + ppos[q];
@@ -310,7 +319,7 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
       for (int x = 0; x < 2; x++) {
         const int h = x == 0 ? pidxA[q] : pidxB[q];
         if (h < 0) continue;   // an odd haplotype out is paired with itself; its second result is dropped
-        double* o = cls.out + (size_t)rid * cls.n_haps_total + h;
+        double* o = out + (size_t)rid * n_haps_total + h;
         if (!finish_pair<VF1>(x == 0 ? sum.x : sum.y, (double)p.log10_init, o)) {
           *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the rerun
           const unsigned int k = atomicAdd(cls.fb_count, 1u);
@@ -323,8 +332,7 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
 
 template <int G, int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_h2_tasks(const __grid_constant__ H2Params p) {
-  extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtxH2 ctx = setup_cta_h2(smem, p.com, WARPS);
+  WarpCtxH2 ctx = setup_cta_h2(p.com, WARPS);
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(p.task_counter, 1u);
@@ -334,43 +342,45 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_h2_tasks(const __grid_constan
   }
 }
 
+// The task functions of the multi-class kernel take everything by value (no pointer to the caller's frame).
 template <int G, int K>
-__device__ __noinline__ void mega_task_h2(const H2Common& com, const H2Class& cls, unsigned int task, WarpCtxH2& ctx) {
-  run_task_h2<G, K>(com, cls, task, ctx);
+__device__ __noinline__ void mega_task_h2(const H2MegaParams& m, int c, unsigned int task, WarpCtxH2 ctx) {
+  run_task_h2<G, K>(m.com, m.cls[c], task, ctx);
 }
 
-#define GKLB_H2_ROW(G, B)                                                   \
-  case B + 0: mega_task_h2<G, 8>(m.com, cls, local, ctx); break;            \
-  case B + 1: mega_task_h2<G, 9>(m.com, cls, local, ctx); break;            \
-  case B + 2: mega_task_h2<G, 10>(m.com, cls, local, ctx); break;           \
-  case B + 3: mega_task_h2<G, 11>(m.com, cls, local, ctx); break;           \
-  case B + 4: mega_task_h2<G, 12>(m.com, cls, local, ctx); break;           \
-  case B + 5: mega_task_h2<G, 13>(m.com, cls, local, ctx); break;           \
-  case B + 6: mega_task_h2<G, 14>(m.com, cls, local, ctx); break;           \
-  case B + 7: mega_task_h2<G, 15>(m.com, cls, local, ctx); break;           \
-  case B + 8: mega_task_h2<G, 16>(m.com, cls, local, ctx); break;
+#define GKLB_H2_ROW(G, B)                                           \
+  case B + 0: mega_task_h2<G, 8>(m, c, local, ctx); break;          \
+  case B + 1: mega_task_h2<G, 9>(m, c, local, ctx); break;          \
+  case B + 2: mega_task_h2<G, 10>(m, c, local, ctx); break;         \
+  case B + 3: mega_task_h2<G, 11>(m, c, local, ctx); break;         \
+  case B + 4: mega_task_h2<G, 12>(m, c, local, ctx); break;         \
+  case B + 5: mega_task_h2<G, 13>(m, c, local, ctx); break;         \
+  case B + 6: mega_task_h2<G, 14>(m, c, local, ctx); break;         \
+  case B + 7: mega_task_h2<G, 15>(m, c, local, ctx); break;         \
+  case B + 8: mega_task_h2<G, 16>(m, c, local, ctx); break;
 
 template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_h2_mega(const __grid_constant__ H2MegaParams m) {
   extern __shared__ __align__(128) uint8_t smem[];
-  WarpCtxH2 ctx = setup_cta_h2(smem, m.com, WARPS, (uint32_t)m.n_classes);
-  for (int i = threadIdx.x; i < m.n_classes; i += blockDim.x) ctx.ends_s[i] = m.task_end[i];
+  WarpCtxH2 ctx = setup_cta_h2(m.com, WARPS, (uint32_t)m.n_classes);
+  int* ends_s = reinterpret_cast<int*>(smem + ctx.ends);
+  for (int i = threadIdx.x; i < m.n_classes; i += blockDim.x) ends_s[i] = m.task_end[i];
   __syncthreads();
-  const unsigned int total = (unsigned)ctx.ends_s[m.n_classes - 1];
+  const unsigned int total = (unsigned)ends_s[m.n_classes - 1];
   for (;;) {
     unsigned int task = 0;
     if (ctx.lane == 0) task = atomicAdd(m.queue, 1u);
     task = __shfl_sync(0xffffffffu, task, 0);
     if (task >= total) break;
-    const int c = class_of_task(ctx.ends_s, m.n_classes, task);
-    const unsigned int local = task - (c ? (unsigned)ctx.ends_s[c - 1] : 0u);
-    const H2Class& cls = m.cls[c];
+    const int c = class_of_task(ends_s, m.n_classes, task);
+    const unsigned int local = task - (c ? (unsigned)ends_s[c - 1] : 0u);
     switch (m.cfg[c]) {
       GKLB_H2_ROW(4, 0)
       GKLB_H2_ROW(8, 9)
       GKLB_H2_ROW(16, 18)
       default: break;
     }
+    ctx.slot_parity ^= 1;  // every task waits once on the warp's slot barrier
   }
 }
 

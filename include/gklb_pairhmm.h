@@ -167,6 +167,7 @@ GKLB_API int gklb_engine_wait(gklb_engine* e);
  * run may be called repeatedly on one staged batch. */
 GKLB_API int gklb_engine_stage(gklb_engine* e, const gklb_pairhmm_batch* batch);
 GKLB_API int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch);
+GKLB_API int gklb_engine_stage_multi(gklb_engine* e, const gklb_pairhmm_batch* batches, int n_batches);
 /* Replace the haplotype bases of the staged batch by device-resident ones of the same lengths (e.g. the
  * buffer an NCCL broadcast just filled): the panel images are rewritten by a kernel on the engine's stream,
  * no host round trip.  [async] */
@@ -179,6 +180,8 @@ GKLB_API int gklb_engine_synchronize(gklb_engine* e);
 GKLB_API int gklb_engine_stats(gklb_engine* e, gklb_pairhmm_stats* out);
 /* Name of the forward-sweep kernel the staged batch's plan launches (for bench reports). */
 GKLB_API const char* gklb_engine_sweep_kernel(gklb_engine* e);
+/* Text description of the staged job's plan: regions, classes, tiles, launch groups, launches (grid, shared memory). */
+GKLB_API int gklb_engine_plan_info(gklb_engine* e, char* buf, int n);
 
 /* Time `iters` back-to-back runs of the staged batch with CUDA events recorded on the engine's
  * stream; returns the mean milliseconds per run in *ms_per_run. */
