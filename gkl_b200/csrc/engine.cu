@@ -25,6 +25,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 
 #include "engine_internal.h"
 #include "pairhmm_tables.h"
@@ -399,7 +400,21 @@ void plan_groups(gklb_engine* e, long long budget, size_t* meta_bytes) {
   }
 }
 
-void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) {
+// byte -> panel byte / symbol index (ConvertChar, pairhmm_common.h:49-67), tabulated: the images are built per call
+struct BaseLut {
+  uint8_t panel[256], index[256];
+  BaseLut() {
+    for (int i = 0; i < 256; i++) { panel[i] = panel_byte((uint8_t)i); index[i] = base_index((uint8_t)i); }
+  }
+};
+const BaseLut& base_lut() {
+  static const BaseLut lut;
+  return lut;
+}
+
+// fill = false: header (positions, lengths) only; the bases are written on the device later
+void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img, bool fill) {
+  const uint8_t* lut = base_lut().panel;
   memset(img, 0, t.bytes);
   int32_t* hpos = reinterpret_cast<int32_t*>(img);
   int32_t* hlen = hpos + t.n;
@@ -411,12 +426,14 @@ void build_tile_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) 
     hpos[i] = (int32_t)(off + kHapLeftMargin - 1);  // column 0; column c is at hpos + c
     hlen[i] = len;
     uint8_t* dst = img + off + kHapLeftMargin;
-    for (int c = 0; c < len; c++) dst[c] = panel_byte(b->hap_bases[o + c]);
+    const uint8_t* src = b->hap_bases + o;
+    for (int c = 0; fill && c < len; c++) dst[c] = lut[src[c]];
     off += kHapLeftMargin + len + kHapRightMargin;
   }
 }
 
-void build_pair_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) {
+void build_pair_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img, bool fill) {
+  const uint8_t* lut = base_lut().index;
   memset(img, 0, t.pbytes);
   int32_t* ppos = reinterpret_cast<int32_t*>(img);
   int32_t* lenA = ppos + t.n_pairs;
@@ -436,8 +453,9 @@ void build_pair_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img) 
     idxA[q] = a;
     idxB[q] = has_b ? bb : -1;
     uint8_t* dst = img + off + kHapLeftMargin;
-    for (int c = 0; c < la; c++)
-      dst[c] = (uint8_t)(base_index(b->hap_bases[oa + c]) | (c < lb ? base_index(b->hap_bases[ob + c]) << 3 : 0));
+    const uint8_t *sa = b->hap_bases + oa, *sb = b->hap_bases + ob;
+    for (int c = 0; fill && c < lb; c++) dst[c] = (uint8_t)(lut[sa[c]] | (lut[sb[c]] << 3));
+    for (int c = lb; fill && c < la; c++) dst[c] = lut[sa[c]];
     off += kHapLeftMargin + la + kHapRightMargin;
   }
 }
@@ -801,7 +819,28 @@ int validate_batch(const gklb_pairhmm_batch* b) {
   return GKLB_OK;
 }
 
+namespace {
+struct StageTimer {   // GKLB_STAGE_TIMING=1: host time of the phases of do_stage, to stderr
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  double acc[8] = {0};
+  StageTimer() : on(getenv("GKLB_STAGE_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void lap(int i) {
+    if (!on) return;
+    const auto t = std::chrono::steady_clock::now();
+    acc[i] += std::chrono::duration<double, std::milli>(t - t0).count();
+    t0 = t;
+  }
+  ~StageTimer() {
+    if (on)
+      fprintf(stderr, "[gklb stage] validate %.3f classes %.3f tiles+groups %.3f alloc %.3f images %.3f plan %.3f copy %.3f pack %.3f ms\n",
+              acc[0], acc[1], acc[2], acc[3], acc[4], acc[5], acc[6], acc[7]);
+  }
+};
+}  // namespace
+
 int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_on_device) {
+  StageTimer tm;
   if (!e->pending_out.empty())
     return fail(GKLB_ERR_STATE, "a submitted batch is still in flight on this engine: call gklb_engine_wait first");
   e->staged = false;
@@ -840,6 +879,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
     e->stats.cells += b.read_off[b.n_reads] * b.hap_off[b.n_haps];
     if (n_reads_all > 0x7fffffff || n_haps_all > 0x7fffffff) return fail(GKLB_ERR_INVALID, "job too large");
   }
+  tm.lap(0);
   e->stats.pairs = total_pairs;
   if (total_pairs == 0) {
     e->staged = true;
@@ -859,11 +899,13 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
 
   for (int r = 0; r < k; r++)
     if (e->regions[r].n_reads && (rc = plan_classes(e, &batches[r], r, e->regions[r].read_base))) return rc;
+  tm.lap(1);
   const long long budget = image_budget(e);
   for (int r = 0; r < k; r++)
     if (e->regions[r].n_reads && (rc = plan_tiles(e, &hb[r], r, budget))) return rc;
   size_t meta_bytes = 0;
   plan_groups(e, budget, &meta_bytes);
+  tm.lap(2);
 
   std::vector<int> tiles_of_region((size_t)k, 0);
   for (auto& t : e->tiles) tiles_of_region[t.region]++;
@@ -923,16 +965,19 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
   CU(e->h_counters.ensure(sizeof(unsigned int) * (size_t)counters));
   if (carry_bytes) CU(e->d_carry.ensure(carry_bytes));
 
+  tm.lap(3);
   uint8_t* hm = static_cast<uint8_t*>(e->h_meta.p);
   for (auto& t : e->tiles) {
-    build_tile_image(t, &hb[t.region], hm + t.meta_off);
-    build_pair_image(t, &hb[t.region], hm + t.pmeta_off);
+    build_tile_image(t, &hb[t.region], hm + t.meta_off, !e->defer_panel);
+    build_pair_image(t, &hb[t.region], hm + t.pmeta_off, !e->defer_panel);
   }
   for (auto& c : e->classes) {
     memcpy(hm + c.meta_rid, c.rid.data(), sizeof(int32_t) * c.n_rec);
     memcpy(hm + c.meta_len, c.len.data(), sizeof(int32_t) * c.n_rec);
   }
+  tm.lap(4);
   if ((rc = build_plan(e, hm))) return rc;  // every device buffer has its final address now
+  tm.lap(5);
 
   cudaStream_t s = e->stream;
   uint8_t* dmw = static_cast<uint8_t*>(e->d_meta.p);
@@ -967,6 +1012,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
     e->p_arenas = da;
   }
 
+  tm.lap(6);
   // one packing launch for all classes (32 classes per launch)
   const uint8_t* dm = dmw;
   for (size_t c0 = 0; c0 < e->classes.size(); c0 += 32) {
@@ -991,6 +1037,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
     }
     CU(launch_pack(pp, s));
   }
+  tm.lap(7);
   e->staged = true;
   return GKLB_OK;
 }
@@ -1105,6 +1152,18 @@ int do_wait(gklb_engine* e) {
   return GKLB_OK;
 }
 
+int fill_panels_from_device(gklb_engine* e, const uint8_t* hap_bases_dev) {
+  if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
+  if (e->regions.size() != 1) return fail(GKLB_ERR_STATE, "the staged job must have one region");
+  CU(cudaSetDevice(e->device));
+  uint8_t* dm = static_cast<uint8_t*>(e->d_meta.p);
+  for (auto& t : e->tiles) {
+    CU(launch_fill_panel(dm + t.meta_off, t.n, t.hap0, e->p_hap_off, hap_bases_dev, e->stream));
+    CU(launch_fill_pair_panel(dm + t.pmeta_off, t.n_pairs, e->p_hap_off, hap_bases_dev, e->stream));
+  }
+  return GKLB_OK;
+}
+
 int create_engine(gklb_engine** out, int device, int use_double) {
   int n = 0;
   cudaError_t ce = cudaGetDeviceCount(&n);
@@ -1135,8 +1194,9 @@ void destroy_engine(gklb_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (DevBuf* b : {&e->d_tables, &e->d_hap_off, &e->d_read_off, &e->d_arenas, &e->d_meta, &e->d_records, &e->d_out, &e->d_fb,
-                    &e->d_counters, &e->d_carry})
+                    &e->d_counters, &e->d_carry, &e->d_xhap, &e->d_xf32, &e->d_xidx, &e->d_xval, &e->d_xcnt})
     b->release();
+  for (HostBuf* b : {&e->h_xf32[0], &e->h_xf32[1], &e->h_xidx, &e->h_xval}) b->release();
   e->h_meta.release();
   e->h_counters.release();
   e->h_out.release();
@@ -1223,16 +1283,7 @@ int gklb_engine_stage_device(gklb_engine* e, const gklb_pairhmm_batch* batch) {
 int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_bases_dev) {
   if (!e || !hap_bases_dev) return fail(GKLB_ERR_INVALID, "null argument");
   std::lock_guard<std::mutex> lk(e->mu);
-  if (!e->staged) return fail(GKLB_ERR_STATE, "nothing staged");
-  CU(cudaSetDevice(e->device));
-  if (e->regions.size() != 1) return fail(GKLB_ERR_STATE, "the staged job must have one region");
-  uint8_t* dm = static_cast<uint8_t*>(e->d_meta.p);
-  for (auto& t : e->tiles) {
-    CU(launch_fill_panel(dm + t.meta_off, t.n, t.hap0, e->p_hap_off, static_cast<const uint8_t*>(hap_bases_dev), e->stream));
-    CU(launch_fill_pair_panel(dm + t.pmeta_off, t.n_pairs, e->p_hap_off, static_cast<const uint8_t*>(hap_bases_dev),
-                              e->stream));
-  }
-  return GKLB_OK;
+  return fill_panels_from_device(e, static_cast<const uint8_t*>(hap_bases_dev));
 }
 
 int gklb_engine_run(gklb_engine* e) {

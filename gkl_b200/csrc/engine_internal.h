@@ -129,6 +129,8 @@ struct gklb_engine {
   std::vector<gklb::Launch> plan;
   gklb::DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
   gklb::HostBuf h_meta, h_counters, h_out;
+  gklb::DevBuf d_xhap, d_xf32, d_xidx, d_xval, d_xcnt;  // NCCL sharding path (engine_nccl.cu): panel, fp32 slab, overrides
+  gklb::HostBuf h_xf32[2], h_xidx, h_xval;
   std::vector<double*> pending_out;  // destinations of the job submitted with gklb_engine_submit, until gklb_engine_wait
   size_t arena_pitch = 0;
   const int64_t* p_read_off = nullptr;  // where the staged offsets / arenas live on the device
@@ -138,6 +140,7 @@ struct gklb_engine {
   int mega_counter0 = 0;  // first of the per-group unified queue counters (two per group)
   gklb_pairhmm_stats stats{};
   char sweep_kernel[96] = {0};  // name of the (last) forward-sweep kernel of the plan
+  bool defer_panel = false;     // stage with empty panel images: the bases arrive in device memory (fill_panels_from_device)
   // forced kernel (measurement): policy,G,K,warps,var
   bool forced = false;
   int f_policy = 0, f_G = 0, f_K = 0, f_warps = 0, f_var = 0;
@@ -156,5 +159,8 @@ int do_fetch(gklb_engine* e, double* const* outs);
 int do_compute(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs);
 int do_submit(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs);
 int do_wait(gklb_engine* e);
+// Write the haplotype bases of the staged (single-region) job's panel images from a device buffer laid out like the
+// batch's hap_bases arena (kernels on the engine's stream).
+int fill_panels_from_device(gklb_engine* e, const uint8_t* hap_bases_dev);
 
 }  // namespace gklb

@@ -353,3 +353,26 @@ def test_config4_shape_at_reduced_size_all_pairs(eng):
     assert np.array_equal(np.isfinite(out), np.isfinite(ref))
     assert rel(out, ref).max() <= REL_TOL
     assert eng.stats().fallback_pairs > 0
+
+
+def test_nccl_sharding_is_bit_identical_to_direct_sharding(monkeypatch):
+    """GKLB_SHARD=nccl (engine_nccl.cu): panel broadcast over NVLink, fp32 slabs + fp64 overrides gathered to GPU 0.
+    Needs two GPUs (one NCCL rank per GPU)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    big = synth.config2(3000, 128)  # 1.1e10 cells -> two shards
+    monkeypatch.setenv("GKLB_DEVICES", "0,1")
+    outs = {}
+    for mode in ("direct", "nccl"):
+        monkeypatch.setenv("GKLB_SHARD", mode)
+        assert native.global_init(False, 1) == 2
+        try:
+            outs[mode] = native.global_compute(big)
+            st = native.global_stats()
+            assert st.pairs == big.n_reads * big.n_haps and st.fallback_pairs > 0
+        finally:
+            native.global_done()
+    assert np.array_equal(outs["direct"], outs["nccl"])
+    ref = checker(big.read_slice(0, 64))
+    assert rel(outs["nccl"][:64 * big.n_haps], ref).max() <= REL_TOL
