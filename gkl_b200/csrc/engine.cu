@@ -167,8 +167,10 @@ int set_kernel_attrs() {
     CU(cudaFuncSetAttribute(t[i].fn_tasks, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
     if (t[i].fn_list) CU(cudaFuncSetAttribute(t[i].fn_list, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   }
-  for (const void* fn : {h2_mega_kernel(), mega_kernel(POL_D1, 0), mega_kernel(POL_D1, 1)})
+  for (const void* fn : {h2_mega_kernel(), r2_mega_kernel(), mega_kernel(POL_D1, 0), mega_kernel(POL_D1, 1)})
     if (fn) CU(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  for (int G : {4, 8, 16})
+    for (int K = 8; K <= 16; K++) CU(cudaFuncSetAttribute(r2_kernel(G, K), cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   return GKLB_OK;
 }
 
@@ -355,14 +357,17 @@ int classes_of_region(const gklb_engine* e, int region) {
   return n;
 }
 
-// Pack consecutive tiles into launch groups (their images resident together) and lay everything out in the meta block.
+// Pack consecutive tiles into launch groups (their images resident together), create the (class, tile) entries and lay
+// everything out in the meta block.
 void plan_groups(gklb_engine* e, long long budget, size_t* meta_bytes) {
   e->groups.clear();
+  e->entries.clear();
   const int max_entries = kMaxMegaClasses;
   size_t i = 0;
   while (i < e->tiles.size()) {
     Group g;
     g.tile0 = (int)i;
+    g.entry0 = (int)e->entries.size();
     while (i < e->tiles.size()) {
       Tile& t = e->tiles[i];
       const int ent = classes_of_region(e, t.region);
@@ -373,10 +378,21 @@ void plan_groups(gklb_engine* e, long long budget, size_t* meta_bytes) {
       t.pimg_off = g.pbytes;
       g.bytes += t.bytes;    // multiples of 16: every image stays 16-byte aligned for the bulk copy
       g.pbytes += t.pbytes;
+      for (size_t ci = 0; ci < e->classes.size(); ci++)
+        if (e->classes[ci].region == t.region) {
+          EntryInst en;
+          en.cls = (int)ci;
+          en.tile = (int)i;
+          e->entries.push_back(en);
+        }
       g.n_entries += ent;
       g.n_tiles++;
       i++;
     }
+    // longest classes first: their tasks are the most expensive
+    std::stable_sort(e->entries.begin() + g.entry0, e->entries.end(), [&](const EntryInst& x, const EntryInst& y) {
+      return e->classes[x.cls].rows > e->classes[y.cls].rows;
+    });
     g.meta_off = *meta_bytes;
     *meta_bytes += align_up(g.bytes, 128);
     g.pmeta_off = *meta_bytes;
@@ -391,6 +407,8 @@ void plan_groups(gklb_engine* e, long long budget, size_t* meta_bytes) {
     g.h2_cls_off = take(sizeof(H2Class) * n);
     g.h2_cfg_off = take(sizeof(int) * n);
     g.h2_end_off = take(sizeof(int) * n);
+    g.r2_cls_off = take(sizeof(R2Class) * n);
+    g.r2_cfg_off = take(sizeof(int) * n);
     g.dl_cls_off = take(sizeof(SweepParams) * n);
     g.dl_cfg_off = take(sizeof(int) * n);
     g.dt_cls_off = take(sizeof(SweepParams) * n);
@@ -482,8 +500,10 @@ struct Sizing { int grid; size_t smem; uint32_t slot_bytes; };
 // Parameters of one fp64 / packed-read (class, tile, kernel) combination.  resident: the panel is part of a group
 // image (multi-class launch); otherwise the launch loads the tile's own image.  work_scale: how many warp slots the
 // launch can count on for this entry (the whole GPU for a single-class launch, a share of it in a group).
-Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const KernelEntry* k, bool list_mode, bool resident,
+Sizing fill_params(gklb_engine* e, const EntryInst& en, const KernelEntry* k, bool list_mode, bool resident,
                    long long group_units, SweepParams* out) {
+  const ClassInst& c = e->classes[en.cls];
+  const Tile& t = e->tiles[en.tile];
   const bool dbl = (k->policy == POL_D1);
   const HostTables& ht = host_tables();
   const Region& reg = e->regions[c.region];
@@ -508,9 +528,9 @@ Sizing fill_params(gklb_engine* e, const ClassInst& c, const Tile& t, const Kern
   p.mm = dbl ? (const void*)e->d_mm_d : (const void*)e->d_mm_f;
   p.out = region_out(e, reg);
   unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
-  p.fb_count = counters + c.counter0;
-  p.fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + c.fb_off : nullptr;
-  p.task_counter = counters + c.counter0 + 1 + 2 * t.index_in_region + (list_mode ? 1 : 0);
+  p.fb_count = counters + en.counter0 + 1;
+  p.fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + en.fb_off : nullptr;
+  p.task_counter = counters + en.counter0 + (list_mode ? 5 : 3);
   p.carry = c.multi ? static_cast<uint8_t*>(e->d_carry.p) + c.carry_off : nullptr;
   p.carry_stride_bytes = c.carry_stride;
   p.init_const = dbl ? ht.init_d : (double)ht.init_f;
@@ -552,8 +572,9 @@ void fill_h2_common(gklb_engine* e, const uint8_t* image, uint32_t bytes, H2Comm
   com->log10_init = ht.log10_init_f;
 }
 
-void fill_h2_class(gklb_engine* e, const ClassInst& c, const Tile& t, int warps, bool resident, long long group_units,
-                   H2Class* cls) {
+void fill_h2_class(gklb_engine* e, const EntryInst& en, int warps, bool resident, long long group_units, H2Class* cls) {
+  const ClassInst& c = e->classes[en.cls];
+  const Tile& t = e->tiles[en.tile];
   memset(cls, 0, sizeof(*cls));
   const Region& reg = e->regions[c.region];
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
@@ -561,8 +582,9 @@ void fill_h2_class(gklb_engine* e, const ClassInst& c, const Tile& t, int warps,
   cls->rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
   cls->rec_len = reinterpret_cast<const int32_t*>(dm + c.meta_len);
   unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
-  cls->fb_count = counters + c.counter0;
-  cls->fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + c.fb_off : nullptr;
+  cls->r2_count = counters + en.counter0;
+  cls->r2_items = static_cast<uint2*>(e->d_r2.p) + en.r2_off;
+  cls->fb_pairs = counters + en.counter0 + 2;
   cls->n_rec = c.n_rec;
   cls->rows = c.rows;
   cls->stride = c.stride;
@@ -593,14 +615,46 @@ int push_launch(gklb_engine* e, Launch&& l) {
   return GKLB_OK;
 }
 
-Launch h2_single_launch(gklb_engine* e, const ClassInst& c, const Tile& t) {
+void fill_r2_class(gklb_engine* e, const EntryInst& en, bool resident, R2Class* cls) {
+  const ClassInst& c = e->classes[en.cls];
+  const Tile& t = e->tiles[en.tile];
+  const Region& reg = e->regions[c.region];
+  static const bool force_fp64 = [] {
+    const char* v = getenv("GKLB_R2");  // GKLB_R2=0: every flagged pair goes to the fp64 kernel (measurement)
+    return v && atoi(v) == 0;
+  }();
+  memset(cls, 0, sizeof(*cls));
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
+  cls->records = static_cast<const uint8_t*>(e->d_records.p) + c.rec_off;
+  cls->rec_rid = reinterpret_cast<const int32_t*>(dm + c.meta_rid);
+  cls->rec_len = reinterpret_cast<const int32_t*>(dm + c.meta_len);
+  cls->items = static_cast<const uint2*>(e->d_r2.p) + en.r2_off;
+  cls->n_items = counters + en.counter0;
+  cls->fb_items = static_cast<uint2*>(e->d_fb.p) + en.fb_off;
+  cls->fb_count = counters + en.counter0 + 1;
+  cls->rows = c.rows;
+  cls->stride = c.stride;
+  cls->panel_off = resident ? t.pimg_off : 0u;
+  cls->n_pairs = t.n_pairs;
+  cls->n_haps_total = reg.n_haps;
+  cls->out = region_out(e, reg);
+  cls->force_fp64 = force_fp64 ? 1 : 0;
+  cls->debug_flags = getenv("GKLB_R2_DEBUG") ? atoi(getenv("GKLB_R2_DEBUG")) : 0;
+}
+
+uint32_t r2_slot_bytes(const ClassInst& c) { return (uint32_t)(kPriorSyms * c.K * 32 * 4); }
+
+Launch h2_single_launch(gklb_engine* e, const EntryInst& en) {
+  const ClassInst& c = e->classes[en.cls];
+  const Tile& t = e->tiles[en.tile];
   H2Params p;
   memset(&p, 0, sizeof(p));
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
   fill_h2_common(e, dm + t.pmeta_off, t.pbytes, &p.com);
-  fill_h2_class(e, c, t, c.kf->warps, false, 0, &p.cls);
+  fill_h2_class(e, en, c.kf->warps, false, 0, &p.cls);
   p.com.slot_bytes = warp_slot_bytes(c, c.kf, false);
-  p.task_counter = static_cast<unsigned int*>(e->d_counters.p) + c.counter0 + 1 + 2 * t.index_in_region;
+  p.task_counter = static_cast<unsigned int*>(e->d_counters.p) + en.counter0 + 3;
   Launch l;
   l.fn = c.kf->fn_tasks;
   l.threads = c.kf->warps * 32;
@@ -612,7 +666,25 @@ Launch h2_single_launch(gklb_engine* e, const ClassInst& c, const Tile& t) {
   return l;
 }
 
-struct Entry { const ClassInst* c; const Tile* t; };
+Launch r2_single_launch(gklb_engine* e, const EntryInst& en) {
+  const ClassInst& c = e->classes[en.cls];
+  const Tile& t = e->tiles[en.tile];
+  R2Params p;
+  memset(&p, 0, sizeof(p));
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  fill_h2_common(e, dm + t.pmeta_off, t.pbytes, &p.com);
+  fill_r2_class(e, en, false, &p.cls);
+  p.com.slot_bytes = r2_slot_bytes(c);
+  p.item_counter = static_cast<unsigned int*>(e->d_counters.p) + en.counter0 + 4;
+  Launch l;
+  l.fn = r2_kernel(c.G, c.K);
+  l.threads = kH2Warps * 32;
+  l.smem = smem_layout(kH2Warps, t.pbytes, p.com.slot_bytes, 4).total;
+  l.grid = e->num_sms;
+  set_params(l, p);
+  return l;
+}
+
 
 // Build the launches of the staged job.  hm: host image of the meta block (the device-resident class arrays of the
 // multi-class kernels are written into it before it is uploaded).
@@ -626,20 +698,19 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
   int rc;
   for (size_t gi = 0; gi < e->groups.size(); gi++) {
     const Group& g = e->groups[gi];
-    // (class, tile) entries of the group, longest classes first: their tasks are the most expensive
-    std::vector<Entry> entries;
-    for (int k = 0; k < g.n_tiles; k++) {
-      const Tile& t = e->tiles[g.tile0 + k];
-      for (auto& c : e->classes)
-        if (c.region == t.region) entries.push_back({&c, &t});
-    }
-    std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.c->rows > b.c->rows; });
-    unsigned int* queue = counters + e->mega_counter0 + 2 * gi;
+    const EntryInst* ents = e->entries.data() + g.entry0;
+    const int n_ent = g.n_entries;
+    unsigned int* queue = counters + e->mega_counter0 + 3 * gi;
+    auto cls_of = [&](const EntryInst& en) -> const ClassInst& { return e->classes[en.cls]; };
+    auto tile_of = [&](const EntryInst& en) -> const Tile& { return e->tiles[en.tile]; };
 
     if (e->use_double) {  // ---- fp64 over all pairs ----
-      if (mega_ok && entries.size() > 1) {
+      if (mega_ok && n_ent > 1) {
         long long units = 0;
-        for (auto& en : entries) units += (long long)(en.c->n_rec / ((32 / en.c->kd->G) * en.c->kd->nr)) * en.t->n;
+        for (int i = 0; i < n_ent; i++) {
+          const ClassInst& c = cls_of(ents[i]);
+          units += (long long)(c.n_rec / ((32 / c.kd->G) * c.kd->nr)) * tile_of(ents[i]).n;
+        }
         MegaParams mp;
         memset(&mp, 0, sizeof(mp));
         SweepParams* arr = reinterpret_cast<SweepParams*>(hm + g.dt_cls_off);
@@ -647,14 +718,15 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
         int* ends = reinterpret_cast<int*>(hm + g.dt_end_off);
         uint32_t slot_bytes = 0;
         int tasks = 0;
-        for (auto& en : entries) {
-          const int i = mp.n_classes++;
-          const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, false, true, units, &arr[i]);
-          cfg[i] = en.c->cfg_d;
+        for (int i = 0; i < n_ent; i++) {
+          const ClassInst& c = cls_of(ents[i]);
+          const Sizing z = fill_params(e, ents[i], c.kd, false, true, units, &arr[i]);
+          cfg[i] = c.cfg_d;
           tasks += arr[i].n_tasks;
           ends[i] = tasks;
           slot_bytes = std::max(slot_bytes, z.slot_bytes);
         }
+        mp.n_classes = n_ent;
         mp.cfg = reinterpret_cast<const int*>(dm + g.dt_cfg_off);
         mp.task_end = reinterpret_cast<const int*>(dm + g.dt_end_off);
         mp.cls = reinterpret_cast<const SweepParams*>(dm + g.dt_cls_off);
@@ -664,26 +736,27 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
         Launch l;
         l.fn = mega_kernel(POL_D1, 0);
         l.threads = 8 * 32;
-        l.smem = smem_layout(8, g.bytes, slot_bytes, 8, (uint32_t)mp.n_classes).total;
+        l.smem = smem_layout(8, g.bytes, slot_bytes, 8, (uint32_t)n_ent).total;
         l.grid = std::min(e->num_sms, (tasks + 7) / 8);
         l.extra = slot_bytes;
         l.sweep = true;
         set_params(l, mp);
-        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_mega_tasks<VD1,8> (%d class x tile entries)", mp.n_classes);
+        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_mega_tasks<VD1,8> (%d class x tile entries)", n_ent);
         if ((rc = push_launch(e, std::move(l)))) return rc;
       } else {
-        for (auto& en : entries) {
+        for (int i = 0; i < n_ent; i++) {
+          const ClassInst& c = cls_of(ents[i]);
           SweepParams p;
-          const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, false, false, 0, &p);
+          const Sizing z = fill_params(e, ents[i], c.kd, false, false, 0, &p);
           Launch l;
-          l.fn = en.c->kd->fn_tasks;
-          l.threads = en.c->kd->warps * 32;
+          l.fn = c.kd->fn_tasks;
+          l.threads = c.kd->warps * 32;
           l.smem = z.smem;
           l.grid = z.grid;
           l.sweep = true;
           set_params(l, p);
-          snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<VD1,%d,%d,%d,%s>", en.c->kd->G, en.c->kd->K,
-                   en.c->kd->warps, en.c->multi ? "multi" : "single");
+          snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<VD1,%d,%d,%d,%s>", c.kd->G, c.kd->K, c.kd->warps,
+                   c.multi ? "multi" : "single");
           if ((rc = push_launch(e, std::move(l)))) return rc;
         }
       }
@@ -691,11 +764,12 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
     }
 
     // ---- fp32 forward sweep ----
-    std::vector<Entry> h2, other;
-    for (auto& en : entries) (en.c->kf->policy == POL_H2 && !e->forced ? h2 : other).push_back(en);
-    if (mega_ok && h2.size() > 1) {
+    std::vector<int> h2, other;  // indices into ents
+    for (int i = 0; i < n_ent; i++) (cls_of(ents[i]).kf->policy == POL_H2 && !e->forced ? h2 : other).push_back(i);
+    const bool h2_mega = mega_ok && h2.size() > 1;
+    if (h2_mega) {
       long long units = 0;
-      for (auto& en : h2) units += (long long)(en.c->n_rec / (32 / en.c->G)) * en.t->n_pairs;
+      for (int i : h2) units += (long long)(cls_of(ents[i]).n_rec / (32 / cls_of(ents[i]).G)) * tile_of(ents[i]).n_pairs;
       H2MegaParams mp;
       memset(&mp, 0, sizeof(mp));
       fill_h2_common(e, dm + g.pmeta_off, g.pbytes, &mp.com);
@@ -704,13 +778,14 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
       int* ends = reinterpret_cast<int*>(hm + g.h2_end_off);
       int tasks = 0;
       uint32_t slot_bytes = 0;
-      for (auto& en : h2) {
-        const int i = mp.n_classes++;
-        fill_h2_class(e, *en.c, *en.t, kH2Warps, true, units, &arr[i]);
-        cfg[i] = en.c->cfg_f;
-        tasks += arr[i].n_tasks;
-        ends[i] = tasks;
-        slot_bytes = std::max(slot_bytes, warp_slot_bytes(*en.c, en.c->kf, false));
+      for (int i : h2) {
+        const ClassInst& c = cls_of(ents[i]);
+        const int k = mp.n_classes++;
+        fill_h2_class(e, ents[i], kH2Warps, true, units, &arr[k]);
+        cfg[k] = c.cfg_f;
+        tasks += arr[k].n_tasks;
+        ends[k] = tasks;
+        slot_bytes = std::max(slot_bytes, warp_slot_bytes(c, c.kf, false));
       }
       mp.com.slot_bytes = slot_bytes;
       mp.cfg = reinterpret_cast<const int*>(dm + g.h2_cfg_off);
@@ -728,63 +803,100 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
                g.n_tiles);
       if ((rc = push_launch(e, std::move(l)))) return rc;
     } else {
-      for (auto& en : h2)
-        if ((rc = push_launch(e, h2_single_launch(e, *en.c, *en.t)))) return rc;
+      for (int i : h2)
+        if ((rc = push_launch(e, h2_single_launch(e, ents[i])))) return rc;
     }
-    for (auto& en : other) {  // multi-pass classes and forced measurement kernels: one launch each
-      if (en.c->kf->policy == POL_H2) {
-        if ((rc = push_launch(e, h2_single_launch(e, *en.c, *en.t)))) return rc;
+    for (int i : other) {  // multi-pass classes and forced measurement kernels: one launch each
+      const ClassInst& c = cls_of(ents[i]);
+      if (c.kf->policy == POL_H2) {
+        if ((rc = push_launch(e, h2_single_launch(e, ents[i])))) return rc;
         continue;
       }
       SweepParams p;
-      const Sizing z = fill_params(e, *en.c, *en.t, en.c->kf, false, false, 0, &p);
+      const Sizing z = fill_params(e, ents[i], c.kf, false, false, 0, &p);
       Launch l;
-      l.fn = en.c->kf->fn_tasks;
-      l.threads = en.c->kf->warps * 32;
+      l.fn = c.kf->fn_tasks;
+      l.threads = c.kf->warps * 32;
       l.smem = z.smem;
       l.grid = z.grid;
       l.sweep = true;
       set_params(l, p);
       if (!e->sweep_kernel[0] || e->forced)
-        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<pol%d,%d,%d,%d,%s,var%d>", en.c->kf->policy,
-                 en.c->G, en.c->K, en.c->kf->warps, en.c->multi ? "multi" : "single", en.c->kf->var);
+        snprintf(e->sweep_kernel, sizeof(e->sweep_kernel), "k_sweep_tasks<pol%d,%d,%d,%d,%s,var%d>", c.kf->policy, c.G, c.K,
+                 c.kf->warps, c.multi ? "multi" : "single", c.kf->var);
       if ((rc = push_launch(e, std::move(l)))) return rc;
     }
 
-    // ---- fp64 rerun of the flagged pairs ----
-    if (mega_ok && entries.size() > 1) {
+    // ---- range-extended fp32 rerun of the pairs the H2 sweep flagged ----
+    std::vector<int> h2all;  // every H2 entry, forced ones included (their lists have the same format)
+    for (int i = 0; i < n_ent; i++)
+      if (cls_of(ents[i]).kf->policy == POL_H2) h2all.push_back(i);
+    if (h2_mega) {
+      R2MegaParams mp;
+      memset(&mp, 0, sizeof(mp));
+      fill_h2_common(e, dm + g.pmeta_off, g.pbytes, &mp.com);
+      R2Class* arr = reinterpret_cast<R2Class*>(hm + g.r2_cls_off);
+      int* cfg = reinterpret_cast<int*>(hm + g.r2_cfg_off);
+      uint32_t slot_bytes = 0;
+      for (int i : h2all) {
+        const ClassInst& c = cls_of(ents[i]);
+        const int k = mp.n_classes++;
+        fill_r2_class(e, ents[i], true, &arr[k]);
+        cfg[k] = c.cfg_f;
+        slot_bytes = std::max(slot_bytes, r2_slot_bytes(c));
+      }
+      mp.com.slot_bytes = slot_bytes;
+      mp.cfg = reinterpret_cast<const int*>(dm + g.r2_cfg_off);
+      mp.cls = reinterpret_cast<const R2Class*>(dm + g.r2_cls_off);
+      mp.queue = queue + 1;
+      Launch l;
+      l.fn = r2_mega_kernel();
+      l.threads = kH2Warps * 32;
+      l.smem = smem_layout(kH2Warps, g.pbytes, slot_bytes, 4, (uint32_t)mp.n_classes).total;
+      l.grid = e->num_sms;
+      set_params(l, mp);
+      if ((rc = push_launch(e, std::move(l)))) return rc;
+    } else {
+      for (int i : h2all)
+        if ((rc = push_launch(e, r2_single_launch(e, ents[i])))) return rc;
+    }
+
+    // ---- fp64: what the rerun's guards passed on, and the flagged pairs of the multi-pass classes ----
+    if (mega_ok && n_ent > 1) {
       MegaParams mp;
       memset(&mp, 0, sizeof(mp));
       SweepParams* arr = reinterpret_cast<SweepParams*>(hm + g.dl_cls_off);
       int* cfg = reinterpret_cast<int*>(hm + g.dl_cfg_off);
       uint32_t slot_bytes = 0;
-      for (auto& en : entries) {
-        const int i = mp.n_classes++;
-        const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, true, true, 0, &arr[i]);
-        cfg[i] = en.c->cfg_d;
+      for (int i = 0; i < n_ent; i++) {
+        const ClassInst& c = cls_of(ents[i]);
+        const Sizing z = fill_params(e, ents[i], c.kd, true, true, 0, &arr[i]);
+        cfg[i] = c.cfg_d;
         slot_bytes = std::max(slot_bytes, z.slot_bytes);
       }
+      mp.n_classes = n_ent;
       mp.cfg = reinterpret_cast<const int*>(dm + g.dl_cfg_off);
       mp.cls = reinterpret_cast<const SweepParams*>(dm + g.dl_cls_off);
-      mp.queue = queue + 1;
+      mp.queue = queue + 2;
       mp.image = dm + g.meta_off;
       mp.image_bytes = g.bytes;
       Launch l;
       l.fn = mega_kernel(POL_D1, 1);
       l.threads = 8 * 32;
-      l.smem = smem_layout(8, g.bytes, slot_bytes, 8, (uint32_t)mp.n_classes).total;
+      l.smem = smem_layout(8, g.bytes, slot_bytes, 8, (uint32_t)n_ent).total;
       l.grid = e->num_sms;
       l.extra = slot_bytes;
       set_params(l, mp);
       if ((rc = push_launch(e, std::move(l)))) return rc;
     } else {
-      for (auto& en : entries) {
-        if (en.c->kf->policy == POL_D1) continue;  // forced fp64 sweep: nothing to rerun
+      for (int i = 0; i < n_ent; i++) {
+        const ClassInst& c = cls_of(ents[i]);
+        if (c.kf->policy == POL_D1) continue;  // forced fp64 sweep: nothing to rerun
         SweepParams p;
-        const Sizing z = fill_params(e, *en.c, *en.t, en.c->kd, true, false, 0, &p);
+        const Sizing z = fill_params(e, ents[i], c.kd, true, false, 0, &p);
         Launch l;
-        l.fn = en.c->kd->fn_list;
-        l.threads = en.c->kd->warps * 32;
+        l.fn = c.kd->fn_list;
+        l.threads = c.kd->warps * 32;
         l.smem = z.smem;
         l.grid = z.grid;
         set_params(l, p);
@@ -795,14 +907,19 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
   return GKLB_OK;
 }
 
-void read_fallback_count(gklb_engine* e) {
-  int64_t fb = 0;
-  const unsigned int* hc = static_cast<const unsigned int*>(e->h_counters.p);
-  for (auto& c : e->classes) fb += hc[c.counter0];
-  e->stats.fallback_pairs = fb;
-}
-
 }  // namespace
+
+void read_fallback_count(gklb_engine* e) {
+  int64_t fb = 0, f64 = 0;
+  const unsigned int* hc = static_cast<const unsigned int*>(e->h_counters.p);
+  for (auto& en : e->entries) {
+    const bool h2 = e->classes[en.cls].kf->policy == POL_H2;
+    fb += h2 ? hc[en.counter0 + 2] : hc[en.counter0 + 1];
+    f64 += hc[en.counter0 + 1];
+  }
+  e->stats.fallback_pairs = fb;
+  e->stats.fp64_pairs = f64;
+}
 
 int validate_batch(const gklb_pairhmm_batch* b) {
   if (!b) return fail(GKLB_ERR_INVALID, "batch is null");
@@ -907,22 +1024,27 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
   plan_groups(e, budget, &meta_bytes);
   tm.lap(2);
 
-  std::vector<int> tiles_of_region((size_t)k, 0);
-  for (auto& t : e->tiles) tiles_of_region[t.region]++;
-  size_t rec_bytes = 0, fb_items = 0, carry_bytes = 0;
+  size_t rec_bytes = 0, fb_items = 0, r2_items = 0, carry_bytes = 0;
   int counters = 0;
+  for (auto& en : e->entries) {
+    const ClassInst& c = e->classes[en.cls];
+    const Tile& t = e->tiles[en.tile];
+    en.fb_off = fb_items;
+    en.r2_off = r2_items;
+    if (!e->use_double) {
+      fb_items += (size_t)c.n_rec * t.n;
+      if (c.kf->policy == POL_H2) r2_items += (size_t)c.n_rec * t.n_pairs;
+    }
+    en.counter0 = counters;
+    counters += kEntryCounters;
+  }
   for (auto& c : e->classes) {
-    const Region& reg = e->regions[c.region];
     c.meta_rid = meta_bytes;
     meta_bytes += align_up(sizeof(int32_t) * c.n_rec, 128);
     c.meta_len = meta_bytes;
     meta_bytes += align_up(sizeof(int32_t) * c.n_rec, 128);
     c.rec_off = rec_bytes;
     rec_bytes += align_up((size_t)c.n_rec * 5 * c.stride, 128);
-    c.fb_off = fb_items;
-    if (!e->use_double) fb_items += (size_t)c.n_rec * reg.n_haps;
-    c.counter0 = counters;
-    counters += 1 + 2 * tiles_of_region[c.region];
     if (c.multi) {
       int max_len = 0;
       for (auto& t : e->tiles)
@@ -935,7 +1057,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
     }
   }
   e->mega_counter0 = counters;
-  counters += 2 * (int)e->groups.size();
+  counters += 3 * (int)e->groups.size();
   e->n_counters = counters;
 
   // host-resident jobs of moderate size: offsets + arenas are staged behind the meta block -> one host->device copy
@@ -961,6 +1083,7 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
   }
   CU(e->d_out.ensure(sizeof(double) * (size_t)total_pairs));
   if (fb_items) CU(e->d_fb.ensure(sizeof(uint2) * fb_items));
+  if (r2_items) CU(e->d_r2.ensure(sizeof(uint2) * r2_items));
   CU(e->d_counters.ensure(sizeof(unsigned int) * (size_t)counters));
   CU(e->h_counters.ensure(sizeof(unsigned int) * (size_t)counters));
   if (carry_bytes) CU(e->d_carry.ensure(carry_bytes));
@@ -1194,7 +1317,7 @@ void destroy_engine(gklb_engine* e) {
   cudaSetDevice(e->device);
   cudaStreamSynchronize(e->stream);
   for (DevBuf* b : {&e->d_tables, &e->d_hap_off, &e->d_read_off, &e->d_arenas, &e->d_meta, &e->d_records, &e->d_out, &e->d_fb,
-                    &e->d_counters, &e->d_carry, &e->d_xhap, &e->d_xf32, &e->d_xidx, &e->d_xval, &e->d_xcnt})
+                    &e->d_r2, &e->d_counters, &e->d_carry, &e->d_xhap, &e->d_xf32, &e->d_xidx, &e->d_xval, &e->d_xcnt})
     b->release();
   for (HostBuf* b : {&e->h_xf32[0], &e->h_xf32[1], &e->h_xidx, &e->h_xval}) b->release();
   e->h_meta.release();

@@ -12,6 +12,7 @@
 #include "../../include/gklb_pairhmm.h"
 #include "pairhmm_device.cuh"
 #include "pairhmm_h2.cuh"
+#include "pairhmm_r2.cuh"
 #include "pairhmm_kernels.h"
 
 namespace gklb {
@@ -66,10 +67,19 @@ struct ClassInst {
   int n_rec = 0;
   size_t meta_rid = 0, meta_len = 0;  // offsets into the meta block
   size_t rec_off = 0;                 // into d_records
-  size_t fb_off = 0;                  // into d_fb (uint2 units)
   size_t carry_off = 0, carry_stride = 0;
-  int counter0 = 0;  // index of this class's first counter (rerun count), then per tile: task counter, list counter
 };
+
+// One (class, tile) combination: the unit the kernels work on.  Its rerun lists and counters.
+//   counters: +0 rerun items (H2 sweep -> range-extended rerun)   +1 fp64 items   +2 pairs flagged by the fp32 sweep
+//             +3 task counter of a single-class sweep   +4 ... of the rerun   +5 ... of the fp64 list kernel
+struct EntryInst {
+  int cls = 0, tile = 0;
+  size_t r2_off = 0;   // into d_r2 (uint2 units): capacity n_rec * n_pairs
+  size_t fb_off = 0;   // into d_fb (uint2 units): capacity n_rec * n (haplotypes of the tile)
+  int counter0 = 0;
+};
+constexpr int kEntryCounters = 6;
 
 // A tile: as many haplotypes of one region as fit in shared memory beside the record slots, as two images.
 struct Tile {
@@ -90,8 +100,9 @@ struct Group {
   int tile0 = 0, n_tiles = 0;
   size_t meta_off = 0, pmeta_off = 0;  // start of the group's contiguous per-haplotype / pair images in the meta block
   uint32_t bytes = 0, pbytes = 0;
-  int n_entries = 0;                   // (class, tile) pairs
+  int entry0 = 0, n_entries = 0;       // (class, tile) entries [entry0, entry0 + n_entries) of e->entries
   size_t h2_cls_off = 0, h2_cfg_off = 0, h2_end_off = 0;      // device-resident arrays of the multi-class launches
+  size_t r2_cls_off = 0, r2_cfg_off = 0;                       //   range-extended rerun
   size_t dl_cls_off = 0, dl_cfg_off = 0;                       //   fp64 rerun list
   size_t dt_cls_off = 0, dt_cfg_off = 0, dt_end_off = 0;      //   fp64 tasks (use_double)
 };
@@ -126,8 +137,9 @@ struct gklb_engine {
   std::vector<gklb::ClassInst> classes;
   std::vector<gklb::Tile> tiles;
   std::vector<gklb::Group> groups;
+  std::vector<gklb::EntryInst> entries;
   std::vector<gklb::Launch> plan;
-  gklb::DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_counters, d_carry;
+  gklb::DevBuf d_read_off, d_hap_off, d_arenas, d_meta, d_records, d_out, d_fb, d_r2, d_counters, d_carry;
   gklb::HostBuf h_meta, h_counters, h_out;
   gklb::DevBuf d_xhap, d_xf32, d_xidx, d_xval, d_xcnt;  // NCCL sharding path (engine_nccl.cu): panel, fp32 slab, overrides
   gklb::HostBuf h_xf32[2], h_xidx, h_xval;
@@ -159,6 +171,8 @@ int do_fetch(gklb_engine* e, double* const* outs);
 int do_compute(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs);
 int do_submit(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* const* outs);
 int do_wait(gklb_engine* e);
+// stats.fallback_pairs / fp64_pairs from the counters last copied to e->h_counters
+void read_fallback_count(gklb_engine* e);
 // Write the haplotype bases of the staged (single-region) job's panel images from a device buffer laid out like the
 // batch's hap_bases arena (kernels on the engine's stream).
 int fill_panels_from_device(gklb_engine* e, const uint8_t* hap_bases_dev);

@@ -105,7 +105,31 @@ __global__ void k_narrow(const double* __restrict__ in, float* __restrict__ out,
     out[i] = (float)in[i];
 }
 
-// The pairs the fp64 rerun produced, as (pair index in the shard, value): one class's rerun list.
+// The same for the rerun items of an H2 entry: (record, pair index in the tile | half mask << 30); the haplotype
+// indices of a pair are in the header of the tile's pair image.
+__global__ void k_collect_overrides_r2(const uint2* __restrict__ items, const unsigned int* __restrict__ count,
+                                       const int32_t* __restrict__ rec_rid, const uint8_t* __restrict__ pair_image, int n_pairs,
+                                       int n_haps, const double* __restrict__ out, uint32_t* __restrict__ idx,
+                                       double* __restrict__ val, unsigned int* cursor) {
+  const int32_t* idxA = reinterpret_cast<const int32_t*>(pair_image) + 3 * n_pairs;
+  const int32_t* idxB = idxA + n_pairs;
+  const unsigned int n = *count;
+  for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const uint2 it = items[k];
+    const int q = (int)(it.y & 0x3fffffffu);
+    const unsigned int mask = it.y >> 30;
+    for (int x = 0; x < 2; x++) {
+      if (!(mask & (1u << x))) continue;
+      const int h = x == 0 ? idxA[q] : idxB[q];
+      const uint32_t pair = (uint32_t)rec_rid[it.x] * (uint32_t)n_haps + (uint32_t)h;
+      const unsigned int at = atomicAdd(cursor, 1u);
+      idx[at] = pair;
+      val[at] = out[pair];
+    }
+  }
+}
+
+// The pairs the fp64 kernel produced from a (record, haplotype) list (multi-pass classes), as (pair index, value).
 __global__ void k_collect_overrides(const uint2* __restrict__ items, const unsigned int* __restrict__ count,
                                     const int32_t* __restrict__ rec_rid, int n_haps, const double* __restrict__ out,
                                     uint32_t* __restrict__ idx, double* __restrict__ val, unsigned int* cursor) {
@@ -218,10 +242,8 @@ int sharded_compute_nccl(const std::vector<gklb_engine*>& engines, const gklb_pa
     gklb_engine* e = engines[g];
     CU(cudaSetDevice(e->device));
     CU(cudaStreamSynchronize(e->stream));
-    const unsigned int* hc = static_cast<const unsigned int*>(e->h_counters.p);
-    size_t fb = 0;
-    for (auto& c : e->classes) fb += hc[c.counter0];
-    e->stats.fallback_pairs = (int64_t)fb;
+    read_fallback_count(e);
+    const size_t fb = (size_t)e->stats.fallback_pairs;
     n_pairs[g] = (size_t)e->stats.pairs;
     n_ovr[g] = fb;
     pair_base[g] = total_pairs;
@@ -244,12 +266,21 @@ int sharded_compute_nccl(const std::vector<gklb_engine*>& engines, const gklb_pa
       k_narrow<<<e->num_sms * 4, 256, 0, e->stream>>>(static_cast<const double*>(e->d_out.p), static_cast<float*>(e->d_xf32.p),
                                                      n_pairs[g]);
       const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
-      for (auto& c : e->classes) {
-        if (!e->d_fb.p) break;
-        k_collect_overrides<<<e->num_sms, 256, 0, e->stream>>>(
-            static_cast<const uint2*>(e->d_fb.p) + c.fb_off, static_cast<const unsigned int*>(e->d_counters.p) + c.counter0,
-            reinterpret_cast<const int32_t*>(dm + c.meta_rid), H, static_cast<const double*>(e->d_out.p),
-            static_cast<uint32_t*>(e->d_xidx.p), static_cast<double*>(e->d_xval.p), static_cast<unsigned int*>(e->d_xcnt.p));
+      for (auto& en : e->entries) {  // every pair the plain fp32 sweep flagged carries a value computed in double
+        const ClassInst& c = e->classes[en.cls];
+        const Tile& t = e->tiles[en.tile];
+        const unsigned int* cnt = static_cast<const unsigned int*>(e->d_counters.p) + en.counter0;
+        if (c.kf->policy == POL_H2) {
+          k_collect_overrides_r2<<<e->num_sms, 256, 0, e->stream>>>(
+              static_cast<const uint2*>(e->d_r2.p) + en.r2_off, cnt, reinterpret_cast<const int32_t*>(dm + c.meta_rid),
+              dm + t.pmeta_off, t.n_pairs, H, static_cast<const double*>(e->d_out.p), static_cast<uint32_t*>(e->d_xidx.p),
+              static_cast<double*>(e->d_xval.p), static_cast<unsigned int*>(e->d_xcnt.p));
+        } else if (e->d_fb.p) {
+          k_collect_overrides<<<e->num_sms, 256, 0, e->stream>>>(
+              static_cast<const uint2*>(e->d_fb.p) + en.fb_off, cnt + 1, reinterpret_cast<const int32_t*>(dm + c.meta_rid), H,
+              static_cast<const double*>(e->d_out.p), static_cast<uint32_t*>(e->d_xidx.p), static_cast<double*>(e->d_xval.p),
+              static_cast<unsigned int*>(e->d_xcnt.p));
+        }
       }
       CU(cudaGetLastError());
     }

@@ -36,8 +36,9 @@ struct H2Class {           // the reads of one length class of one region agains
   const uint8_t* records;  // [n_rec][5 planes][stride]   (rows = G * K of the class kernel, packed by k_pack_reads)
   const int32_t* rec_rid;  // [n_rec] read index in the batch, -1 for filler records
   const int32_t* rec_len;  // [n_rec]
-  uint2* fb_items;         // (record, haplotype) of pairs whose scaled sum is < 1e-28f or not finite
-  unsigned int* fb_count;
+  uint2* r2_items;         // rerun items: (record, pair index | half mask << 30) of pairs whose scaled sum is
+  unsigned int* r2_count;  //   < 1e-28f or not finite (consumed by the range-extended rerun, pairhmm_r2.cuh)
+  unsigned int* fb_pairs;  // how many pairs that is (statistics)
   int n_rec;               // multiple of 32 / G
   int rows;                // G * K
   int stride;              // bytes per plane
@@ -315,6 +316,7 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
     // steps G..min(lenA, lenB) need no guard: every lane is inside both haplotypes
     const float2 sum = sw.run(hap, lenA, lenB, min(lenA, lenB), lenA + G - 1, t, initY, tbs);
     if (t == G - 1 && rid >= 0) {
+      unsigned int mask = 0;
 #pragma unroll
       for (int x = 0; x < 2; x++) {
         const int h = x == 0 ? pidxA[q] : pidxB[q];
@@ -322,9 +324,13 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
         double* o = out + (size_t)rid * n_haps_total + h;
         if (!finish_pair<VF1>(x == 0 ? sum.x : sum.y, (double)p.log10_init, o)) {
           *o = __longlong_as_double(0x7ff8000000000000LL);  // overwritten by the rerun
-          const unsigned int k = atomicAdd(cls.fb_count, 1u);
-          cls.fb_items[k] = make_uint2((unsigned)rec, (unsigned)h);
+          mask |= 1u << x;
         }
+      }
+      if (mask) {
+        const unsigned int k = atomicAdd(cls.r2_count, 1u);
+        cls.r2_items[k] = make_uint2((unsigned)rec, (unsigned)q | (mask << 30));
+        atomicAdd(cls.fb_pairs, (unsigned)__popc(mask));
       }
     }
   }

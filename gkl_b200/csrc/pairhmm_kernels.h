@@ -9,6 +9,7 @@
 
 #include "pairhmm_device.cuh"
 #include "pairhmm_h2.cuh"
+#include "pairhmm_r2.cuh"
 
 namespace gklb {
 
@@ -28,6 +29,12 @@ const KernelEntry* find_kernel(int policy, int G, int K, int warps, int multi, i
 // Multi-class kernels (8 warps per CTA): the fp64 task kernel (list_mode 0) and rerun-list kernel (1); the H2 sweep.
 const void* mega_kernel(int policy, int list_mode);
 const void* h2_mega_kernel();
+// Range-extended fp32 rerun (pairhmm_r2.cuh): per class (G = 4, 8, 16; K = 8..16; 8 warps) and multi-class.
+const void* r2_kernel(int G, int K);
+const void* r2_mega_kernel();
+const void* r2_kernel_g4(int K);
+const void* r2_kernel_g8(int K);
+const void* r2_kernel_g16(int K);
 
 cudaError_t launch_pack(const PackParams& p, cudaStream_t s);
 cudaError_t launch_fill_panel(uint8_t* image, int n_haps, int hap0, const int64_t* hap_off, const uint8_t* bases,

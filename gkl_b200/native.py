@@ -37,7 +37,7 @@ class Stats(C.Structure):
     _fields_ = [("pairs", C.c_int64), ("cells", C.c_int64), ("fallback_pairs", C.c_int64),
                 ("kernel_launches", C.c_int32), ("n_classes", C.c_int32),
                 ("h2d_ms", C.c_float), ("kernel_ms", C.c_float), ("d2h_ms", C.c_float),
-                ("sweep_ms", C.c_float), ("sweep_launches", C.c_int32)]
+                ("sweep_ms", C.c_float), ("sweep_launches", C.c_int32), ("fp64_pairs", C.c_int64)]
 
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_pairhmm_devices_in_use",

@@ -76,7 +76,8 @@ typedef struct gklb_pairhmm_batch {
 typedef struct gklb_pairhmm_stats {
   int64_t pairs;            /* n_reads * n_haps */
   int64_t cells;            /* sum over pairs of rslen * haplen */
-  int64_t fallback_pairs;   /* pairs re-run in fp64 because the scaled fp32 sum was < 1e-28f */
+  int64_t fallback_pairs;   /* pairs whose scaled fp32 sum was < 1e-28f (IntelPairHmm.cc:159): recomputed by the
+                               range-extended fp32 rerun, or by the fp64 kernel when its guards say so */
   int32_t kernel_launches;  /* kernels of this library launched by the last run */
   int32_t n_classes;        /* read-length classes (distinct kernel instantiations) used */
   float h2d_ms;             /* cudaEvent-timed phases of the last gklb_pairhmm_compute; 0 if not timed */
@@ -85,6 +86,7 @@ typedef struct gklb_pairhmm_stats {
   float sweep_ms;           /* device time of the forward-sweep task kernels alone in the last run (the
                                dominant kernel; excludes packing and the fp64 rerun of flagged pairs) */
   int32_t sweep_launches;   /* how many launches sweep_ms covers */
+  int64_t fp64_pairs;       /* of fallback_pairs, how many went through the fp64 kernel */
 } gklb_pairhmm_stats;
 
 typedef struct gklb_engine gklb_engine;
