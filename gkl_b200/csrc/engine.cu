@@ -478,6 +478,16 @@ void build_pair_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img, 
   }
 }
 
+// The range-extended fp32 rerun (pairhmm_r2.cuh) is built and tested but measured slower than the fp64 rerun it
+// would replace (profiles/r2_rerun_r2_vs_fp64.json), so it is opt-in: GKLB_R2=1.
+bool use_r2() {
+  static const bool v = [] {
+    const char* s = getenv("GKLB_R2");
+    return s && atoi(s) == 1;
+  }();
+  return v;
+}
+
 int tasks_per_warp_target() {
   // aim at ~this many tasks per resident warp: enough for the dynamic queue to balance the tail, few enough that
   // the per-task constant set-up stays negligible (GKLB_TASKS_PER_WARP overrides, for measurement)
@@ -585,6 +595,9 @@ void fill_h2_class(gklb_engine* e, const EntryInst& en, int warps, bool resident
   cls->r2_count = counters + en.counter0;
   cls->r2_items = static_cast<uint2*>(e->d_r2.p) + en.r2_off;
   cls->fb_pairs = counters + en.counter0 + 2;
+  cls->fb_count = counters + en.counter0 + 1;
+  cls->fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + en.fb_off : nullptr;
+  cls->use_r2 = use_r2() ? 1 : 0;
   cls->n_rec = c.n_rec;
   cls->rows = c.rows;
   cls->stride = c.stride;
@@ -619,10 +632,7 @@ void fill_r2_class(gklb_engine* e, const EntryInst& en, bool resident, R2Class* 
   const ClassInst& c = e->classes[en.cls];
   const Tile& t = e->tiles[en.tile];
   const Region& reg = e->regions[c.region];
-  static const bool force_fp64 = [] {
-    const char* v = getenv("GKLB_R2");  // GKLB_R2=0: every flagged pair goes to the fp64 kernel (measurement)
-    return v && atoi(v) == 0;
-  }();
+  const bool force_fp64 = false;
   memset(cls, 0, sizeof(*cls));
   const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
   unsigned int* counters = static_cast<unsigned int*>(e->d_counters.p);
@@ -831,7 +841,9 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
     std::vector<int> h2all;  // every H2 entry, forced ones included (their lists have the same format)
     for (int i = 0; i < n_ent; i++)
       if (cls_of(ents[i]).kf->policy == POL_H2) h2all.push_back(i);
-    if (h2_mega) {
+    if (!use_r2()) {
+      // the H2 sweep appended its flagged pairs straight to the fp64 lists
+    } else if (h2_mega) {
       R2MegaParams mp;
       memset(&mp, 0, sizeof(mp));
       fill_h2_common(e, dm + g.pmeta_off, g.pbytes, &mp.com);

@@ -39,6 +39,9 @@ struct H2Class {           // the reads of one length class of one region agains
   uint2* r2_items;         // rerun items: (record, pair index | half mask << 30) of pairs whose scaled sum is
   unsigned int* r2_count;  //   < 1e-28f or not finite (consumed by the range-extended rerun, pairhmm_r2.cuh)
   unsigned int* fb_pairs;  // how many pairs that is (statistics)
+  uint2* fb_items;         // use_r2 == 0: the flagged pairs go straight to the fp64 kernel as (record, haplotype)
+  unsigned int* fb_count;
+  int use_r2;
   int n_rec;               // multiple of 32 / G
   int rows;                // G * K
   int stride;              // bytes per plane
@@ -328,9 +331,18 @@ __device__ __forceinline__ void run_task_h2(const H2Common& p, const H2Class& cl
         }
       }
       if (mask) {
-        const unsigned int k = atomicAdd(cls.r2_count, 1u);
-        cls.r2_items[k] = make_uint2((unsigned)rec, (unsigned)q | (mask << 30));
         atomicAdd(cls.fb_pairs, (unsigned)__popc(mask));
+        if (cls.use_r2) {
+          const unsigned int k = atomicAdd(cls.r2_count, 1u);
+          cls.r2_items[k] = make_uint2((unsigned)rec, (unsigned)q | (mask << 30));
+        } else {
+#pragma unroll
+          for (int x = 0; x < 2; x++)
+            if (mask & (1u << x)) {
+              const unsigned int k = atomicAdd(cls.fb_count, 1u);
+              cls.fb_items[k] = make_uint2((unsigned)rec, (unsigned)(x == 0 ? pidxA[q] : pidxB[q]));
+            }
+        }
       }
     }
   }
