@@ -8,6 +8,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <mutex>
 #include <vector>
 
@@ -108,8 +109,22 @@ struct PdEngine {
   gklb_pdhmm_stats stats{};
 };
 
+// The process-global surface is a pool of engines, like the PairHMM one (engine_global.cu): init/done are reference
+// counted (the reference's doneNative only frees its DP tables and several IntelPDHMM instances may live side by
+// side, pdhmm/IntelPDHMM.cc:43-60,246-249), every compute call borrows an engine of its own, so concurrent Java
+// threads do not serialise on one lock, and the last done frees the idle engines.
+struct PdSlot { struct PdEngine* e = nullptr; bool busy = false; };
 std::mutex g_mu;
-PdEngine* g_pd = nullptr;
+std::condition_variable g_cv;
+std::vector<PdSlot> g_slots;
+int g_refs = 0;
+bool g_inited = false;
+int g_carry_state = 1;
+bool g_allow_v2 = true;
+int g_device = 0;
+PdEngine* g_last = nullptr;   // engine of the last finished compute call: what last_stats / time_runs refer to
+gklb_pdhmm_stats g_last_stats{};
+constexpr int kMaxPdEngines = 4;
 
 void destroy(PdEngine* e) {
   if (!e) return;
@@ -278,17 +293,13 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
 
 }  // namespace
 
-extern "C" {
+namespace {
 
-int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_memory_mb) {
-  (void)openmp_setting; (void)max_threads; (void)avx_level; (void)max_memory_mb;
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (g_pd) { destroy(g_pd); g_pd = nullptr; }
+int create_pd_engine(PdEngine** out) {
   int n = 0;
   cudaError_t ce = cudaGetDeviceCount(&n);
   if (ce != cudaSuccess || n <= 0) return gklb_internal_fail(GKLB_ERR_NO_DEVICE, "no CUDA device (%s)", cudaGetErrorString(ce));
-  const char* dev = getenv("GKLB_DEVICE");
-  const int device = dev ? atoi(dev) : 0;
+  const int device = g_device;
   if (device < 0 || device >= n) return gklb_internal_fail(GKLB_ERR_NO_DEVICE, "device %d out of range", device);
   cudaDeviceProp prop;
   CU(cudaGetDeviceProperties(&prop, device));
@@ -297,10 +308,8 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
   PdEngine* e = new PdEngine;
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
-  const char* rs = getenv("GKLB_PDHMM_ROW_STATE");
-  e->carry_state = (rs && !strcmp(rs, "reset")) ? 0 : 1;
-  const char* kv = getenv("GKLB_PDHMM_KERNEL");  // "1": the pair-at-a-time kernel for every batch (measurement)
-  e->allow_v2 = !(kv && !strcmp(kv, "1"));
+  e->carry_state = g_carry_state;
+  e->allow_v2 = g_allow_v2;
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) CU(cudaEventCreate(&ev));
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, false>),
@@ -312,50 +321,148 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
   CU(cudaMemcpy(e->tables.p, t.q2err, sizeof(t.q2err), cudaMemcpyHostToDevice));
   CU(cudaMemcpy(static_cast<double*>(e->tables.p) + (kMaxQual + 1), t.mm, sizeof(t.mm), cudaMemcpyHostToDevice));
-  g_pd = e;
+  *out = e;
+  return GKLB_OK;
+}
+
+int acquire_pd(PdEngine** out) {
+  std::unique_lock<std::mutex> lk(g_mu);
+  if (!g_inited) return gklb_internal_fail(GKLB_ERR_STATE, "gklb_pdhmm_init has not been called");
+  for (;;) {
+    for (auto& s : g_slots)
+      if (!s.busy && s.e) { s.busy = true; *out = s.e; return GKLB_OK; }
+    if ((int)g_slots.size() < kMaxPdEngines) {
+      g_slots.push_back(PdSlot{nullptr, true});
+      const size_t idx = g_slots.size() - 1;
+      lk.unlock();
+      PdEngine* e = nullptr;
+      const int rc = create_pd_engine(&e);
+      lk.lock();
+      if (rc) {
+        g_slots.erase(g_slots.begin() + idx);
+        g_cv.notify_all();
+        return rc;
+      }
+      g_slots[idx].e = e;
+      *out = e;
+      return GKLB_OK;
+    }
+    g_cv.wait(lk);
+  }
+}
+
+void release_pd(PdEngine* e) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& s : g_slots)
+    if (s.e == e) s.busy = false;
+  g_last = e;
+  g_last_stats = e->stats;
+  g_cv.notify_all();
+}
+
+}  // namespace
+
+extern "C" {
+
+int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_memory_mb) {
+  (void)openmp_setting; (void)max_threads; (void)avx_level; (void)max_memory_mb;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const char* dev = getenv("GKLB_DEVICE");
+    const int device = dev ? atoi(dev) : 0;
+    const char* rs = getenv("GKLB_PDHMM_ROW_STATE");
+    const int carry = (rs && !strcmp(rs, "reset")) ? 0 : 1;
+    const char* kv = getenv("GKLB_PDHMM_KERNEL");  // "1": the pair-at-a-time kernel for every batch (measurement)
+    const bool allow_v2 = !(kv && !strcmp(kv, "1"));
+    if (g_inited && (device != g_device || carry != g_carry_state || allow_v2 != g_allow_v2)) {
+      // a different configuration: idle engines are rebuilt lazily with it
+      for (size_t i = 0; i < g_slots.size();)
+        if (!g_slots[i].busy) { if (g_last == g_slots[i].e) g_last = nullptr; destroy(g_slots[i].e); g_slots.erase(g_slots.begin() + i); } else i++;
+    }
+    g_device = device;
+    g_carry_state = carry;
+    g_allow_v2 = allow_v2;
+    g_inited = true;
+    g_refs++;
+  }
+  PdEngine* e = nullptr;  // one engine now: a missing device must fail initialize(), not the first compute
+  const int rc = acquire_pd(&e);
+  if (rc) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (--g_refs == 0) g_inited = false;
+    return rc;
+  }
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& s : g_slots)
+      if (s.e == e) s.busy = false;
+    g_cv.notify_all();
+  }
   return GKLB_OK;
 }
 
 int gklb_pdhmm_compute(const gklb_pdhmm_batch* batch, double* likelihoods) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_pd) return gklb_internal_fail(GKLB_ERR_STATE, "gklb_pdhmm_init has not been called");
-  return compute(g_pd, batch, 0, 0, likelihoods);
+  PdEngine* e = nullptr;
+  int rc = acquire_pd(&e);
+  if (rc) return rc;
+  rc = compute(e, batch, 0, 0, likelihoods);
+  release_pd(e);
+  return rc;
 }
 
 int gklb_pdhmm_compute_cross(const gklb_pdhmm_batch* operands, int32_t n_reads, int32_t n_haps, double* likelihoods) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_pd) return gklb_internal_fail(GKLB_ERR_STATE, "gklb_pdhmm_init has not been called");
-  if (n_reads <= 0 || n_haps <= 0) return gklb_internal_fail(GKLB_ERR_INVALID, "empty read or haplotype array");
-  return compute(g_pd, operands, n_reads, n_haps, likelihoods);
+  if (n_reads <= 0 || n_haps <= 0) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_inited) return gklb_internal_fail(GKLB_ERR_STATE, "gklb_pdhmm_init has not been called");
+    return gklb_internal_fail(GKLB_ERR_INVALID, "empty read or haplotype array");
+  }
+  PdEngine* e = nullptr;
+  int rc = acquire_pd(&e);
+  if (rc) return rc;
+  rc = compute(e, operands, n_reads, n_haps, likelihoods);
+  release_pd(e);
+  return rc;
 }
 
 int gklb_pdhmm_done(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_pd) { destroy(g_pd); g_pd = nullptr; }
+  if (g_refs > 0) g_refs--;
+  if (g_refs == 0) {
+    for (size_t i = 0; i < g_slots.size();)
+      if (!g_slots[i].busy) { if (g_last == g_slots[i].e) g_last = nullptr; destroy(g_slots[i].e); g_slots.erase(g_slots.begin() + i); } else i++;
+  }
   return GKLB_OK;
 }
 
 int gklb_pdhmm_last_stats(gklb_pdhmm_stats* out) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_pd || !out) return gklb_internal_fail(GKLB_ERR_STATE, "no engine");
-  *out = g_pd->stats;
+  if (!out) return gklb_internal_fail(GKLB_ERR_INVALID, "out is null");
+  *out = g_last_stats;
   return GKLB_OK;
 }
 
 int gklb_pdhmm_time_runs(int iters, float* ms_per_run) {
-  std::lock_guard<std::mutex> lk(g_mu);
-  if (!g_pd || !g_pd->have_last || iters <= 0 || !ms_per_run) return gklb_internal_fail(GKLB_ERR_STATE, "nothing to time");
-  PdEngine* e = g_pd;
-  CU(cudaSetDevice(e->device));
-  CU(cudaEventRecord(e->ev[0], e->stream));
-  for (int i = 0; i < iters; i++) {
-    int rc = launch(e);
-    if (rc) return rc;
+  PdEngine* e = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& s : g_slots)
+      if (s.e == g_last && g_last && !s.busy) { s.busy = true; e = s.e; }
   }
-  CU(cudaEventRecord(e->ev[1], e->stream));
-  CU(cudaEventSynchronize(e->ev[1]));
+  if (!e || !e->have_last || iters <= 0 || !ms_per_run) {
+    if (e) release_pd(e);
+    return gklb_internal_fail(GKLB_ERR_STATE, "nothing to time");
+  }
+  int rc = GKLB_OK;
   float ms = 0;
-  CU(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
+  do {
+    if (cudaSetDevice(e->device) != cudaSuccess || cudaEventRecord(e->ev[0], e->stream) != cudaSuccess) { rc = GKLB_ERR_CUDA; break; }
+    for (int i = 0; i < iters && rc == GKLB_OK; i++) rc = launch(e);
+    if (rc) break;
+    if (cudaEventRecord(e->ev[1], e->stream) != cudaSuccess || cudaEventSynchronize(e->ev[1]) != cudaSuccess) { rc = GKLB_ERR_CUDA; break; }
+    cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]);
+  } while (0);
+  release_pd(e);
+  if (rc) return gklb_internal_fail(rc, "timing run failed");
   *ms_per_run = ms / iters;
   return GKLB_OK;
 }

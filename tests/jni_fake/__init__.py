@@ -12,7 +12,7 @@ SO = HERE / "libfakejvm.so"
 def build():
     src = HERE / "fake_jvm.cc"
     if not SO.exists() or SO.stat().st_mtime < src.stat().st_mtime:
-        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-o", str(SO), str(src), "-ldl"], check=True)
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-o", str(SO), str(src), "-ldl"], check=True)
 
 
 def _lib():
@@ -37,6 +37,25 @@ def pairhmm(lib_path, b, use_double=False, fault=0):
                            p(b.ins_gop), p(b.del_gop), p(b.gcp), p(b.hap_off), p(b.hap_bases), int(use_double),
                            int(fault), p(out), ec, em, leaks)
     return rc, out[:b.n_reads * b.n_haps], ec.value.decode(), em.value.decode(), (leaks[0], leaks[1])
+
+
+def pairhmm_threads(lib_path, batches, n_threads: int, rounds: int = 1):
+    """n_threads concurrent callers, each with its own JNIEnv and IntelPairHmm instance, share `batches` round-robin.
+    Returns (failed_calls, [likelihood arrays], last exception message, (leaked local refs, leaked pins))."""
+    l = _lib()
+    n = len(batches)
+    outs = [np.zeros(max(1, b.n_reads * b.n_haps), dtype=np.float64) for b in batches]
+    arr_i = lambda vals: (C.c_int * n)(*vals)
+    arr_p = lambda arrays: (C.c_void_p * n)(*[a.ctypes.data for a in arrays])
+    em = C.create_string_buffer(256)
+    leaks = (C.c_long * 2)()
+    rc = l.fakejvm_pairhmm_mt(str(lib_path).encode(), int(n_threads), n, arr_i([b.n_reads for b in batches]),
+                              arr_i([b.n_haps for b in batches]), arr_p([b.read_off for b in batches]),
+                              arr_p([b.read_bases for b in batches]), arr_p([b.read_quals for b in batches]),
+                              arr_p([b.ins_gop for b in batches]), arr_p([b.del_gop for b in batches]),
+                              arr_p([b.gcp for b in batches]), arr_p([b.hap_off for b in batches]),
+                              arr_p([b.hap_bases for b in batches]), arr_p(outs), int(rounds), leaks, em)
+    return rc, [o[:b.n_reads * b.n_haps] for o, b in zip(outs, batches)], em.value.decode(), (leaks[0], leaks[1])
 
 
 def pdhmm(lib_path, b, object_api=False, n_reads=0, n_haps=0, fault=0):

@@ -7,7 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../gkl_b200/csrc/jni_min.h"
@@ -34,7 +36,7 @@ struct Vm {
   std::vector<ClassObj*> found;
   std::vector<std::pair<double*, DblArr*>> dbl_copies;
 };
-Vm* g_vm = nullptr;
+thread_local Vm* g_vm = nullptr;  // one fake JVM state per thread, like a JNIEnv
 
 jclass fFindClass(JNIEnv*, const char* name) {
   ClassObj* c = new ClassObj;
@@ -250,6 +252,80 @@ int fakejvm_pairhmm(const char* lib_path, int n_reads, int n_haps, const int64_t
   return exc ? 1 : 0;
 }
 
+
+// Concurrent callers: n_threads threads, each with its own JNIEnv, its own IntelPairHmm "instance" (initNative at
+// the start, doneNative at the end) and every n_threads-th region; every region is computed `rounds` times.
+// GATK's Spark executors call computeLikelihoods from several threads (IntelPairHmm.java:65 synchronises only load).
+// Returns the number of calls that ended with a pending exception (message of the last one copied out).
+int fakejvm_pairhmm_mt(const char* lib_path, int n_threads, int n_regions, const int* n_reads, const int* n_haps,
+                       const int64_t* const* read_off, const uint8_t* const* bases, const uint8_t* const* quals,
+                       const uint8_t* const* ins, const uint8_t* const* del, const uint8_t* const* gcp,
+                       const int64_t* const* hap_off, const uint8_t* const* haps, double* const* outs, int rounds,
+                       long* leaks, char* exc_msg) {
+  void* h = dlopen(lib_path, RTLD_NOW | RTLD_LOCAL);
+  if (!h) { snprintf(exc_msg, 255, "%s", dlerror()); return -2; }
+  InitFn init = (InitFn)dlsym(h, "Java_com_intel_gkl_pairhmm_IntelPairHmm_initNative");
+  ComputeFn compute = (ComputeFn)dlsym(h, "Java_com_intel_gkl_pairhmm_IntelPairHmm_computeLikelihoodsNative");
+  DoneFn done = (DoneFn)dlsym(h, "Java_com_intel_gkl_pairhmm_IntelPairHmm_doneNative");
+  if (!init || !compute || !done) return -3;
+  std::atomic<int> failures(0);
+  std::atomic<long> leaked_locals(0), leaked_pins(0);
+  std::vector<std::string> msgs(n_threads);
+  std::vector<std::thread> th;
+  for (int t = 0; t < n_threads; t++) {
+    th.emplace_back([&, t] {
+      Vm vm;
+      init_vm(&vm);
+      g_vm = &vm;
+      ClassObj read_cls, hap_cls, self_cls;
+      read_cls.fields = {"readBases", "readQuals", "insertionGOP", "deletionGOP", "overallGCP"};
+      hap_cls.fields = {"haplotypeBases"};
+      Obj self;
+      init(&vm.env, &self_cls, &read_cls, &hap_cls, JNI_FALSE, 1);
+      if (vm.exc) { failures++; msgs[t] = vm.exc_class + ": " + vm.exc_msg; g_vm = nullptr; return; }
+      for (int round = 0; round < rounds; round++)
+        for (int k = t; k < n_regions; k += n_threads) {
+          ObjArr reads, hap_arr;
+          for (int r = 0; r < n_reads[k]; r++) {
+            Holder* o = new Holder;
+            o->cls = &read_cls;
+            const int64_t a = read_off[k][r], b = read_off[k][r + 1];
+            o->vals = {make_bytes(bases[k], a, b), make_bytes(quals[k], a, b), make_bytes(ins[k], a, b), make_bytes(del[k], a, b),
+                       make_bytes(gcp[k], a, b)};
+            reads.elems.push_back(o);
+          }
+          for (int i = 0; i < n_haps[k]; i++) {
+            Holder* o = new Holder;
+            o->cls = &hap_cls;
+            o->vals = {make_bytes(haps[k], hap_off[k][i], hap_off[k][i + 1])};
+            hap_arr.elems.push_back(o);
+          }
+          DblArr result;
+          result.data.assign((size_t)n_reads[k] * n_haps[k], -12345.0);
+          compute(&vm.env, &self, &reads, &hap_arr, &result);
+          if (vm.exc) {
+            failures++;
+            msgs[t] = vm.exc_class + ": " + vm.exc_msg;
+            vm.exc = false;
+          } else {
+            memcpy(outs[k], result.data.data(), sizeof(double) * result.data.size());
+          }
+          for (auto* o : reads.elems) { for (auto* v : static_cast<Holder*>(o)->vals) delete v; delete static_cast<Holder*>(o); }
+          for (auto* o : hap_arr.elems) { for (auto* v : static_cast<Holder*>(o)->vals) delete v; delete static_cast<Holder*>(o); }
+        }
+      done(&vm.env, &self);
+      leaked_locals += vm.locals;
+      leaked_pins += vm.pins;
+      g_vm = nullptr;
+    });
+  }
+  for (auto& t : th) t.join();
+  leaks[0] = leaked_locals;
+  leaks[1] = leaked_pins;
+  for (auto& m : msgs)
+    if (!m.empty()) snprintf(exc_msg, 255, "%s", m.c_str());
+  return failures;
+}
 
 // PDHMM binding (com.intel.gkl.pdhmm.IntelPDHMM).  object_api = 0: computePDHMMNative on the flat arrays
 // (n pairs).  object_api = 1: computeLikelihoodsNative on n_reads ReadDataHolders x n_haps HaplotypeDataHolders

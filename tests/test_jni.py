@@ -159,3 +159,24 @@ def test_smithwaterman_align_through_jni():
     # GetPrimitiveArrayCritical failing -> IllegalArgumentException("Arrays aren't valid."), IntelSmithWaterman.cc:82-104
     rc, _, _, cls, msg, leaks = jni_fake.smithwaterman(LIB, refs[0], alts[0], PARAMS[0], 9, fault=1)
     assert rc == 1 and cls == "java/lang/IllegalArgumentException" and msg == "Arrays aren't valid." and leaks == (0, 0)
+
+
+@pytest.mark.gpu
+def test_concurrent_callers_through_the_jni_layer(monkeypatch):
+    """8 threads x 32 regions over the fake JVM, every thread its own JNIEnv and IntelPairHmm instance (init at the
+    start, done at the end, while other threads are still computing): the engine pool must hand every call its own
+    engine, results must be bit-identical to serial calls, no reference or pin may leak.  GKL's state is read-only
+    after initNative, so GATK may and does call computeLikelihoods concurrently (IntelPairHmm.java:65)."""
+    import torch
+    if torch.cuda.device_count() >= 2:
+        monkeypatch.setenv("GKLB_DEVICES", "all")   # concurrent calls spread over the GPUs of the box
+    regions = synth.config3(32, seed=21)
+    eng = native.Engine(0, False)
+    serial = [eng.compute(r) for r in regions]
+    eng.close()
+    failed, outs, msg, leaks = jni_fake.pairhmm_threads(LIB, regions, n_threads=8, rounds=2)
+    assert failed == 0, msg
+    assert leaks == (0, 0)
+    for a, b in zip(serial, outs):
+        assert np.array_equal(a, b)
+    assert native.lib().gklb_pairhmm_engines_alive() == 0   # the last doneNative freed the pool
