@@ -32,22 +32,6 @@
 
 namespace gklb {
 
-namespace {
-thread_local std::string t_last_error;
-}
-
-int fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  t_last_error = buf;
-  return code;
-}
-const std::string& last_error_string() { return t_last_error; }
-void set_last_error(const std::string& s) { t_last_error = s; }
-
 cudaError_t DevBuf::ensure(size_t bytes) {
   if (bytes <= cap) return cudaSuccess;
   if (p) cudaFree(p);
@@ -81,17 +65,6 @@ void HostBuf::release() {
 }
 
 }  // namespace gklb
-
-// shared with pdhmm_engine.cu / sw_engine.cu
-int gklb_internal_fail(int code, const char* fmt, ...) {
-  char buf[512];
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(buf, sizeof(buf), fmt, ap);
-  va_end(ap);
-  gklb::set_last_error(buf);
-  return code;
-}
 
 namespace gklb {
 
@@ -1497,21 +1470,6 @@ int gklb_engine_time_runs(gklb_engine* e, int iters, float* ms_per_run) {
   CU(cudaEventElapsedTime(&ms, e->ev[0], e->ev[1]));
   *ms_per_run = ms / (float)iters;
   return GKLB_OK;
-}
-
-const char* gklb_last_error(void) { return last_error_string().c_str(); }
-
-const char* gklb_version(void) { return "gkl_b200 0.2 (sm_100a)"; }
-
-int gklb_device_count(void) {
-  int n = 0;
-  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
-  int ok = 0;
-  for (int i = 0; i < n; i++) {
-    cudaDeviceProp p;
-    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
-  }
-  return ok;
 }
 
 const void* gklb_pairhmm_table(int which, int* n) {

@@ -92,16 +92,6 @@ int pipeline_block_reads() {
 
 extern "C" {
 
-// System.load() fails (UnsatisfiedLinkError -> NativeLibraryLoader.load returns false ->
-// IntelPairHmm.load() returns false -> GATK falls back to its Java PairHMM) when this machine has no
-// sm_100 GPU: that is the reference's own failover path (NativeLibraryLoader.java:114-133,
-// IntelPairHmm.java:66-82); there is no CPU implementation inside this library.
-JNIEXPORT jint JNICALL JNI_OnLoad(JavaVM* vm, void* reserved) {
-  (void)vm;
-  (void)reserved;
-  return gklb_device_count() > 0 ? JNI_VERSION_1_6 : JNI_ERR;
-}
-
 JNIEXPORT void JNICALL Java_com_intel_gkl_pairhmm_IntelPairHmm_initNative(JNIEnv* env, jclass cls,
                                                                             jclass readDataHolder,
                                                                             jclass haplotypeDataHolder,

@@ -15,7 +15,9 @@ import numpy as np
 from .batch import PairHmmBatch
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libgkl_pairhmm.so"
+# GKLB_LIB_DIR: another build of the libraries, e.g. gkl_b200/lib_exp (make EXPERIMENTAL=1: measurement-only kernels)
+LIB_DIR = Path(os.environ["GKLB_LIB_DIR"]).resolve() if os.environ.get("GKLB_LIB_DIR") else PKG / "lib"
+LIB_PATH = LIB_DIR / "libgkl_pairhmm.so"
 
 OK, ERR_OOM, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_STATE = range(6)
 
@@ -53,7 +55,7 @@ _lib = None
 
 def build(experimental: bool = False) -> None:
     """Compile the library in-tree (nvcc cross-compiles sm_100a without a GPU)."""
-    cmd = ["make", "-s", "-C", str(PKG / "csrc")]
+    cmd = ["make", "-s", "-j", str(min(8, os.cpu_count() or 1)), "-C", str(PKG / "csrc")]
     if experimental:
         cmd.append("EXPERIMENTAL=1")
     subprocess.run(cmd, check=True)

@@ -54,23 +54,31 @@ def test_library_exports_every_symbol_of_the_header():
     for name in declared:
         assert hasattr(lib, name), name
     assert b"sm_100a" in lib.gklb_version()
-    # the PDHMM surface (include/gklb_pdhmm.h), exported by the same binary under both library names
+    # the PDHMM surface (include/gklb_pdhmm.h): exported by libgkl_pairhmm.so (which holds everything) and by
+    # libgkl_pdhmm.so (the PDHMM engine + its JNI exports alone, under the name GKL's loader asks for)
     from gkl_b200 import pdhmm
     pd_header = (ROOT / "include" / "gklb_pdhmm.h").read_text()
     pd_declared = set(re.findall(r"GKLB_API\s+[\w\s\*]+?\b(gklb_\w+)\s*\(", pd_header))
     assert pd_declared == set(pdhmm.PD_EXPORTS), pd_declared ^ set(pdhmm.PD_EXPORTS)
     import ctypes
     pd_lib = ctypes.CDLL(str(native.LIB_PATH.with_name("libgkl_pdhmm.so")))
-    for name in pd_declared | declared:
+    common = {"gklb_last_error", "gklb_version", "gklb_device_count"}
+    for name in pd_declared | common:
         assert hasattr(pd_lib, name), name
+        assert hasattr(lib, name), name
+    for name in ("initNative", "computeLikelihoodsNative", "computePDHMMNative", "doneNative"):
+        assert hasattr(pd_lib, "Java_com_intel_gkl_pdhmm_IntelPDHMM_" + name)
+    assert hasattr(pd_lib, "JNI_OnLoad") and not hasattr(pd_lib, "gklb_pairhmm_compute")
     # the Smith-Waterman surface (include/gklb_sw.h), third library name
     from gkl_b200 import smithwaterman
     sw_header = (ROOT / "include" / "gklb_sw.h").read_text()
     sw_declared = set(re.findall(r"GKLB_API\s+[\w\s\*]+?\b(gklb_\w+)\s*\(", sw_header))
     assert sw_declared == set(smithwaterman.SW_EXPORTS), sw_declared ^ set(smithwaterman.SW_EXPORTS)
     sw_lib = ctypes.CDLL(str(native.LIB_PATH.with_name("libgkl_smithwaterman.so")))
-    for name in sw_declared:
+    for name in sw_declared | common:
         assert hasattr(sw_lib, name), name
+        assert hasattr(lib, name), name
+    assert hasattr(sw_lib, "Java_com_intel_gkl_smithwaterman_IntelSmithWaterman_alignNative") and hasattr(sw_lib, "JNI_OnLoad")
 
 
 def test_host_tables_are_bit_identical_to_the_oracle():
