@@ -376,3 +376,32 @@ def test_nccl_sharding_is_bit_identical_to_direct_sharding(monkeypatch):
     assert np.array_equal(outs["direct"], outs["nccl"])
     ref = checker(big.read_slice(0, 64))
     assert rel(outs["nccl"][:64 * big.n_haps], ref).max() <= REL_TOL
+
+
+def test_global_surface_lifecycle_is_reference_counted():
+    """GKL's doneNative is empty and initNative only sets flags (IntelPairHmm.cc:55-118,189-192): several IntelPairHmm
+    instances initialise and close independently.  Here init/done are reference counted over a pool of engines."""
+    lib = native.lib()
+    b = synth.config2(40, 8)
+    ref = native.Engine(0, False)
+    want = ref.compute(b)
+    ref.close()
+    assert native.global_init(False, 1) == 1          # instance A
+    assert native.global_init(False, 1) == 1          # instance B: cheap, engines are kept
+    alive = lib.gklb_pairhmm_engines_alive()
+    assert alive >= 1
+    native.global_done()                              # A closes
+    assert lib.gklb_pairhmm_engines_alive() == alive  # ... B still holds a reference
+    assert np.array_equal(native.global_compute(b), want)
+    native.global_done()                              # B closes: the idle engines are freed
+    assert lib.gklb_pairhmm_engines_alive() == 0
+    native.global_done()                              # idempotent
+    assert np.array_equal(native.global_compute(b), want)  # a late compute creates an engine again
+    native.global_done()
+    assert lib.gklb_pairhmm_engines_alive() == 0
+    # precision follows the last initialize, as GKL's g_use_double does
+    native.global_init(True, 1)
+    d = native.Engine(0, True)
+    assert np.array_equal(native.global_compute(b), d.compute(b))
+    d.close()
+    native.global_done()
