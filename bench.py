@@ -245,20 +245,30 @@ def run_ours(args):
     sweep_kernel = eng.sweep_kernel()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    from gkl_b200 import multi
     panel_buf = hap_dev if rank == 0 else torch.empty_like(hap_dev)
-    gather_bufs = [torch.empty(pairs, dtype=torch.float64, device=dev) for _ in range(world)] if (distributed and rank == 0) else None
+    gather_bufs, cap, packed_bytes = None, 0, 0
+    if distributed:
+        # capacity of the override list (pairs that took the fp64 rerun), agreed once outside the timed region
+        eng.run()
+        eng.fetch(pairs)
+        capt = torch.tensor([int(eng.stats().fallback_pairs)], dtype=torch.int64, device=dev)
+        dist.all_reduce(capt, op=dist.ReduceOp.MAX)
+        cap = (int(capt[0]) * 5 // 4 + 4096) // 1024 * 1024
+        _, packed_bytes = eng.narrow(cap)
+        if rank == 0:
+            gather_bufs = [torch.empty(packed_bytes, dtype=torch.uint8, device=dev) for _ in range(world)]
 
     def step():
         if distributed:
             # the haplotype panel travels from GPU 0 over NVLink (one broadcast of the packed bases; the lengths are
-            # part of the staged batch) and is consumed by this step's sweep; the likelihood slabs go back to GPU 0
+            # part of the staged batch) and is consumed by this step's sweep; the results go back to GPU 0 as what
+            # the reference's values really are: an fp32 per pair + (index, fp64) overrides for the rerun pairs
             dist.broadcast(panel_buf, src=0)
             eng.update_haps_device(panel_buf)
         eng.run()
         if distributed:
-            res = torch.as_tensor(_DevArray(eng.result_device_ptr(), pairs), device=dev)
-            dist.gather(res, gather_bufs, dst=0)
+            ptr, nbytes = eng.narrow(cap)
+            dist.gather(torch.as_tensor(_DevArray(ptr, nbytes, "|u1"), device=dev), gather_bufs, dst=0)
 
     for _ in range(args.warmup):
         step()
@@ -351,8 +361,8 @@ def run_ours(args):
             "cells_per_step": total_cells, "pairs_per_gpu": pairs, "fallback_pairs_rank0": fallback,
             "l2": "flushed between steps (256 MiB write)",
             "parallelism": (f"reads sharded over {world} GPUs, one process per GPU; per step one NCCL broadcast of the "
-                            "haplotype panel and one NCCL gather of the likelihood slabs to GPU 0") if world > 1
-                           else "single GPU",
+                            "haplotype panel and one NCCL gather of the results (fp32 matrix + fp64 overrides of the rerun "
+                            f"pairs, {packed_bytes} bytes per GPU) to GPU 0") if world > 1 else "single GPU",
             "parity_max_rel_err_all_pairs_vs_cpu_baseline": parity,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": int(5 * int(b.read_off[-1]) + int(b.hap_off[-1]) + 8 * (b.n_reads + 1)

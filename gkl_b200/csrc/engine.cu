@@ -453,7 +453,7 @@ void build_pair_image(const Tile& t, const gklb_pairhmm_batch* b, uint8_t* img, 
 
 // The range-extended fp32 rerun (pairhmm_r2.cuh) is built and tested but measured slower than the fp64 rerun it
 // would replace (profiles/r2_rerun_r2_vs_fp64.json), so it is opt-in: GKLB_R2=1.
-bool use_r2() {
+bool use_r2_env() {
   static const bool v = [] {
     const char* s = getenv("GKLB_R2");
     return s && atoi(s) == 1;
@@ -570,7 +570,7 @@ void fill_h2_class(gklb_engine* e, const EntryInst& en, int warps, bool resident
   cls->fb_pairs = counters + en.counter0 + 2;
   cls->fb_count = counters + en.counter0 + 1;
   cls->fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + en.fb_off : nullptr;
-  cls->use_r2 = use_r2() ? 1 : 0;
+  cls->use_r2 = use_r2_env() ? 1 : 0;
   cls->n_rec = c.n_rec;
   cls->rows = c.rows;
   cls->stride = c.stride;
@@ -814,7 +814,7 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
     std::vector<int> h2all;  // every H2 entry, forced ones included (their lists have the same format)
     for (int i = 0; i < n_ent; i++)
       if (cls_of(ents[i]).kf->policy == POL_H2) h2all.push_back(i);
-    if (!use_r2()) {
+    if (!use_r2_env()) {
       // the H2 sweep appended its flagged pairs straight to the fp64 lists
     } else if (h2_mega) {
       R2MegaParams mp;
@@ -893,6 +893,8 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
 }
 
 }  // namespace
+
+bool use_r2() { return use_r2_env(); }
 
 void read_fallback_count(gklb_engine* e) {
   int64_t fb = 0, f64 = 0;

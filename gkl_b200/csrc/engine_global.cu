@@ -293,6 +293,7 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
       total_stats.pairs += st.pairs;
       total_stats.cells += st.cells;
       total_stats.fallback_pairs += st.fallback_pairs;
+      total_stats.fp64_pairs += st.fp64_pairs;
       total_stats.kernel_launches += st.kernel_launches;
       total_stats.n_classes = std::max(total_stats.n_classes, st.n_classes);
       total_stats.h2d_ms = std::max(total_stats.h2d_ms, st.h2d_ms);
@@ -313,25 +314,94 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
 // launch group (engine.cu: plan_groups), so that a dozen small regions fill the GPU like one large batch;
 // likelihoods[r] receives region r's matrix.  Results are bit-identical to one gklb_pairhmm_compute per region.
 int gklb_pairhmm_compute_multi(const gklb_pairhmm_batch* batches, int n_batches, double* const* likelihoods) {
+  std::vector<int> devices;
   {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!g_inited) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
+    devices = g_devices;
   }
   if (n_batches < 0 || (n_batches > 0 && (!batches || !likelihoods))) return fail(GKLB_ERR_INVALID, "bad region array");
   if (n_batches == 0) return GKLB_OK;
-  gklb_engine* e = nullptr;
-  int rc = acquire(-1, &e);
-  if (rc) return rc;
-  {
-    std::lock_guard<std::mutex> lk(e->mu);
-    rc = do_compute(e, batches, n_batches, likelihoods);
+  int rc;
+  for (int r = 0; r < n_batches; r++)
+    if ((rc = validate_batch(&batches[r]))) return rc;
+  // Regions large enough to be sharded over the devices go through gklb_pairhmm_compute one by one; the others are
+  // coalesced into jobs of bounded size (the staging buffer is pinned memory), balanced over the configured devices
+  // when there is enough work for several, each job on an engine of its own.
+  const long long kMaxJobBytes = 192LL << 20;
+  std::vector<int> small;
+  std::vector<long long> cells((size_t)n_batches, 0), bytes((size_t)n_batches, 0);
+  gklb_pairhmm_stats total{};
+  for (int r = 0; r < n_batches; r++) {
+    const gklb_pairhmm_batch& b = batches[r];
+    if (b.n_reads == 0 || b.n_haps == 0) continue;
+    cells[r] = (long long)b.read_off[b.n_reads] * (long long)b.hap_off[b.n_haps];
+    bytes[r] = 5LL * b.read_off[b.n_reads] + b.hap_off[b.n_haps] + 8LL * b.n_reads * b.n_haps;
+    if (cells[r] >= kMinCellsPerDevice || bytes[r] > kMaxJobBytes / 2) {
+      if ((rc = gklb_pairhmm_compute(&b, likelihoods[r]))) return rc;
+      std::lock_guard<std::mutex> lk(g_mu);
+      total.pairs += g_last_stats.pairs; total.cells += g_last_stats.cells; total.fallback_pairs += g_last_stats.fallback_pairs;
+      total.fp64_pairs += g_last_stats.fp64_pairs; total.kernel_launches += g_last_stats.kernel_launches;
+    } else {
+      small.push_back(r);
+    }
   }
-  {
-    std::lock_guard<std::mutex> lk(g_mu);
-    g_last_stats = e->stats;
+  if (!small.empty()) {
+    long long small_cells = 0, small_bytes = 0;
+    for (int r : small) { small_cells += cells[r]; small_bytes += bytes[r]; }
+    int n_jobs = (int)std::max<long long>(1, (small_bytes + kMaxJobBytes - 1) / kMaxJobBytes);
+    // several devices: one job per device once every job still holds about a millisecond of work
+    n_jobs = std::max(n_jobs, (int)std::min<long long>((long long)devices.size(), small_cells / 2000000000LL));
+    n_jobs = std::max(1, std::min(n_jobs, (int)small.size()));
+    // greedy balance: largest regions first, each to the lightest job (region order inside a job does not matter)
+    std::vector<std::vector<int>> jobs((size_t)n_jobs);
+    std::vector<long long> load((size_t)n_jobs, 0);
+    std::vector<int> order = small;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cells[x] > cells[y]; });
+    for (int r : order) {
+      const int j = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      jobs[j].push_back(r);
+      load[j] += cells[r];
+    }
+    std::vector<int> rcs((size_t)n_jobs, GKLB_OK);
+    std::vector<std::string> errs((size_t)n_jobs);
+    std::vector<gklb_pairhmm_stats> sts((size_t)n_jobs);
+    auto run_job = [&](int j) {
+      std::vector<gklb_pairhmm_batch> jb;
+      std::vector<double*> jo;
+      for (int r : jobs[j]) { jb.push_back(batches[r]); jo.push_back(likelihoods[r]); }
+      gklb_engine* e = nullptr;
+      rcs[j] = acquire(-1, &e);
+      if (!rcs[j]) {
+        {
+          std::lock_guard<std::mutex> lk(e->mu);
+          rcs[j] = do_compute(e, jb.data(), (int)jb.size(), jo.data());
+          sts[j] = e->stats;
+        }
+        release(e);
+      }
+      if (rcs[j]) errs[j] = last_error_string();
+    };
+    if (n_jobs == 1) {
+      run_job(0);
+    } else {
+      std::vector<std::thread> th;
+      for (int j = 0; j < n_jobs; j++) th.emplace_back(run_job, j);
+      for (auto& t : th) t.join();
+    }
+    for (int j = 0; j < n_jobs; j++) {
+      if (rcs[j]) { set_last_error(errs[j]); return rcs[j]; }
+      total.pairs += sts[j].pairs; total.cells += sts[j].cells; total.fallback_pairs += sts[j].fallback_pairs;
+      total.fp64_pairs += sts[j].fp64_pairs; total.kernel_launches += sts[j].kernel_launches;
+      total.n_classes = std::max(total.n_classes, sts[j].n_classes);
+      total.h2d_ms = std::max(total.h2d_ms, sts[j].h2d_ms);
+      total.kernel_ms = std::max(total.kernel_ms, sts[j].kernel_ms);
+      total.d2h_ms = std::max(total.d2h_ms, sts[j].d2h_ms);
+    }
   }
-  release(e);
-  return rc;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_last_stats = total;
+  return GKLB_OK;
 }
 
 int gklb_pairhmm_done(void) {

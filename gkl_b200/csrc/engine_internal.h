@@ -173,6 +173,7 @@ int do_submit(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* 
 int do_wait(gklb_engine* e);
 // stats.fallback_pairs / fp64_pairs from the counters last copied to e->h_counters
 void read_fallback_count(gklb_engine* e);
+bool use_r2();  // GKLB_R2=1: the H2 sweep's flagged pairs go through the range-extended fp32 rerun
 // Write the haplotype bases of the staged (single-region) job's panel images from a device buffer laid out like the
 // batch's hap_bases arena (kernels on the engine's stream).
 int fill_panels_from_device(gklb_engine* e, const uint8_t* hap_bases_dev);

@@ -110,7 +110,7 @@ __global__ void k_narrow(const double* __restrict__ in, float* __restrict__ out,
 __global__ void k_collect_overrides_r2(const uint2* __restrict__ items, const unsigned int* __restrict__ count,
                                        const int32_t* __restrict__ rec_rid, const uint8_t* __restrict__ pair_image, int n_pairs,
                                        int n_haps, const double* __restrict__ out, uint32_t* __restrict__ idx,
-                                       double* __restrict__ val, unsigned int* cursor) {
+                                       double* __restrict__ val, unsigned int* cursor, unsigned int cap) {
   const int32_t* idxA = reinterpret_cast<const int32_t*>(pair_image) + 3 * n_pairs;
   const int32_t* idxB = idxA + n_pairs;
   const unsigned int n = *count;
@@ -123,8 +123,10 @@ __global__ void k_collect_overrides_r2(const uint2* __restrict__ items, const un
       const int h = x == 0 ? idxA[q] : idxB[q];
       const uint32_t pair = (uint32_t)rec_rid[it.x] * (uint32_t)n_haps + (uint32_t)h;
       const unsigned int at = atomicAdd(cursor, 1u);
-      idx[at] = pair;
-      val[at] = out[pair];
+      if (at < cap) {  // the cursor keeps counting: the receiver sees an overflow as count > capacity
+        idx[at] = pair;
+        val[at] = out[pair];
+      }
     }
   }
 }
@@ -132,15 +134,44 @@ __global__ void k_collect_overrides_r2(const uint2* __restrict__ items, const un
 // The pairs the fp64 kernel produced from a (record, haplotype) list (multi-pass classes), as (pair index, value).
 __global__ void k_collect_overrides(const uint2* __restrict__ items, const unsigned int* __restrict__ count,
                                     const int32_t* __restrict__ rec_rid, int n_haps, const double* __restrict__ out,
-                                    uint32_t* __restrict__ idx, double* __restrict__ val, unsigned int* cursor) {
+                                    uint32_t* __restrict__ idx, double* __restrict__ val, unsigned int* cursor,
+                                    unsigned int cap) {
   const unsigned int n = *count;
   for (unsigned int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const uint2 it = items[k];
     const uint32_t pair = (uint32_t)rec_rid[it.x] * (uint32_t)n_haps + it.y;
     const unsigned int at = atomicAdd(cursor, 1u);
-    idx[at] = pair;
-    val[at] = out[pair];
+    if (at < cap) {
+      idx[at] = pair;
+      val[at] = out[pair];
+    }
   }
+}
+
+// Enqueue the narrowing of one engine's (single-region) result: fp32 matrix + overrides of at most `cap` flagged pairs.
+int enqueue_narrow(gklb_engine* e, float* f32, uint32_t* idx, double* val, unsigned int* cursor, unsigned int cap) {
+  const size_t n = (size_t)e->stats.pairs;
+  const int H = e->regions[0].n_haps;
+  GKLB_CU(cudaMemsetAsync(cursor, 0, sizeof(unsigned int), e->stream));
+  if (!n) return GKLB_OK;
+  k_narrow<<<e->num_sms * 4, 256, 0, e->stream>>>(static_cast<const double*>(e->d_out.p), f32, n);
+  const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
+  for (auto& en : e->entries) {  // every pair the plain fp32 sweep flagged carries a value computed in double
+    const ClassInst& c = e->classes[en.cls];
+    const Tile& t = e->tiles[en.tile];
+    const unsigned int* cnt = static_cast<const unsigned int*>(e->d_counters.p) + en.counter0;
+    if (c.kf->policy == POL_H2 && use_r2()) {  // the H2 sweep's flagged pairs are rerun items (record, pair | mask)
+      k_collect_overrides_r2<<<e->num_sms, 256, 0, e->stream>>>(
+          static_cast<const uint2*>(e->d_r2.p) + en.r2_off, cnt, reinterpret_cast<const int32_t*>(dm + c.meta_rid),
+          dm + t.pmeta_off, t.n_pairs, H, static_cast<const double*>(e->d_out.p), idx, val, cursor, cap);
+    } else if (e->d_fb.p) {
+      k_collect_overrides<<<e->num_sms, 256, 0, e->stream>>>(
+          static_cast<const uint2*>(e->d_fb.p) + en.fb_off, cnt + 1, reinterpret_cast<const int32_t*>(dm + c.meta_rid), H,
+          static_cast<const double*>(e->d_out.p), idx, val, cursor, cap);
+    }
+  }
+  GKLB_CU(cudaGetLastError());
+  return GKLB_OK;
 }
 
 void widen(const float* src, double* dst, size_t n, int threads) {
@@ -261,29 +292,9 @@ int sharded_compute_nccl(const std::vector<gklb_engine*>& engines, const gklb_pa
     CU(e->d_xidx.ensure(sizeof(uint32_t) * std::max<size_t>(1, g == 0 ? total_ovr : n_ovr[g])));
     CU(e->d_xval.ensure(sizeof(double) * std::max<size_t>(1, g == 0 ? total_ovr : n_ovr[g])));
     CU(e->d_xcnt.ensure(sizeof(unsigned int)));
-    CU(cudaMemsetAsync(e->d_xcnt.p, 0, sizeof(unsigned int), e->stream));
-    if (n_pairs[g]) {
-      k_narrow<<<e->num_sms * 4, 256, 0, e->stream>>>(static_cast<const double*>(e->d_out.p), static_cast<float*>(e->d_xf32.p),
-                                                     n_pairs[g]);
-      const uint8_t* dm = static_cast<const uint8_t*>(e->d_meta.p);
-      for (auto& en : e->entries) {  // every pair the plain fp32 sweep flagged carries a value computed in double
-        const ClassInst& c = e->classes[en.cls];
-        const Tile& t = e->tiles[en.tile];
-        const unsigned int* cnt = static_cast<const unsigned int*>(e->d_counters.p) + en.counter0;
-        if (c.kf->policy == POL_H2) {
-          k_collect_overrides_r2<<<e->num_sms, 256, 0, e->stream>>>(
-              static_cast<const uint2*>(e->d_r2.p) + en.r2_off, cnt, reinterpret_cast<const int32_t*>(dm + c.meta_rid),
-              dm + t.pmeta_off, t.n_pairs, H, static_cast<const double*>(e->d_out.p), static_cast<uint32_t*>(e->d_xidx.p),
-              static_cast<double*>(e->d_xval.p), static_cast<unsigned int*>(e->d_xcnt.p));
-        } else if (e->d_fb.p) {
-          k_collect_overrides<<<e->num_sms, 256, 0, e->stream>>>(
-              static_cast<const uint2*>(e->d_fb.p) + en.fb_off, cnt + 1, reinterpret_cast<const int32_t*>(dm + c.meta_rid), H,
-              static_cast<const double*>(e->d_out.p), static_cast<uint32_t*>(e->d_xidx.p), static_cast<double*>(e->d_xval.p),
-              static_cast<unsigned int*>(e->d_xcnt.p));
-        }
-      }
-      CU(cudaGetLastError());
-    }
+    if ((rc = enqueue_narrow(e, static_cast<float*>(e->d_xf32.p), static_cast<uint32_t*>(e->d_xidx.p),
+                             static_cast<double*>(e->d_xval.p), static_cast<unsigned int*>(e->d_xcnt.p), 0xffffffffu)))
+      return rc;
   }
   // gather to GPU 0 over NVLink
   {
@@ -352,6 +363,7 @@ int sharded_compute_nccl(const std::vector<gklb_engine*>& engines, const gklb_pa
     stats->pairs += st.pairs;
     stats->cells += st.cells;
     stats->fallback_pairs += st.fallback_pairs;
+    stats->fp64_pairs += st.fp64_pairs;
     stats->kernel_launches += st.kernel_launches;
     stats->n_classes = std::max(stats->n_classes, st.n_classes);
   }
@@ -363,3 +375,32 @@ int sharded_compute_nccl(const std::vector<gklb_engine*>& engines, const gklb_pa
 }
 
 }  // namespace gklb
+
+using namespace gklb;
+
+extern "C" {
+
+// The result of the last run as one packed device buffer (used by multi-process hosts that gather results over
+// NVLink, bench.py --gpus N):  float likelihoods[pairs] | uint32 count | uint32 capacity | uint32 index[capacity] |
+// (8-byte aligned) double value[capacity].  The reference's value for an unflagged pair IS an fp32 widened to double
+// (IntelPairHmm.cc:164), so the fp32 matrix loses nothing; the flagged pairs (fp64 results) travel as overrides.
+// count > capacity means the override list overflowed.  Asynchronous on the engine's stream.
+int gklb_engine_narrow(gklb_engine* e, unsigned int capacity, void** packed_dev, size_t* packed_bytes) {
+  if (!e || !packed_dev || !packed_bytes) return fail(GKLB_ERR_INVALID, "null argument");
+  std::lock_guard<std::mutex> lk(e->mu);
+  if (!e->staged || e->regions.size() != 1) return fail(GKLB_ERR_STATE, "a single-region job must be staged");
+  GKLB_CU(cudaSetDevice(e->device));
+  const size_t n = (size_t)e->stats.pairs;
+  const size_t off_cnt = sizeof(float) * n, off_idx = off_cnt + 8, off_val = (off_idx + sizeof(uint32_t) * capacity + 7) / 8 * 8;
+  const size_t bytes = off_val + sizeof(double) * capacity;
+  GKLB_CU(e->d_xf32.ensure(bytes));
+  uint8_t* base = static_cast<uint8_t*>(e->d_xf32.p);
+  int rc = enqueue_narrow(e, reinterpret_cast<float*>(base), reinterpret_cast<uint32_t*>(base + off_idx),
+                          reinterpret_cast<double*>(base + off_val), reinterpret_cast<unsigned int*>(base + off_cnt), capacity);
+  if (rc) return rc;
+  *packed_dev = base;
+  *packed_bytes = bytes;
+  return GKLB_OK;
+}
+
+}  // extern "C"

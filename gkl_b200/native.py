@@ -44,7 +44,7 @@ class Stats(C.Structure):
 
 EXPORTS = ["gklb_pairhmm_init", "gklb_pairhmm_compute", "gklb_pairhmm_done", "gklb_pairhmm_devices_in_use",
            "gklb_pairhmm_last_stats", "gklb_pairhmm_engines_alive", "gklb_pairhmm_acquire_engine",
-           "gklb_pairhmm_release_engine", "gklb_pairhmm_compute_multi", "gklb_engine_compute_multi", "gklb_engine_device", "gklb_engine_sweep_kernel", "gklb_engine_plan_info", "gklb_engine_stage_multi", "gklb_engine_create",
+           "gklb_pairhmm_release_engine", "gklb_pairhmm_compute_multi", "gklb_engine_compute_multi", "gklb_engine_device", "gklb_engine_sweep_kernel", "gklb_engine_plan_info", "gklb_engine_stage_multi", "gklb_engine_narrow", "gklb_engine_create",
            "gklb_engine_destroy", "gklb_engine_set_stream", "gklb_engine_compute", "gklb_engine_submit", "gklb_engine_wait", "gklb_engine_stage",
            "gklb_engine_stage_device", "gklb_engine_update_haps_device", "gklb_engine_run", "gklb_engine_fetch", "gklb_engine_result_device",
            "gklb_engine_synchronize", "gklb_engine_stats", "gklb_engine_time_runs", "gklb_last_error",
@@ -93,6 +93,7 @@ def lib() -> C.CDLL:
         l.gklb_engine_sweep_kernel.argtypes = [C.c_void_p]
         l.gklb_engine_device.argtypes = [C.c_void_p]
         l.gklb_engine_stage_multi.argtypes = [C.c_void_p, C.POINTER(_Batch), C.c_int]
+        l.gklb_engine_narrow.argtypes = [C.c_void_p, C.c_uint, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         l.gklb_engine_plan_info.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         l.gklb_pairhmm_acquire_engine.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
         l.gklb_pairhmm_release_engine.argtypes = [C.c_void_p]
@@ -227,6 +228,12 @@ class Engine:
         s = Stats()
         _check(lib().gklb_engine_stats(self._h, C.byref(s)))
         return s
+
+    def narrow(self, capacity: int):
+        """(device pointer, bytes) of the last run's result as fp32 matrix + fp64 overrides (gklb_engine_narrow)."""
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(lib().gklb_engine_narrow(self._h, int(capacity), C.byref(p), C.byref(n)))
+        return p.value, n.value
 
     def plan_info(self) -> str:
         buf = C.create_string_buffer(1 << 16)

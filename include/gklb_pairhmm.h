@@ -177,6 +177,12 @@ GKLB_API int gklb_engine_update_haps_device(gklb_engine* e, const void* hap_base
 GKLB_API int gklb_engine_run(gklb_engine* e);
 GKLB_API int gklb_engine_fetch(gklb_engine* e, double* likelihoods);
 GKLB_API int gklb_engine_result_device(gklb_engine* e, void** dev_ptr);
+/* The result of the last run narrowed on the device to one packed buffer, for hosts that gather results over NVLink
+ * (bench.py --gpus N; the in-process NCCL path does the same internally):
+ *   float likelihoods[pairs] | uint32 count | uint32 pad | uint32 index[capacity] | (8-aligned) double value[capacity]
+ * An unflagged pair's value IS an fp32 widened to double (IntelPairHmm.cc:164), so the fp32 matrix loses nothing; the
+ * flagged pairs (fp64 results) travel as (pair index, value) overrides; count > capacity = the list overflowed.  [async] */
+GKLB_API int gklb_engine_narrow(gklb_engine* e, unsigned int capacity, void** packed_dev, size_t* packed_bytes);
 GKLB_API int gklb_engine_synchronize(gklb_engine* e);
 
 GKLB_API int gklb_engine_stats(gklb_engine* e, gklb_pairhmm_stats* out);

@@ -228,6 +228,10 @@ def test_submit_wait_equals_compute(eng):
     other.submit(b2, o2)
     with pytest.raises(native.GklbError):
         eng.submit(b2, o2)  # one batch in flight per engine
+    for call in (lambda: eng.compute(b2), lambda: eng.stage(b2), lambda: eng.fetch(b1.n_reads * b1.n_haps)):
+        with pytest.raises(native.GklbError) as ei:   # ... and nothing may restage or fetch under it
+            call()
+        assert ei.value.code == native.ERR_STATE
     eng.wait()
     other.wait()
     other.close()
@@ -330,6 +334,31 @@ def test_multi_region_call_through_the_global_surface():
         native.global_done()
 
 
+def test_multi_region_call_spreads_jobs_over_the_configured_devices(monkeypatch):
+    """gklb_pairhmm_compute_multi with GKLB_DEVICES: the regions are balanced into one job per device (each on an
+    engine of its own) once there is enough work; a region big enough to shard goes through gklb_pairhmm_compute.
+    Two engines on device 0 exercise the same code path as two GPUs."""
+    import torch
+    devs = "0,1" if torch.cuda.device_count() >= 2 else "0,0"
+    monkeypatch.setenv("GKLB_DEVICES", devs)
+    assert native.global_init(False, 1) == 2
+    try:
+        regions = synth.config3(20, seed=13)                 # 5e9 cells -> two jobs
+        empty = fixtures.PairHmmBatch.from_lists([], [], [], [], [], [b"ACGT"])
+        big = synth.config2(3000, 128)                       # shards on its own
+        job = regions[:7] + [empty] + regions[7:] + [big]
+        outs = native.global_compute_multi(job)
+        st = native.global_stats()
+        assert st.pairs == sum(r.n_reads * r.n_haps for r in job)
+        assert st.cells == sum(r.cells() for r in job)
+        one = native.Engine(0, False)
+        for r, o in zip(job, outs):
+            assert np.array_equal(one.compute(r), o) if r.n_reads else o.size == 0
+        one.close()
+    finally:
+        native.global_done()
+
+
 def test_quality_bytes_above_127_are_masked_like_the_reference(eng, eng_d):
     """avx-pairhmm-template.h:134-136,149: every quality byte is used `& 127`; bytes with the high bit set must give
     the same likelihoods as their low seven bits (checked against GKL's own code on the raw bytes)."""
@@ -405,3 +434,32 @@ def test_global_surface_lifecycle_is_reference_counted():
     assert np.array_equal(native.global_compute(b), d.compute(b))
     d.close()
     native.global_done()
+
+
+def test_narrowed_result_reconstructs_the_likelihoods_exactly(eng):
+    """gklb_engine_narrow: fp32 matrix + (pair index, fp64) overrides of the rerun pairs must give back every double
+    bit for bit (an unflagged pair's value is an fp32 widened to double, IntelPairHmm.cc:164)."""
+    import torch
+    b = synth.config2(400, 64)
+    want = eng.compute(b)
+    eng.stage(b)
+    eng.run()
+    n = b.n_reads * b.n_haps
+    cap = 8192
+    ptr, nbytes = eng.narrow(cap)
+    eng.synchronize()
+
+    class _Dev:
+        def __init__(self, p, k):
+            self.__cuda_array_interface__ = {"shape": (k,), "typestr": "|u1", "data": (p, False), "version": 3}
+    raw = torch.as_tensor(_Dev(ptr, nbytes), device="cuda").cpu().numpy()
+    f32 = raw[:4 * n].view(np.float32)
+    count = int(raw[4 * n:4 * n + 4].view(np.uint32)[0])
+    assert 0 < count <= cap
+    idx = raw[4 * n + 8:4 * n + 8 + 4 * cap].view(np.uint32)[:count]
+    off_val = (4 * n + 8 + 4 * cap + 7) // 8 * 8
+    val = raw[off_val:off_val + 8 * cap].view(np.float64)[:count]
+    got = f32.astype(np.float64)
+    got[idx] = val
+    assert np.array_equal(got, want)
+    assert count == int((want < -64.0).sum()) or abs(count - int((want < -64.0).sum())) < 50

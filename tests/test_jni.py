@@ -87,6 +87,24 @@ def test_large_calls_are_pipelined_in_read_blocks(monkeypatch):
 
 
 @pytest.mark.gpu
+def test_pipelined_calls_run_on_the_configured_device(monkeypatch):
+    """The read-block pipeline borrows its two engines from the pool, i.e. on the device the pool was configured
+    with (GKLB_DEVICES), not on device 0."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    monkeypatch.setenv("GKLB_DEVICES", "1")
+    monkeypatch.setenv("GKLB_JNI_BLOCK_READS", "40")
+    b = synth.random_batch(63, 200, 7, read_len=(20, 140), hap_len=(60, 200))
+    free0 = torch.cuda.mem_get_info(0)[0]
+    rc, out, cls, msg, leaks = jni_fake.pairhmm(LIB, b)
+    assert rc == 0 and leaks == (0, 0), (cls, msg)
+    assert torch.cuda.mem_get_info(0)[0] >= free0 - (64 << 20)   # nothing was allocated on device 0
+    ref = (oracle.ref_pairhmm if oracle.ref_available() else oracle.port_pairhmm)(b, threads=oracle.host_threads())[0]
+    assert (np.abs(out - ref) / np.abs(ref)).max() <= 1e-5
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("fault,cls", [(2, "java/lang/NullPointerException"), (3, "java/lang/OutOfMemoryError"),
                                        (4, "java/lang/IllegalArgumentException"), (6, "java/lang/IllegalArgumentException")])
 def test_fault_injection_maps_to_gkl_exception_classes(fault, cls):
