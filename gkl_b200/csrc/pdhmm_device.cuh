@@ -467,7 +467,7 @@ __device__ __forceinline__ double dmax_if(double a, double b, bool cond) {
 
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, int read_block, int n_blocks,
-                                                          unsigned int n_tasks) {
+                                                          unsigned int n_tasks, const uint8_t* __restrict__ only) {
   constexpr int G = 32;
   constexpr int CAP = G * K;
   extern __shared__ __align__(16) uint8_t smem[];
@@ -483,14 +483,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
   const bool cross = p.n_haps > 0;
   const bool first = (t == 0);
 
+  unsigned int next_static = blockIdx.x * WARPS + warp;   // `only`: few haplotypes of many, strided instead of queued
   for (;;) {
     unsigned int task = 0;
-    if (lane == 0) task = atomicAdd(p.counter, 1u);
-    task = __shfl_sync(0xffffffffu, task, 0);
+    if (only) {
+      task = next_static;
+      next_static += gridDim.x * WARPS;
+    } else {
+      if (lane == 0) task = atomicAdd(p.counter, 1u);
+      task = __shfl_sync(0xffffffffu, task, 0);
+    }
     if (task >= n_tasks) break;
     long long hi, r_begin, r_end;
     if (cross) {
       hi = task / (unsigned)n_blocks;
+      if (only && !only[hi]) continue;   // the other haplotypes were taken by k_pdhmm3
       const long long blk = task - hi * (unsigned)n_blocks;
       const long long n_reads = p.n / p.n_haps;
       r_begin = blk * read_block;
@@ -791,5 +798,314 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
     }
   }
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// k_pdhmm3 -- two reads per warp (16 lanes x K rows each) against one haplotype.
+//   Same arithmetic and evaluation order as k_pdhmm2 (results are bit-identical); what changes is the shape:
+//   * 101-row reads fill 101 of 16 x 7 = 112 rows (k_pdhmm2: 128), the fill/drain is 15 steps, a special column keeps
+//     the warp in the state-machine steps for 16 + 2 steps instead of 32 + 2, and the per-step overhead (shuffles, table
+//     loads, loop) is spread over 7 cells per lane instead of 4;
+//   * both reads of a warp meet the same haplotype, so the column tables, the step count and the special windows are
+//     shared and every branch of the step loop stays warp-uniform;
+//   * the branch twins live in shared memory ([3 K][32 lanes] doubles per warp): they are written on the columns that
+//     capture them and read on the two columns that merge them, nowhere else -- the registers they occupied in k_pdhmm2
+//     pay for K = 7;
+//   * haplotypes whose rows do not all start in the NORMAL state (they end inside or right after a deletion and the
+//     state is carried to the next row, pdhmm-serial.cc:306) are left to k_pdhmm2: `deferred[h]` is set by the host.
+// ------------------------------------------------------------------------------------------------------------
+// Columns of one haplotype grouped by what decides the prior: the class mask and, for a byte outside ACGTacgtN, the
+// byte itself (it matches an identical read byte).  keys[i] = mask | (0x100 | byte) << 16; colid[c] = index of column
+// c's key.  Returns the number of distinct keys; columns beyond `max_ids` keys get the last index (the caller gives
+// such a haplotype to k_pdhmm2).  Warp-cooperative: 32 columns at a time, new keys appended in column order.
+constexpr int kPdMaxIds = 10;
+__device__ __forceinline__ bool pd_other_byte(uint32_t y) {
+  const uint32_t u = y & 0xDFu;
+  return !(u == 'A' || u == 'C' || u == 'G' || u == 'T' || y == 'N');
+}
+__device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap, const uint8_t* ys, const uint16_t* cmask,
+                                                    uint8_t* colid, uint32_t* keys) {
+  for (int c = lane - kPdMargin; c < max_hap + kPdMargin; c += 32) colid[c] = 0;
+  __syncwarp();
+  int n = 0;
+  for (int base = 1; base <= H; base += 32) {
+    const int c = base + lane;
+    const bool valid = c <= H;
+    uint32_t key = 0xFFFFFFFFu;
+    if (valid) {
+      const uint32_t y = ys[c];
+      key = (uint32_t)cmask[c] | (pd_other_byte(y) ? (0x100u | y) << 16 : 0u);
+    }
+    int id = -1;
+    for (int i = 0; i < min(n, kPdMaxIds); i++)
+      if (key == keys[i]) id = i;
+    unsigned pending = __ballot_sync(0xffffffffu, valid && id < 0);
+    while (pending) {
+      const uint32_t kk = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
+      if (lane == 0 && n < kPdMaxIds) keys[n] = kk;
+      if (key == kk) id = n;
+      n++;
+      pending = __ballot_sync(0xffffffffu, valid && id < 0);
+    }
+    __syncwarp();
+    if (valid) colid[c] = (uint8_t)min(id, kPdMaxIds - 1);
+  }
+  __syncwarp();
+  return n;
+}
+
+template <int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, int read_block, int n_blocks,
+                                                          unsigned int n_tasks, uint8_t* deferred) {
+  constexpr int G = 16;
+  constexpr int CAP = G * K;
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = lane & (G - 1), g = lane >> 4;
+  const int col_pitch = (p.max_hap + 2 * kPdMargin + 1) & ~1;
+  const size_t table_bytes = ((size_t)8 * col_pitch + 15) & ~(size_t)15;   // the seven column tables + colid
+  constexpr size_t kDoubles = (size_t)(3 + kPdMaxIds) * K * 32;
+  uint8_t* gs = smem + (size_t)warp * (table_bytes + kDoubles * sizeof(double) + 64);
+  uint8_t* ys = gs + kPdMargin;
+  uint8_t* infos = gs + col_pitch + kPdMargin;
+  uint8_t* alleles = gs + 2 * col_pitch + kPdMargin;
+  uint16_t* nspec = reinterpret_cast<uint16_t*>(gs + 3 * col_pitch) + kPdMargin;
+  uint16_t* cmask = reinterpret_cast<uint16_t*>(gs + 5 * col_pitch) + kPdMargin;
+  uint8_t* colid = gs + 7 * col_pitch + kPdMargin;            // which prior-table block column c reads
+  double* tw = reinterpret_cast<double*>(gs + table_bytes);   // twins: tw[(3 j + q) * 32 + lane]
+  double* tw_me = tw + lane;
+  // priors of this lane's rows for every kind of column: tab[(id * K + j) * 32 + lane]
+  double* tab_me = tw + 3 * K * 32 + lane;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(gs + table_bytes + kDoubles * sizeof(double));
+  const double* tw_up = tw + 3 * (K - 1) * 32 + (t == 0 ? lane : lane - 1);  // bottom-row twins of the lane above
+  const long long n_reads = p.n / p.n_haps;
+
+  for (;;) {
+    unsigned int task = 0;
+    if (lane == 0) task = atomicAdd(p.counter, 1u);
+    task = __shfl_sync(0xffffffffu, task, 0);
+    if (task >= n_tasks) break;
+    const long long hi = task / (unsigned)n_blocks;
+    if (deferred[hi]) continue;
+    const long long blk = task - hi * (unsigned)n_blocks;
+    const long long r_begin = blk * read_block;
+    const long long r_end = min(n_reads, r_begin + read_block);
+    const int H = (int)p.hap_lengths[hi];
+    const int8_t* hap = p.hap_bases + hi * p.max_hap;
+    const int8_t* pd = p.hap_pdbases + hi * p.max_hap;
+    pd_build_column_tables(lane, 32, 0, H, p.max_hap, hap, pd, p.carry_state, ys, infos, alleles, nspec, cmask);
+    const int n_ids = pd_assign_column_ids(lane, H, p.max_hap, ys, cmask, colid, keys);
+    if (n_ids > kPdMaxIds) {   // more kinds of columns than the prior table holds: k_pdhmm2 takes this haplotype
+      if (lane == 0) deferred[hi] = 1;
+      continue;
+    }
+    const double init = p.init_cond / (double)H;
+    const int n_steps = H + G - 1;
+
+    for (long long r0 = r_begin; r0 < r_end; r0 += 2) {
+      const bool mine = r0 + g < r_end;
+      const long long ri = mine ? r0 + g : r0;     // an odd last read is computed twice, stored once
+      const long long item = ri * p.n_haps + hi;
+      const int R = (int)p.read_lengths[ri];
+      const int64_t ro = ri * (int64_t)p.max_read;
+      const int n_pad = CAP - R;
+      // ---- per-row constants ----
+      double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];
+      uint32_t rbit[K], xeq[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        const int row = t * K + j - n_pad;
+        tMM[j] = tIM[j] = tMI[j] = tMD[j] = 0.0;
+        tII[j] = 1.0;
+        pMa[j] = pMi[j] = 0.0;
+        rbit[j] = 0;
+        xeq[j] = 0x200;
+        if (row >= 0) {
+          const int8_t iq = p.read_ins_qual[ro + row], dq = p.read_del_qual[ro + row], gq = p.gcp[ro + row];
+          if (iq < 0 || dq < 0 || gq < 0) atomicOr(p.error_flag, 1u);
+          const int qi = iq & 0xFF, qd = dq & 0xFF, qg = gq & 0xFF, qq = p.read_qual[ro + row] & 0xFF;
+          const int mn = min(qi, qd), mx = max(qi, qd);
+          tMM[j] = (mx > 254) ? 1.0 - (pow(10.0, -0.1 * mn) + pow(10.0, -0.1 * mx))
+                              : __ldg(p.mm + ((mx * (mx + 1)) >> 1) + mn);
+          tMI[j] = __ldg(p.q2err + min(qi, 254));
+          tMD[j] = __ldg(p.q2err + min(qd, 254));
+          const double eg = __ldg(p.q2err + min(qg, 254));
+          tIM[j] = 1.0 - eg;
+          tII[j] = eg;
+          const double eq = __ldg(p.q2err + min(qq, 254));
+          pMa[j] = 1.0 - eq;
+          pMi[j] = eq / 3.0;
+          const uint32_t x = (uint8_t)p.read_bases[ro + row];
+          const uint32_t rc = read_class(x);
+          rbit[j] = 1u << rc;
+          xeq[j] = (rc == 9) ? (0x100u | x) : 0x200u;
+        }
+      }
+      double M[K], I[K], D[K];
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        M[j] = I[j] = 0.0;
+        D[j] = (t * K + j < n_pad) ? init : 0.0;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 3 * K; q++) tw_me[q * 32] = 0.0;
+      // the prior of row j on a column of kind id (pdhmm-serial.cc:228-277), once per pair instead of once per cell
+      for (int id = 0; id < n_ids; id++) {
+        const uint32_t key = keys[id];
+#pragma unroll
+        for (int j = 0; j < K; j++)
+          tab_me[(id * K + j) * 32] = (((key & rbit[j]) != 0u) | ((key >> 16) == xeq[j])) ? pMa[j] : pMi[j];
+      }
+      __syncwarp();
+      double gM = 0, gI = 0, gD = (t == 0) ? init : 0.0, gbM = 0, gbI = 0, gbD = 0;
+      double sum = 0.0;
+      int c = 1 - t;
+      double uM, uI, uD, ubM = 0.0, ubI = 0.0, ubD = 0.0;
+      // lane 0 of each half holds only padding rows (reads of more than 16 K - K rows go to the other kernels), and a
+      // padding row IS row 0, so the half-wide shuffle hands it exactly the row above it
+      auto fetch_main = [&]() {
+        uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
+      };
+      auto fetch_twins = [&]() {
+        __syncwarp();
+        ubM = tw_up[0]; ubI = tw_up[32]; ubD = tw_up[64];
+      };
+      fetch_main();
+      int s = 1;
+      while (s <= n_steps) {
+        const int first_special = nspec[max(s - G, -kPdMargin)];
+        int n_run = min(first_special - (s + 1), n_steps - s + 1);
+        n_run = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(n_run, 0));
+        if (n_run > 0) {
+          const int s_end = s + n_run;
+          auto single = [&]() {
+            if ((unsigned)(c - 1) < (unsigned)H) {
+              const double* pt = tab_me + (int)colid[c] * (K * 32);
+              double tM = uM, tI = uI;
+              double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const double lM = M[j], lI = I[j], lD = D[j];
+                const double prior = pt[j * 32];
+                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+                const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
+                dM = lM; dI = lI; dD = lD;
+                M[j] = nM; I[j] = nI; D[j] = nD;
+                tM = nM; tI = nI;
+              }
+              sum += M[K - 1] + I[K - 1];
+            }
+            gM = uM; gI = uI; gD = uD;
+            c++;
+            s++;
+            fetch_main();
+          };
+          while (s < s_end && s < G) single();                        // fill: lanes enter one by one
+          const int n_fast = max(0, s_end - s) & ~1;
+          if (n_fast > 0) {
+            double M2[K], I2[K], D2[K];
+            auto half = [&](const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K], double (&Mo)[K],
+                            double (&Io)[K], double (&Do)[K]) {
+              const double* pt = tab_me + (int)colid[c] * (K * 32);
+              double tM = uM, tI = uI;
+              double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+              for (int j = 0; j < K; j++) {
+                const double prior = pt[j * 32];
+                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+                const double nD = pd_gap(Mi[j], tMD[j], Di[j], tII[j]);
+                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
+                dM = Mi[j]; dI = Ii[j]; dD = Di[j];
+                Mo[j] = nM; Io[j] = nI; Do[j] = nD;
+                tM = nM; tI = nI;
+              }
+              const double add = Mo[K - 1] + Io[K - 1];
+              sum += (c <= H) ? add : 0.0;
+              gM = uM; gI = uI; gD = uD;
+              c++;
+              uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
+            };
+            for (int k = 0; k < n_fast; k += 2) {
+              half(M, I, D, M2, I2, D2);
+              half(M2, I2, D2, M, I, D);
+            }
+            s += n_fast;
+          }
+          while (s < s_end) single();                                 // the odd step of a run
+          // no twin is read or written during a run; the next window step takes its top twins from shared memory,
+          // its diagonal twins are only read on special columns, at least one window step away
+          fetch_twins();
+          gbM = gbI = gbD = 0.0;
+          continue;
+        }
+        // ---- one special-window step (every row starts NORMAL, see k_pdhmm2): AFTER_DEL merges the left and diagonal
+        // inputs with their twins, the columns flagged 0x80 capture the twins, DEL_END redoes the insertion chain ----
+        const bool inrange = (unsigned)(c - 1) < (unsigned)H;
+        const uint32_t info = inrange ? infos[c] : 0u;
+        const bool after = (info & 3u) == 2u, del_end = (info & 0x40u) != 0, capture = (info & 0x80u) != 0;
+        if (__any_sync(0xffffffffu, after)) {
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            M[j] = dmax_if(M[j], tw_me[(3 * j) * 32], after);
+            I[j] = dmax_if(I[j], tw_me[(3 * j + 1) * 32], after);
+            D[j] = dmax_if(D[j], tw_me[(3 * j + 2) * 32], after);
+          }
+          gM = dmax_if(gM, gbM, after);
+          gI = dmax_if(gI, gbI, after);
+          gD = dmax_if(gD, gbD, after);
+        }
+        if (__any_sync(0xffffffffu, capture)) {
+          __syncwarp();   // the lane below has read last step's twins
+          if (capture) {
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+              tw_me[(3 * j) * 32] = M[j];
+              tw_me[(3 * j + 1) * 32] = I[j];
+              tw_me[(3 * j + 2) * 32] = D[j];
+            }
+          }
+        }
+        if (s >= G || inrange) {
+          const double* pt = tab_me + (int)colid[c] * (K * 32);
+          double tM = uM, tI = uI;
+          double dM = gM, dI = gI, dD = gD;
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            const double lM = M[j], lI = I[j], lD = D[j];
+            const double prior = pt[j * 32];
+            const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
+            const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+            const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
+            dM = lM; dI = lI; dD = lD;
+            M[j] = nM; I[j] = nI; D[j] = nD;
+            tM = nM; tI = nI;
+          }
+        }
+        if (__any_sync(0xffffffffu, del_end)) {
+          double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
+#pragma unroll
+          for (int j = 0; j < K; j++) {
+            const double nI = pd_gap(dmax(tbM, tM), tMI[j], dmax(tbI, tI), tII[j]);
+            I[j] = del_end ? nI : I[j];
+            tM = M[j]; tI = I[j];
+            tbM = tw_me[(3 * j) * 32]; tbI = tw_me[(3 * j + 1) * 32];
+          }
+        }
+        {
+          const double add = M[K - 1] + I[K - 1];
+          sum += inrange ? add : 0.0;
+        }
+        gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
+        c++;
+        s++;
+        fetch_main();
+        fetch_twins();
+      }
+      if (t == G - 1 && mine) p.out[item] = log10(sum) - p.log10_init;
+    }
+  }
+}
+
 
 }  // namespace gklb

@@ -40,6 +40,12 @@ const V2Config kV2[] = {
     {6, 8, 32 * 6 - 6, reinterpret_cast<const void*>(&k_pdhmm2<6, 8>)},
 };
 constexpr int kNumV2 = (int)(sizeof(kV2) / sizeof(kV2[0]));
+// k_pdhmm3: two reads per warp, 16 lanes x 7 rows each (reads of up to 16 * 7 - 7 rows), cross layout only
+constexpr int kV3K = 7, kV3Warps = 8, kV3MaxRead = 16 * kV3K - kV3K;
+const void* const kV3Fn = reinterpret_cast<const void*>(&k_pdhmm3<kV3K, kV3Warps>);
+size_t v3_smem(size_t col_pitch) {
+  return (size_t)kV3Warps * (((8 * col_pitch + 15) & ~(size_t)15) + (size_t)(3 + kPdMaxIds) * kV3K * 32 * sizeof(double) + 64);
+}
 constexpr int kMaxQual = 254;
 constexpr int kMmSizePd = ((kMaxQual + 1) * (kMaxQual + 2)) >> 1;
 constexpr int kSmemMax = 232448;
@@ -95,7 +101,7 @@ struct PdEngine {
   int device = 0, num_sms = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-  Buf tables, hap, pd, rd[5], hl, rl, out, misc, carry;
+  Buf tables, hap, pd, rd[5], hl, rl, out, misc, carry, deferred;
   int carry_state = 1;
   PdhmmParams last{};
   bool have_last = false;
@@ -104,6 +110,13 @@ struct PdEngine {
   // k_pdhmm2 (single pass, haplotype-major tasks): reads per task, blocks per haplotype, tasks
   bool use_v2 = false, allow_v2 = true;
   int v2 = 0;  // index into kV2
+  // k_pdhmm3 takes the haplotypes whose rows all start NORMAL, k_pdhmm2 the deferred rest (same task space)
+  bool use_v3 = false, allow_v3 = true;
+  int n_deferred = 0;
+  size_t v3_smem_bytes = 0;
+  int v3_grid = 0;
+  int read_block2 = 1, n_blocks2 = 1;   // the deferred haplotypes: small read blocks, every resident warp gets some
+  unsigned int n_tasks2 = 0;
   int read_block = 1, n_blocks = 1;
   unsigned int n_tasks = 0;
   gklb_pdhmm_stats stats{};
@@ -120,7 +133,7 @@ std::vector<PdSlot> g_slots;
 int g_refs = 0;
 bool g_inited = false;
 int g_carry_state = 1;
-bool g_allow_v2 = true;
+bool g_allow_v2 = true, g_allow_v3 = true;
 int g_device = 0;
 PdEngine* g_last = nullptr;   // engine of the last finished compute call: what last_stats / time_runs refer to
 gklb_pdhmm_stats g_last_stats{};
@@ -131,7 +144,7 @@ void destroy(PdEngine* e) {
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);
   for (Buf* b : {&e->tables, &e->hap, &e->pd, &e->rd[0], &e->rd[1], &e->rd[2], &e->rd[3], &e->rd[4], &e->hl, &e->rl,
-                 &e->out, &e->misc, &e->carry})
+                 &e->out, &e->misc, &e->carry, &e->deferred})
     b->release();
   for (auto& ev : e->ev)
     if (ev) cudaEventDestroy(ev);
@@ -142,7 +155,21 @@ void destroy(PdEngine* e) {
 int launch(PdEngine* e) {
   CU(cudaMemsetAsync(e->misc.p, 0, 8, e->stream));
   if (e->use_v2) {
-    void* args2[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks};
+    const uint8_t* only = nullptr;
+    if (e->use_v3) {
+      // k_pdhmm3 adds the haplotypes with more kinds of columns than its prior table holds to `deferred`, so the
+      // second launch always follows (a few microseconds when nothing was deferred)
+      uint8_t* deferred = static_cast<uint8_t*>(e->deferred.p);
+      void* args3[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks, &deferred};
+      CU(cudaLaunchKernel(kV3Fn, dim3(e->v3_grid), dim3(kV3Warps * 32), args3, e->v3_smem_bytes, e->stream));
+      e->stats.kernel_launches++;
+      only = deferred;
+      void* args2[] = {&e->last, &e->read_block2, &e->n_blocks2, &e->n_tasks2, &only};
+      CU(cudaLaunchKernel(kV2[e->v2].fn, dim3(e->num_sms), dim3(kV2[e->v2].warps * 32), args2, e->last_smem, e->stream));
+      e->stats.kernel_launches++;
+      return GKLB_OK;
+    }
+    void* args2[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks, &only};
     CU(cudaLaunchKernel(kV2[e->v2].fn, dim3(e->last_grid), dim3(kV2[e->v2].warps * 32), args2, e->last_smem, e->stream));
     e->stats.kernel_launches++;
     return GKLB_OK;
@@ -258,6 +285,46 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
       e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
       tasks = (long long)e->n_blocks * n_haps;
     }
+    // Two reads per warp (k_pdhmm3) when every read fits 16 x 7 rows: the haplotypes whose last column leaves the state
+    // machine outside NORMAL (the state is carried into the next row, pdhmm-serial.cc:306,370-385) stay with k_pdhmm2.
+    e->use_v3 = false;
+    e->n_deferred = 0;
+    if (cross && e->allow_v3 && b->max_read <= kV3MaxRead && v3_smem(col_pitch) <= (size_t)kSmemMax &&
+        tasks <= 0xFFFFFFF0LL) {
+      std::vector<uint8_t> deferred((size_t)n_haps, 0);
+      for (int h = 0; h < n_haps && e->carry_state; h++) {
+        const int8_t* f = b->hap_pdbases + (size_t)h * b->max_hap;
+        int st = 0;
+        for (long long c = 0; c < b->hap_lengths[h]; c++) {
+          if (st == 2) st = 0;
+          if (f[c] & 2) st = 1;
+          if (f[c] & 4) st = 2;
+        }
+        deferred[h] = st != 0;
+        e->n_deferred += st != 0;
+      }
+      CU(e->deferred.ensure((size_t)n_haps));
+      CU(cudaMemcpyAsync(e->deferred.p, deferred.data(), (size_t)n_haps, cudaMemcpyHostToDevice, s));
+      CU(cudaStreamSynchronize(s));   // `deferred` is a local
+      const int w3 = kV3Warps;
+      const long long want = 16LL * w3 * e->num_sms;
+      const long long nb = std::min<long long>((n_reads + 1) / 2, std::max<long long>(1, (want + n_haps - 1) / n_haps));
+      e->read_block = (int)((n_reads + nb - 1) / nb);
+      e->read_block += e->read_block & 1;   // whole pairs of reads
+      e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
+      tasks = (long long)e->n_blocks * n_haps;
+      e->use_v3 = true;
+      {
+        const long long resident = (long long)kV2[e->v2].warps * e->num_sms;
+        long long rb2 = std::max<long long>(1, (long long)n_reads * std::max(1, e->n_deferred) / (2 * resident));
+        while ((n_reads + rb2 - 1) / rb2 * n_haps > 0x7FFFFFF0LL) rb2 *= 2;
+        e->read_block2 = (int)rb2;
+        e->n_blocks2 = (int)((n_reads + rb2 - 1) / rb2);
+        e->n_tasks2 = (unsigned int)((long long)e->n_blocks2 * n_haps);
+      }
+      e->v3_smem_bytes = v3_smem(col_pitch);
+      e->v3_grid = (int)std::min<long long>(e->num_sms, (tasks + w3 - 1) / w3);
+    }
     if (tasks > 0xFFFFFFF0LL) {
       e->use_v2 = false;  // the task counter is 32 bits wide
     } else {
@@ -310,6 +377,7 @@ int create_pd_engine(PdEngine** out) {
   e->num_sms = prop.multiProcessorCount;
   e->carry_state = g_carry_state;
   e->allow_v2 = g_allow_v2;
+  e->allow_v3 = g_allow_v3;
   CU(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   for (auto& ev : e->ev) CU(cudaEventCreate(&ev));
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, false>),
@@ -317,6 +385,7 @@ int create_pd_engine(PdEngine** out) {
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   for (const V2Config& c : kV2) CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  CU(cudaFuncSetAttribute(kV3Fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
   CU(cudaMemcpy(e->tables.p, t.q2err, sizeof(t.q2err), cudaMemcpyHostToDevice));
@@ -372,9 +441,11 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
     const int device = dev ? atoi(dev) : 0;
     const char* rs = getenv("GKLB_PDHMM_ROW_STATE");
     const int carry = (rs && !strcmp(rs, "reset")) ? 0 : 1;
-    const char* kv = getenv("GKLB_PDHMM_KERNEL");  // "1": the pair-at-a-time kernel for every batch (measurement)
+    // measurement knob: "1" = the pair-at-a-time kernel for every batch, "2" = no two-reads-per-warp kernel
+    const char* kv = getenv("GKLB_PDHMM_KERNEL");
     const bool allow_v2 = !(kv && !strcmp(kv, "1"));
-    if (g_inited && (device != g_device || carry != g_carry_state || allow_v2 != g_allow_v2)) {
+    const bool allow_v3 = allow_v2 && !(kv && !strcmp(kv, "2"));
+    if (g_inited && (device != g_device || carry != g_carry_state || allow_v2 != g_allow_v2 || allow_v3 != g_allow_v3)) {
       // a different configuration: idle engines are rebuilt lazily with it
       for (size_t i = 0; i < g_slots.size();)
         if (!g_slots[i].busy) { if (g_last == g_slots[i].e) g_last = nullptr; destroy(g_slots[i].e); g_slots.erase(g_slots.begin() + i); } else i++;
@@ -382,6 +453,7 @@ int gklb_pdhmm_init(int openmp_setting, int max_threads, int avx_level, int max_
     g_device = device;
     g_carry_state = carry;
     g_allow_v2 = allow_v2;
+    g_allow_v3 = allow_v3;
     g_inited = true;
     g_refs++;
   }
