@@ -1005,8 +1005,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           const int n_fast = max(0, s_end - s) & ~1;
           if (n_fast > 0) {
             double M2[K], I2[K], D2[K];
-            auto half = [&](const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K], double (&Mo)[K],
-                            double (&Io)[K], double (&Do)[K]) {
+            // `masked`: some lane may be past the last column (the drain); its sum contribution is dropped
+            auto half = [&](auto masked, const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K],
+                            double (&Mo)[K], double (&Io)[K], double (&Do)[K]) {
               const double* pt = tab_me + (int)colid[c] * (K * 32);
               double tM = uM, tI = uI;
               double dM = gM, dI = gI, dD = gD;
@@ -1021,14 +1022,29 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
                 tM = nM; tI = nI;
               }
               const double add = Mo[K - 1] + Io[K - 1];
-              sum += (c <= H) ? add : 0.0;
+              if constexpr (decltype(masked)::value) sum += (c <= H) ? add : 0.0;
+              else sum += add;
               gM = uM; gI = uI; gD = uD;
               c++;
               uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
             };
-            for (int k = 0; k < n_fast; k += 2) {
-              half(M, I, D, M2, I2, D2);
-              half(M2, I2, D2, M, I, D);
+            // steady phase: lane 0 has not passed the last column, so every lane sits on a real column
+            const int n_steady = max(0, min(n_fast, H + 1 - s)) & ~1;
+            int k = 0;
+            for (; k + 8 <= n_steady; k += 8) {
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                half(std::false_type{}, M, I, D, M2, I2, D2);
+                half(std::false_type{}, M2, I2, D2, M, I, D);
+              }
+            }
+            for (; k < n_steady; k += 2) {
+              half(std::false_type{}, M, I, D, M2, I2, D2);
+              half(std::false_type{}, M2, I2, D2, M, I, D);
+            }
+            for (; k < n_fast; k += 2) {
+              half(std::true_type{}, M, I, D, M2, I2, D2);
+              half(std::true_type{}, M2, I2, D2, M, I, D);
             }
             s += n_fast;
           }
