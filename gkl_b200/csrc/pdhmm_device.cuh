@@ -801,7 +801,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
 
 // ------------------------------------------------------------------------------------------------------------
 // k_pdhmm3 -- two reads per warp (16 lanes x K rows each) against one haplotype.
-//   Same arithmetic and evaluation order as k_pdhmm2 (results are bit-identical); what changes is the shape:
+//   The recurrence of k_pdhmm2 with the deletion state folded (pd_match_y; results agree to ~1e-13); the shape differs:
 //   * 101-row reads fill 101 of 16 x 7 = 112 rows (k_pdhmm2: 128), the fill/drain is 15 steps, a special column keeps
 //     the warp in the state-machine steps for 16 + 2 steps instead of 32 + 2, and the per-step overhead (shuffles, table
 //     loads, loop) is spread over 7 cells per lane instead of 4;
@@ -851,6 +851,14 @@ __device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap
   }
   __syncwarp();
   return n;
+}
+
+// k_pdhmm3 keeps the deletion state divided by its row's match-to-deletion probability (Y = D / tMD): the update
+// becomes one fused multiply-add, Y' = M + Y * tDD, and the match state reads it back through bD = tMD(row above) * tIM.
+// Y never exceeds the sum of its row's match values, which the total probability mass bounds by the initial condition.
+__device__ __forceinline__ double pd_match_y(double prior, double dM, double dI, double dY, double tMM, double tIM,
+                                             double bD) {
+  return __dmul_rn(prior, fma(dY, bD, fma(dI, tIM, __dmul_rn(dM, tMM))));
 }
 
 template <int K, int WARPS>
@@ -909,13 +917,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
       const int64_t ro = ri * (int64_t)p.max_read;
       const int n_pad = CAP - R;
       // ---- per-row constants ----
-      double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];
+      double tMM[K], tIM[K], tMI[K], tII[K], tMD[K], pMa[K], pMi[K];   // tMD: 1 on padding rows (Y = D there)
       uint32_t rbit[K], xeq[K];
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int row = t * K + j - n_pad;
-        tMM[j] = tIM[j] = tMI[j] = tMD[j] = 0.0;
-        tII[j] = 1.0;
+        tMM[j] = tIM[j] = tMI[j] = 0.0;
+        tII[j] = tMD[j] = 1.0;
         pMa[j] = pMi[j] = 0.0;
         rbit[j] = 0;
         xeq[j] = 0x200;
@@ -940,7 +948,16 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           xeq[j] = (rc == 9) ? (0x100u | x) : 0x200u;
         }
       }
-      double M[K], I[K], D[K];
+      double bD[K];   // what the match state multiplies the Y of the row above with
+      {
+        double above = shfl_up_d(tMD[K - 1], G);   // lane 0 of a half: its own padding row, 1
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          bD[j] = __dmul_rn(above, tIM[j]);
+          above = tMD[j];
+        }
+      }
+      double M[K], I[K], D[K];   // D holds Y
 #pragma unroll
       for (int j = 0; j < K; j++) {
         M[j] = I[j] = 0.0;
@@ -987,8 +1004,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
               for (int j = 0; j < K; j++) {
                 const double lM = M[j], lI = I[j], lD = D[j];
                 const double prior = pt[j * 32];
-                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
-                const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+                const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
+                const double nD = fma(lD, tII[j], lM);
                 const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
                 dM = lM; dI = lI; dD = lD;
                 M[j] = nM; I[j] = nI; D[j] = nD;
@@ -1014,8 +1031,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
 #pragma unroll
               for (int j = 0; j < K; j++) {
                 const double prior = pt[j * 32];
-                const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
-                const double nD = pd_gap(Mi[j], tMD[j], Di[j], tII[j]);
+                const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
+                const double nD = fma(Di[j], tII[j], Mi[j]);
                 const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
                 dM = Mi[j]; dI = Ii[j]; dD = Di[j];
                 Mo[j] = nM; Io[j] = nI; Do[j] = nD;
@@ -1090,8 +1107,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           for (int j = 0; j < K; j++) {
             const double lM = M[j], lI = I[j], lD = D[j];
             const double prior = pt[j * 32];
-            const double nM = pd_match(prior, dM, dI, dD, tMM[j], tIM[j]);
-            const double nD = pd_gap(lM, tMD[j], lD, tII[j]);
+            const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
+            const double nD = fma(lD, tII[j], lM);
             const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
             dM = lM; dI = lI; dD = lD;
             M[j] = nM; I[j] = nI; D[j] = nD;
