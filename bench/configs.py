@@ -147,6 +147,7 @@ def config5(device: int = 0) -> dict:
         best = min(best, time.perf_counter() - t0)
     st = hmm.stats()
     kernel_ms = hmm.time_runs(3)
+    kernel_name = hmm.kernel_name()
     hmm.done()
     threads = oracle.host_threads()
     # parity: every pair against the reference's scalar path (what GATK's Java produced the golden files with);
@@ -186,7 +187,7 @@ def config5(device: int = 0) -> dict:
         "parity": {"max_abs_err": err, "pairs_checked": R * H,
                    "against": f"restatement of pdhmm-serial.cc (bit-identical to GKL's scalar path), every pair, {t_chk:.1f} s",
                    "max_abs_diff_vs_gkl_fastest_on_cpu_sample": dev_avx, "tolerance": "1e-4 absolute (IntelPDHMMUnitTest.java:33)"},
-        "roofline": {"bound": "fp64", "kernel": "k_pdhmm2", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        "roofline": {"bound": "fp64", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                      "frac": ach / peak, "peak_source": peak_src, "flop_per_cell": FLOP_PER_CELL, "traffic": None},
         "cpu_baseline": {"value": cpu_gcups, "unit": "GCUPS", "cores": threads, "kind": kind,
                          "sample": f"first {n_cpu} reads x all haplotypes ({detail})"},

@@ -817,13 +817,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
 // byte itself (it matches an identical read byte).  keys[i] = mask | (0x100 | byte) << 16; colid[c] = index of column
 // c's key.  Returns the number of distinct keys; columns beyond `max_ids` keys get the last index (the caller gives
 // such a haplotype to k_pdhmm2).  Warp-cooperative: 32 columns at a time, new keys appended in column order.
-constexpr int kPdMaxIds = 10;
 __device__ __forceinline__ bool pd_other_byte(uint32_t y) {
   const uint32_t u = y & 0xDFu;
   return !(u == 'A' || u == 'C' || u == 'G' || u == 'T' || y == 'N');
 }
 __device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap, const uint8_t* ys, const uint16_t* cmask,
-                                                    uint8_t* colid, uint32_t* keys) {
+                                                    uint8_t* colid, uint32_t* keys, int max_ids) {
   for (int c = lane - kPdMargin; c < max_hap + kPdMargin; c += 32) colid[c] = 0;
   __syncwarp();
   int n = 0;
@@ -836,18 +835,18 @@ __device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap
       key = (uint32_t)cmask[c] | (pd_other_byte(y) ? (0x100u | y) << 16 : 0u);
     }
     int id = -1;
-    for (int i = 0; i < min(n, kPdMaxIds); i++)
+    for (int i = 0; i < min(n, max_ids); i++)
       if (key == keys[i]) id = i;
     unsigned pending = __ballot_sync(0xffffffffu, valid && id < 0);
     while (pending) {
       const uint32_t kk = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
-      if (lane == 0 && n < kPdMaxIds) keys[n] = kk;
+      if (lane == 0 && n < max_ids) keys[n] = kk;
       if (key == kk) id = n;
       n++;
       pending = __ballot_sync(0xffffffffu, valid && id < 0);
     }
     __syncwarp();
-    if (valid) colid[c] = (uint8_t)min(id, kPdMaxIds - 1);
+    if (valid) colid[c] = (uint8_t)min(id, max_ids - 1);
   }
   __syncwarp();
   return n;
@@ -861,17 +860,18 @@ __device__ __forceinline__ double pd_match_y(double prior, double dM, double dI,
   return __dmul_rn(prior, fma(dY, bD, fma(dI, tIM, __dmul_rn(dM, tMM))));
 }
 
-template <int K, int WARPS>
+template <int G, int K, int WARPS, int NID>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, int read_block, int n_blocks,
                                                           unsigned int n_tasks, uint8_t* deferred) {
-  constexpr int G = 16;
+  static_assert(G == 16 || G == 32, "one or two reads per warp");
+  constexpr int GPW = 32 / G;
   constexpr int CAP = G * K;
   extern __shared__ __align__(16) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int t = lane & (G - 1), g = lane >> 4;
+  const int t = lane & (G - 1), g = lane / G;
   const int col_pitch = (p.max_hap + 2 * kPdMargin + 1) & ~1;
   const size_t table_bytes = ((size_t)8 * col_pitch + 15) & ~(size_t)15;   // the seven column tables + colid
-  constexpr size_t kDoubles = (size_t)(3 + kPdMaxIds) * K * 32;
+  constexpr size_t kDoubles = (size_t)(3 + NID) * K * 32;
   uint8_t* gs = smem + (size_t)warp * (table_bytes + kDoubles * sizeof(double) + 64);
   uint8_t* ys = gs + kPdMargin;
   uint8_t* infos = gs + col_pitch + kPdMargin;
@@ -901,15 +901,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
     const int8_t* hap = p.hap_bases + hi * p.max_hap;
     const int8_t* pd = p.hap_pdbases + hi * p.max_hap;
     pd_build_column_tables(lane, 32, 0, H, p.max_hap, hap, pd, p.carry_state, ys, infos, alleles, nspec, cmask);
-    const int n_ids = pd_assign_column_ids(lane, H, p.max_hap, ys, cmask, colid, keys);
-    if (n_ids > kPdMaxIds) {   // more kinds of columns than the prior table holds: k_pdhmm2 takes this haplotype
+    const int n_ids = pd_assign_column_ids(lane, H, p.max_hap, ys, cmask, colid, keys, NID);
+    if (n_ids > NID) {   // more kinds of columns than the prior table holds: k_pdhmm2 takes this haplotype
       if (lane == 0) deferred[hi] = 1;
       continue;
     }
     const double init = p.init_cond / (double)H;
     const int n_steps = H + G - 1;
 
-    for (long long r0 = r_begin; r0 < r_end; r0 += 2) {
+    for (long long r0 = r_begin; r0 < r_end; r0 += GPW) {
       const bool mine = r0 + g < r_end;
       const long long ri = mine ? r0 + g : r0;     // an odd last read is computed twice, stored once
       const long long item = ri * p.n_haps + hi;

@@ -40,11 +40,18 @@ const V2Config kV2[] = {
     {6, 8, 32 * 6 - 6, reinterpret_cast<const void*>(&k_pdhmm2<6, 8>)},
 };
 constexpr int kNumV2 = (int)(sizeof(kV2) / sizeof(kV2[0]));
-// k_pdhmm3: two reads per warp, 16 lanes x 7 rows each (reads of up to 16 * 7 - 7 rows), cross layout only
-constexpr int kV3K = 7, kV3Warps = 8, kV3MaxRead = 16 * kV3K - kV3K;
-const void* const kV3Fn = reinterpret_cast<const void*>(&k_pdhmm3<kV3K, kV3Warps>);
-size_t v3_smem(size_t col_pitch) {
-  return (size_t)kV3Warps * (((8 * col_pitch + 15) & ~(size_t)15) + (size_t)(3 + kPdMaxIds) * kV3K * 32 * sizeof(double) + 64);
+// k_pdhmm3 instantiations (cross layout only): lanes per read, rows per lane, warps per CTA, longest read (lane 0 of a
+// read stays all padding).  Two 101-base reads per warp, or one read of up to 155 rows.
+// `ids`: kinds of columns the per-pair prior table holds (haplotypes with more go to k_pdhmm2).
+struct V3Config { int G, K, warps, ids, max_read; const void* fn; };
+const V3Config kV3[] = {
+    {16, 7, 8, 10, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 10>)},
+    {32, 5, 10, 10, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 10, 10>)},
+    {32, 5, 12, 8, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 12, 8>)},
+};
+constexpr int kNumV3 = (int)(sizeof(kV3) / sizeof(kV3[0]));
+size_t v3_smem(const V3Config& c, size_t col_pitch) {
+  return (size_t)c.warps * (((8 * col_pitch + 15) & ~(size_t)15) + (size_t)(3 + c.ids) * c.K * 32 * sizeof(double) + 64);
 }
 constexpr int kMaxQual = 254;
 constexpr int kMmSizePd = ((kMaxQual + 1) * (kMaxQual + 2)) >> 1;
@@ -112,6 +119,7 @@ struct PdEngine {
   int v2 = 0;  // index into kV2
   // k_pdhmm3 takes the haplotypes whose rows all start NORMAL, k_pdhmm2 the deferred rest (same task space)
   bool use_v3 = false, allow_v3 = true;
+  int v3 = 0;  // index into kV3
   int n_deferred = 0;
   size_t v3_smem_bytes = 0;
   int v3_grid = 0;
@@ -161,7 +169,7 @@ int launch(PdEngine* e) {
       // second launch always follows (a few microseconds when nothing was deferred)
       uint8_t* deferred = static_cast<uint8_t*>(e->deferred.p);
       void* args3[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks, &deferred};
-      CU(cudaLaunchKernel(kV3Fn, dim3(e->v3_grid), dim3(kV3Warps * 32), args3, e->v3_smem_bytes, e->stream));
+      CU(cudaLaunchKernel(kV3[e->v3].fn, dim3(e->v3_grid), dim3(kV3[e->v3].warps * 32), args3, e->v3_smem_bytes, e->stream));
       e->stats.kernel_launches++;
       only = deferred;
       void* args2[] = {&e->last, &e->read_block2, &e->n_blocks2, &e->n_tasks2, &only};
@@ -289,8 +297,16 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
     // machine outside NORMAL (the state is carried into the next row, pdhmm-serial.cc:306,370-385) stay with k_pdhmm2.
     e->use_v3 = false;
     e->n_deferred = 0;
-    if (cross && e->allow_v3 && b->max_read <= kV3MaxRead && v3_smem(col_pitch) <= (size_t)kSmemMax &&
-        tasks <= 0xFFFFFFF0LL) {
+    int v3 = -1;
+    for (int i = kNumV3 - 1; i >= 0; i--)
+      if (b->max_read <= kV3[i].max_read && v3_smem(kV3[i], col_pitch) <= (size_t)kSmemMax) v3 = i;
+    if (const char* force = getenv("GKLB_PDHMM_V3")) {   // measurement: a given instantiation, if it fits
+      const int i = atoi(force);
+      if (i >= 0 && i < kNumV3 && b->max_read <= kV3[i].max_read && v3_smem(kV3[i], col_pitch) <= (size_t)kSmemMax) v3 = i;
+    }
+    if (cross && e->allow_v3 && v3 >= 0 && tasks <= 0xFFFFFFF0LL) {
+      e->v3 = v3;
+      const int reads_per_warp = 32 / kV3[v3].G;
       std::vector<uint8_t> deferred((size_t)n_haps, 0);
       for (int h = 0; h < n_haps && e->carry_state; h++) {
         const int8_t* f = b->hap_pdbases + (size_t)h * b->max_hap;
@@ -306,11 +322,12 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
       CU(e->deferred.ensure((size_t)n_haps));
       CU(cudaMemcpyAsync(e->deferred.p, deferred.data(), (size_t)n_haps, cudaMemcpyHostToDevice, s));
       CU(cudaStreamSynchronize(s));   // `deferred` is a local
-      const int w3 = kV3Warps;
+      const int w3 = kV3[v3].warps;
       const long long want = 16LL * w3 * e->num_sms;
-      const long long nb = std::min<long long>((n_reads + 1) / 2, std::max<long long>(1, (want + n_haps - 1) / n_haps));
+      const long long groups = (n_reads + reads_per_warp - 1) / reads_per_warp;
+      const long long nb = std::min<long long>(groups, std::max<long long>(1, (want + n_haps - 1) / n_haps));
       e->read_block = (int)((n_reads + nb - 1) / nb);
-      e->read_block += e->read_block & 1;   // whole pairs of reads
+      e->read_block = (e->read_block + reads_per_warp - 1) / reads_per_warp * reads_per_warp;   // whole warps
       e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
       tasks = (long long)e->n_blocks * n_haps;
       e->use_v3 = true;
@@ -322,7 +339,7 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
         e->n_blocks2 = (int)((n_reads + rb2 - 1) / rb2);
         e->n_tasks2 = (unsigned int)((long long)e->n_blocks2 * n_haps);
       }
-      e->v3_smem_bytes = v3_smem(col_pitch);
+      e->v3_smem_bytes = v3_smem(kV3[v3], col_pitch);
       e->v3_grid = (int)std::min<long long>(e->num_sms, (tasks + w3 - 1) / w3);
     }
     if (tasks > 0xFFFFFFF0LL) {
@@ -385,7 +402,7 @@ int create_pd_engine(PdEngine** out) {
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   for (const V2Config& c : kV2) CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-  CU(cudaFuncSetAttribute(kV3Fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  for (const V3Config& c : kV3) CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
   CU(cudaMemcpy(e->tables.p, t.q2err, sizeof(t.q2err), cudaMemcpyHostToDevice));
@@ -511,6 +528,17 @@ int gklb_pdhmm_last_stats(gklb_pdhmm_stats* out) {
   if (!out) return gklb_internal_fail(GKLB_ERR_INVALID, "out is null");
   *out = g_last_stats;
   return GKLB_OK;
+}
+
+const char* gklb_pdhmm_kernel_name(void) {
+  static thread_local char name[48];
+  std::lock_guard<std::mutex> lk(g_mu);
+  const PdEngine* e = g_last;
+  if (!e || !e->have_last) return "";
+  if (e->use_v2 && e->use_v3) snprintf(name, sizeof(name), "k_pdhmm3<%d,%d,%d>", kV3[e->v3].G, kV3[e->v3].K, kV3[e->v3].warps);
+  else if (e->use_v2) snprintf(name, sizeof(name), "k_pdhmm2<%d,%d>", kV2[e->v2].K, kV2[e->v2].warps);
+  else snprintf(name, sizeof(name), "k_pdhmm<%d,%d,%d>", kG, kK, kWarps);
+  return name;
 }
 
 int gklb_pdhmm_time_runs(int iters, float* ms_per_run) {

@@ -32,7 +32,7 @@ class PdStats(C.Structure):
 
 
 PD_EXPORTS = ["gklb_pdhmm_init", "gklb_pdhmm_compute", "gklb_pdhmm_compute_cross", "gklb_pdhmm_done",
-              "gklb_pdhmm_last_stats", "gklb_pdhmm_time_runs", "gklb_pdhmm_table"]
+              "gklb_pdhmm_last_stats", "gklb_pdhmm_time_runs", "gklb_pdhmm_table", "gklb_pdhmm_kernel_name"]
 
 
 @dataclass
@@ -66,6 +66,8 @@ def _lib():
     l.gklb_pdhmm_last_stats.argtypes = [C.POINTER(PdStats)]
     l.gklb_pdhmm_time_runs.argtypes = [C.c_int, C.POINTER(C.c_float)]
     l.gklb_pdhmm_table.restype = C.c_void_p
+    l.gklb_pdhmm_kernel_name.restype = C.c_char_p
+    l.gklb_pdhmm_kernel_name.argtypes = []
     l.gklb_pdhmm_table.argtypes = [C.c_int, C.POINTER(C.c_int)]
     return l
 
@@ -176,6 +178,10 @@ class IntelPDHMM:
         if rc:
             _raise(rc)
         return ms.value
+
+    def kernel_name(self) -> str:
+        """The kernel that carried the last compute call (gklb_pdhmm_kernel_name)."""
+        return _lib().gklb_pdhmm_kernel_name().decode()
 
     def done(self) -> None:
         _lib().gklb_pdhmm_done()

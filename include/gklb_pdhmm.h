@@ -62,6 +62,8 @@ GKLB_API int gklb_pdhmm_done(void);
 GKLB_API int gklb_pdhmm_last_stats(gklb_pdhmm_stats* out);
 /* Time `iters` kernel launches over the operands of the last compute call (still resident in HBM). */
 GKLB_API int gklb_pdhmm_time_runs(int iters, float* ms_per_run);
+/* Name of the kernel that carried the last finished compute call ("k_pdhmm3<7,8>", "k_pdhmm2<4,12>", ...); "" before. */
+GKLB_API const char* gklb_pdhmm_kernel_name(void);
 /* which: 0 qualToErrorProb double[255], 1 matchToMatchProb double[32640] (pdhmm-common.h:149-195) */
 GKLB_API const void* gklb_pdhmm_table(int which, int* n);
 
