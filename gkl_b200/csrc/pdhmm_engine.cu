@@ -47,7 +47,6 @@ struct V3Config { int G, K, warps, ids, max_read; const void* fn; };
 const V3Config kV3[] = {
     {16, 7, 8, 10, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 10>)},
     {32, 5, 10, 10, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 10, 10>)},
-    {32, 5, 12, 8, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 12, 8>)},
 };
 constexpr int kNumV3 = (int)(sizeof(kV3) / sizeof(kV3[0]));
 size_t v3_smem(const V3Config& c, size_t col_pitch) {
