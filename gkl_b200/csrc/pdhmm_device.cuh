@@ -815,15 +815,15 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
 // ------------------------------------------------------------------------------------------------------------
 // Columns of one haplotype grouped by what decides the prior: the class mask and, for a byte outside ACGTacgtN, the
 // byte itself (it matches an identical read byte).  keys[i] = mask | (0x100 | byte) << 16; colid[c] = index of column
-// c's key.  Returns the number of distinct keys; columns beyond `max_ids` keys get the last index (the caller gives
-// such a haplotype to k_pdhmm2).  Warp-cooperative: 32 columns at a time, new keys appended in column order.
+// c's key, max_ids outside the haplotype.  Returns the number of distinct keys; columns beyond `max_ids` keys get the
+// last index (the caller gives such a haplotype to k_pdhmm2).  Warp-cooperative: 32 columns at a time, new keys appended in column order.
 __device__ __forceinline__ bool pd_other_byte(uint32_t y) {
   const uint32_t u = y & 0xDFu;
   return !(u == 'A' || u == 'C' || u == 'G' || u == 'T' || y == 'N');
 }
 __device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap, const uint8_t* ys, const uint16_t* cmask,
                                                     uint8_t* colid, uint32_t* keys, int max_ids) {
-  for (int c = lane - kPdMargin; c < max_hap + kPdMargin; c += 32) colid[c] = 0;
+  for (int c = lane - kPdMargin; c < max_hap + kPdMargin; c += 32) colid[c] = (uint8_t)max_ids;   // "no column"
   __syncwarp();
   int n = 0;
   for (int base = 1; base <= H; base += 32) {
@@ -870,7 +870,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = lane & (G - 1), g = lane / G;
   const int col_pitch = (p.max_hap + 2 * kPdMargin + 1) & ~1;
-  const size_t table_bytes = ((size_t)8 * col_pitch + 15) & ~(size_t)15;   // the seven column tables + colid
+  const size_t table_bytes = ((size_t)7 * col_pitch + 15) & ~(size_t)15;
   constexpr size_t kDoubles = (size_t)(3 + NID) * K * 32;
   uint8_t* gs = smem + (size_t)warp * (table_bytes + kDoubles * sizeof(double) + 64);
   uint8_t* ys = gs + kPdMargin;
@@ -878,7 +878,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
   uint8_t* alleles = gs + 2 * col_pitch + kPdMargin;
   uint16_t* nspec = reinterpret_cast<uint16_t*>(gs + 3 * col_pitch) + kPdMargin;
   uint16_t* cmask = reinterpret_cast<uint16_t*>(gs + 5 * col_pitch) + kPdMargin;
-  uint8_t* colid = gs + 7 * col_pitch + kPdMargin;            // which prior-table block column c reads
+  uint8_t* colid = alleles;   // which prior-table block column c reads (the allele bits are only used to build cmask)
   double* tw = reinterpret_cast<double*>(gs + table_bytes);   // twins: tw[(3 j + q) * 32 + lane]
   double* tw_me = tw + lane;
   // priors of this lane's rows for every kind of column: tab[(id * K + j) * 32 + lane]
@@ -886,6 +886,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
   uint32_t* keys = reinterpret_cast<uint32_t*>(gs + table_bytes + kDoubles * sizeof(double));
   const double* tw_up = tw + 3 * (K - 1) * 32 + (t == 0 ? lane : lane - 1);  // bottom-row twins of the lane above
   const long long n_reads = p.n / p.n_haps;
+#pragma unroll
+  for (int j = 0; j < K; j++) tab_me[((NID - 1) * K + j) * 32] = 0.0;
 
   for (;;) {
     unsigned int task = 0;
@@ -901,8 +903,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
     const int8_t* hap = p.hap_bases + hi * p.max_hap;
     const int8_t* pd = p.hap_pdbases + hi * p.max_hap;
     pd_build_column_tables(lane, 32, 0, H, p.max_hap, hap, pd, p.carry_state, ys, infos, alleles, nspec, cmask);
-    const int n_ids = pd_assign_column_ids(lane, H, p.max_hap, ys, cmask, colid, keys, NID);
-    if (n_ids > NID) {   // more kinds of columns than the prior table holds: k_pdhmm2 takes this haplotype
+    // kind NID - 1 is "no column" (prior 0): the margins on both sides of the haplotype
+    const int n_ids = pd_assign_column_ids(lane, H, p.max_hap, ys, cmask, colid, keys, NID - 1);
+    if (n_ids > NID - 1) {   // more kinds of columns than the prior table holds: k_pdhmm2 takes this haplotype
       if (lane == 0) deferred[hi] = 1;
       continue;
     }
@@ -978,111 +981,52 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
       double sum = 0.0;
       int c = 1 - t;
       double uM, uI, uD, ubM = 0.0, ubI = 0.0, ubD = 0.0;
-      // lane 0 of each half holds only padding rows (reads of more than 16 K - K rows go to the other kernels), and a
-      // padding row IS row 0, so the half-wide shuffle hands it exactly the row above it
-      auto fetch_main = [&]() {
-        uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
-      };
+      // lane 0 of each half holds only padding rows (reads of more than G K - K rows go to the other kernels), and a
+      // padding row IS row 0, so the half-wide shuffle hands it exactly the row above it.
+      // Lanes that have not reached column 1 yet run the same update: the margin columns are of the kind with prior 0,
+      // which keeps a lane in the state of column 0 (M = I = 0, Y unchanged: 0 on real rows, init on padding rows).
+      // Lanes past the last column compute values nobody reads; only their sums are masked.
+      double M2[K], I2[K], D2[K];
       auto fetch_twins = [&]() {
         __syncwarp();
         ubM = tw_up[0]; ubI = tw_up[32]; ubD = tw_up[64];
       };
-      fetch_main();
-      int s = 1;
-      while (s <= n_steps) {
-        const int first_special = nspec[max(s - G, -kPdMargin)];
-        int n_run = min(first_special - (s + 1), n_steps - s + 1);
-        n_run = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(n_run, 0));
-        if (n_run > 0) {
-          const int s_end = s + n_run;
-          auto single = [&]() {
-            if ((unsigned)(c - 1) < (unsigned)H) {
-              const double* pt = tab_me + (int)colid[c] * (K * 32);
-              double tM = uM, tI = uI;
-              double dM = gM, dI = gI, dD = gD;
+      // one plain column, from one register set into the other (`masked`: some lane may be past the last column)
+      auto half = [&](auto masked, const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K],
+                      double (&Mo)[K], double (&Io)[K], double (&Do)[K]) {
+        const double* pt = tab_me + (int)colid[c] * (K * 32);
+        double tM = uM, tI = uI;
+        double dM = gM, dI = gI, dD = gD;
 #pragma unroll
-              for (int j = 0; j < K; j++) {
-                const double lM = M[j], lI = I[j], lD = D[j];
-                const double prior = pt[j * 32];
-                const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
-                const double nD = fma(lD, tII[j], lM);
-                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
-                dM = lM; dI = lI; dD = lD;
-                M[j] = nM; I[j] = nI; D[j] = nD;
-                tM = nM; tI = nI;
-              }
-              sum += M[K - 1] + I[K - 1];
-            }
-            gM = uM; gI = uI; gD = uD;
-            c++;
-            s++;
-            fetch_main();
-          };
-          while (s < s_end && s < G) single();                        // fill: lanes enter one by one
-          const int n_fast = max(0, s_end - s) & ~1;
-          if (n_fast > 0) {
-            double M2[K], I2[K], D2[K];
-            // `masked`: some lane may be past the last column (the drain); its sum contribution is dropped
-            auto half = [&](auto masked, const double (&Mi)[K], const double (&Ii)[K], const double (&Di)[K],
-                            double (&Mo)[K], double (&Io)[K], double (&Do)[K]) {
-              const double* pt = tab_me + (int)colid[c] * (K * 32);
-              double tM = uM, tI = uI;
-              double dM = gM, dI = gI, dD = gD;
-#pragma unroll
-              for (int j = 0; j < K; j++) {
-                const double prior = pt[j * 32];
-                const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
-                const double nD = fma(Di[j], tII[j], Mi[j]);
-                const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
-                dM = Mi[j]; dI = Ii[j]; dD = Di[j];
-                Mo[j] = nM; Io[j] = nI; Do[j] = nD;
-                tM = nM; tI = nI;
-              }
-              const double add = Mo[K - 1] + Io[K - 1];
-              if constexpr (decltype(masked)::value) sum += (c <= H) ? add : 0.0;
-              else sum += add;
-              gM = uM; gI = uI; gD = uD;
-              c++;
-              uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
-            };
-            // steady phase: lane 0 has not passed the last column, so every lane sits on a real column
-            const int n_steady = max(0, min(n_fast, H + 1 - s)) & ~1;
-            int k = 0;
-            for (; k + 8 <= n_steady; k += 8) {
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                half(std::false_type{}, M, I, D, M2, I2, D2);
-                half(std::false_type{}, M2, I2, D2, M, I, D);
-              }
-            }
-            for (; k < n_steady; k += 2) {
-              half(std::false_type{}, M, I, D, M2, I2, D2);
-              half(std::false_type{}, M2, I2, D2, M, I, D);
-            }
-            for (; k < n_fast; k += 2) {
-              half(std::true_type{}, M, I, D, M2, I2, D2);
-              half(std::true_type{}, M2, I2, D2, M, I, D);
-            }
-            s += n_fast;
-          }
-          while (s < s_end) single();                                 // the odd step of a run
-          // no twin is read or written during a run; the next window step takes its top twins from shared memory,
-          // its diagonal twins are only read on special columns, at least one window step away
-          fetch_twins();
-          gbM = gbI = gbD = 0.0;
-          continue;
+        for (int j = 0; j < K; j++) {
+          const double prior = pt[j * 32];
+          const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
+          const double nD = fma(Di[j], tII[j], Mi[j]);
+          const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
+          dM = Mi[j]; dI = Ii[j]; dD = Di[j];
+          Mo[j] = nM; Io[j] = nI; Do[j] = nD;
+          tM = nM; tI = nI;
         }
-        // ---- one special-window step (every row starts NORMAL, see k_pdhmm2): AFTER_DEL merges the left and diagonal
-        // inputs with their twins, the columns flagged 0x80 capture the twins, DEL_END redoes the insertion chain ----
+        const double add = Mo[K - 1] + Io[K - 1];
+        if constexpr (decltype(masked)::value) sum += (c <= H) ? add : 0.0;
+        else sum += add;
+        gM = uM; gI = uI; gD = uD;
+        c++;
+        uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
+      };
+      // one column of a special window (every row starts NORMAL, see k_pdhmm2): AFTER_DEL merges the left and diagonal
+      // inputs with their twins, the columns flagged 0x80 capture the twins, DEL_END redoes the insertion chain
+      auto window = [&](double (&Mi)[K], double (&Ii)[K], double (&Di)[K], double (&Mo)[K], double (&Io)[K],
+                        double (&Do)[K]) {
         const bool inrange = (unsigned)(c - 1) < (unsigned)H;
         const uint32_t info = inrange ? infos[c] : 0u;
         const bool after = (info & 3u) == 2u, del_end = (info & 0x40u) != 0, capture = (info & 0x80u) != 0;
         if (__any_sync(0xffffffffu, after)) {
 #pragma unroll
           for (int j = 0; j < K; j++) {
-            M[j] = dmax_if(M[j], tw_me[(3 * j) * 32], after);
-            I[j] = dmax_if(I[j], tw_me[(3 * j + 1) * 32], after);
-            D[j] = dmax_if(D[j], tw_me[(3 * j + 2) * 32], after);
+            Mi[j] = dmax_if(Mi[j], tw_me[(3 * j) * 32], after);
+            Ii[j] = dmax_if(Ii[j], tw_me[(3 * j + 1) * 32], after);
+            Di[j] = dmax_if(Di[j], tw_me[(3 * j + 2) * 32], after);
           }
           gM = dmax_if(gM, gbM, after);
           gI = dmax_if(gI, gbI, after);
@@ -1093,25 +1037,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           if (capture) {
 #pragma unroll
             for (int j = 0; j < K; j++) {
-              tw_me[(3 * j) * 32] = M[j];
-              tw_me[(3 * j + 1) * 32] = I[j];
-              tw_me[(3 * j + 2) * 32] = D[j];
+              tw_me[(3 * j) * 32] = Mi[j];
+              tw_me[(3 * j + 1) * 32] = Ii[j];
+              tw_me[(3 * j + 2) * 32] = Di[j];
             }
           }
         }
-        if (s >= G || inrange) {
+        {
           const double* pt = tab_me + (int)colid[c] * (K * 32);
           double tM = uM, tI = uI;
           double dM = gM, dI = gI, dD = gD;
 #pragma unroll
           for (int j = 0; j < K; j++) {
-            const double lM = M[j], lI = I[j], lD = D[j];
             const double prior = pt[j * 32];
             const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
-            const double nD = fma(lD, tII[j], lM);
+            const double nD = fma(Di[j], tII[j], Mi[j]);
             const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
-            dM = lM; dI = lI; dD = lD;
-            M[j] = nM; I[j] = nI; D[j] = nD;
+            dM = Mi[j]; dI = Ii[j]; dD = Di[j];
+            Mo[j] = nM; Io[j] = nI; Do[j] = nD;
             tM = nM; tI = nI;
           }
         }
@@ -1120,20 +1063,62 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
 #pragma unroll
           for (int j = 0; j < K; j++) {
             const double nI = pd_gap(dmax(tbM, tM), tMI[j], dmax(tbI, tI), tII[j]);
-            I[j] = del_end ? nI : I[j];
-            tM = M[j]; tI = I[j];
+            Io[j] = del_end ? nI : Io[j];
+            tM = Mo[j]; tI = Io[j];
             tbM = tw_me[(3 * j) * 32]; tbI = tw_me[(3 * j + 1) * 32];
           }
         }
         {
-          const double add = M[K - 1] + I[K - 1];
+          const double add = Mo[K - 1] + Io[K - 1];
           sum += inrange ? add : 0.0;
         }
         gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
         c++;
-        s++;
-        fetch_main();
+        uM = shfl_up_d(Mo[K - 1], G); uI = shfl_up_d(Io[K - 1], G); uD = shfl_up_d(Do[K - 1], G);
         fetch_twins();
+      };
+      uM = shfl_up_d(M[K - 1], G); uI = shfl_up_d(I[K - 1], G); uD = shfl_up_d(D[K - 1], G);
+      int s = 1;
+      while (s <= n_steps) {
+        // lane 0 is at column s, lane G-1 at s - G + 1.  A run of columns needs no state machine while the window
+        // [s - G, s + 1] holds no special column (the +1 keeps one window step between a run and the next special
+        // column, which re-establishes the diagonal twins).  Runs and windows both advance two columns at a time,
+        // ping-ponging between the register sets; a window step is valid on any column.
+        const int first_special = nspec[max(s - G, -kPdMargin)];
+        int n_run = min(first_special - (s + 1), n_steps - s + 1);
+        n_run = (int)__reduce_max_sync(0xffffffffu, (unsigned)max(n_run, 0)) & ~1;   // identical on all lanes
+        if (n_run > 0) {
+          // while lane 0 has not passed the last column every lane sits on a real column or on the left margin
+          const int n_steady = max(0, min(n_run, H + 1 - s)) & ~1;
+          int k = 0;
+          for (; k + 8 <= n_steady; k += 8) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              half(std::false_type{}, M, I, D, M2, I2, D2);
+              half(std::false_type{}, M2, I2, D2, M, I, D);
+            }
+          }
+          for (; k < n_steady; k += 2) {
+            half(std::false_type{}, M, I, D, M2, I2, D2);
+            half(std::false_type{}, M2, I2, D2, M, I, D);
+          }
+          for (; k < n_run; k += 2) {
+            half(std::true_type{}, M, I, D, M2, I2, D2);
+            half(std::true_type{}, M2, I2, D2, M, I, D);
+          }
+          s += n_run;
+          // no twin is read or written during a run; the next window step takes its top twins from shared memory,
+          // its diagonal twins are only read on special columns, at least one window step away
+          fetch_twins();
+          gbM = gbI = gbD = 0.0;
+          continue;
+        }
+        window(M, I, D, M2, I2, D2);
+        s++;
+        if (s <= n_steps) {
+          window(M2, I2, D2, M, I, D);
+          s++;
+        }
       }
       if (t == G - 1 && mine) p.out[item] = log10(sum) - p.log10_init;
     }

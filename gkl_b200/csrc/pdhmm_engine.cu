@@ -42,15 +42,16 @@ const V2Config kV2[] = {
 constexpr int kNumV2 = (int)(sizeof(kV2) / sizeof(kV2[0]));
 // k_pdhmm3 instantiations (cross layout only): lanes per read, rows per lane, warps per CTA, longest read (lane 0 of a
 // read stays all padding).  Two 101-base reads per warp, or one read of up to 155 rows.
-// `ids`: kinds of columns the per-pair prior table holds (haplotypes with more go to k_pdhmm2).
+// `ids`: kinds of columns the per-pair prior table holds, one of them "no column" (haplotypes with more go to k_pdhmm2).
 struct V3Config { int G, K, warps, ids, max_read; const void* fn; };
 const V3Config kV3[] = {
-    {16, 7, 8, 10, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 10>)},
-    {32, 5, 10, 10, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 10, 10>)},
+    {16, 7, 8, 11, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 11>)},   // haplotypes of up to ~470 columns
+    {16, 7, 8, 9, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 9>)},
+    {32, 5, 8, 11, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 8, 11>)},
 };
 constexpr int kNumV3 = (int)(sizeof(kV3) / sizeof(kV3[0]));
 size_t v3_smem(const V3Config& c, size_t col_pitch) {
-  return (size_t)c.warps * (((8 * col_pitch + 15) & ~(size_t)15) + (size_t)(3 + c.ids) * c.K * 32 * sizeof(double) + 64);
+  return (size_t)c.warps * (((7 * col_pitch + 15) & ~(size_t)15) + (size_t)(3 + c.ids) * c.K * 32 * sizeof(double) + 64);
 }
 constexpr int kMaxQual = 254;
 constexpr int kMmSizePd = ((kMaxQual + 1) * (kMaxQual + 2)) >> 1;
