@@ -47,7 +47,7 @@ struct PdhmmParams {
   double log10_init;
   double* out;                  // [n]
   unsigned int* counter;        // work counter
-  unsigned int* error_flag;     // set when a negative insertion/deletion/gcp quality is met
+  unsigned int* error_flag;     // bit 0: a negative insertion/deletion/gcp quality; bit 1: a result above 0 or NaN
   double* carry;                // per warp: GPW * 2 * 6 * (max_hap + 2) doubles
   size_t carry_stride;          // doubles per warp
   int carry_state;
@@ -60,6 +60,13 @@ __device__ __forceinline__ double pd_match(double prior, double dM, double dI, d
 }
 __device__ __forceinline__ double pd_gap(double a, double ca, double b, double cb) {  // a * ca + b * cb
   return fma(b, cb, __dmul_rn(a, ca));
+}
+
+// pdhmm-serial.cc:411,432-441: log10(sum) - log10(initial condition); a result above 0 or a NaN is PDHMM_FAILURE
+__device__ __forceinline__ void pd_store_result(const PdhmmParams& p, long long item, double sum) {
+  const double r = log10(sum) - p.log10_init;
+  if (!(r <= 0.0)) atomicOr(p.error_flag, 2u);
+  p.out[item] = r;
 }
 
 __device__ __forceinline__ double shfl_up_d(double v, int width) { return __shfl_up_sync(0xffffffffu, v, 1, width); }
@@ -429,7 +436,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm(const PdhmmParams p) {
       }
       __syncwarp();
     }
-    if (mine && t == G - 1) p.out[item] = log10(sum) - p.log10_init;
+    if (mine && t == G - 1) pd_store_result(p, item, sum);
   }
 }
 
@@ -794,7 +801,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm2(const PdhmmParams p, i
         fetch_main();
         fetch_twins();
       }
-      if (t == G - 1) p.out[item] = log10(sum) - p.log10_init;
+      if (t == G - 1) pd_store_result(p, item, sum);
     }
   }
 }
@@ -837,6 +844,7 @@ __device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap
     int id = -1;
     for (int i = 0; i < min(n, max_ids); i++)
       if (key == keys[i]) id = i;
+    __syncwarp();   // every lane has compared against the keys found so far
     unsigned pending = __ballot_sync(0xffffffffu, valid && id < 0);
     while (pending) {
       const uint32_t kk = __shfl_sync(0xffffffffu, key, __ffs(pending) - 1);
@@ -1120,7 +1128,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           s++;
         }
       }
-      if (t == G - 1 && mine) p.out[item] = log10(sum) - p.log10_init;
+      if (t == G - 1 && mine) pd_store_result(p, item, sum);
     }
   }
 }

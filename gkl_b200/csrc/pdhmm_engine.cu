@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
+#include <array>
 #include <vector>
 
 #include "../../include/gklb_pdhmm.h"
@@ -190,6 +191,69 @@ int launch(PdEngine* e) {
   return GKLB_OK;
 }
 
+// pdhmm-serial.cc:228-277: a read byte that is not one of ACGTacgt, is not 'N' and differs from the haplotype byte
+// fails the call with PDHMM_INPUT_DATA_ERROR when it meets a column that carries SNP alleles (and is not 'N').
+// Checked on the host: one pass over the read bytes, the haplotypes only when some read holds such a byte.
+struct ByteSet {
+  uint64_t w[4] = {0, 0, 0, 0};
+  void add(uint8_t x) { w[x >> 6] |= 1ull << (x & 63); }
+  bool empty() const { return !(w[0] | w[1] | w[2] | w[3]); }
+  void merge(const ByteSet& o) { for (int i = 0; i < 4; i++) w[i] |= o.w[i]; }
+  // some member of *this differs from some member of o
+  bool differs_from(const ByteSet& o) const {
+    if (empty() || o.empty()) return false;
+    int na = 0, nb = 0;
+    for (int i = 0; i < 4; i++) { na += __builtin_popcountll(w[i]); nb += __builtin_popcountll(o.w[i]); }
+    if (na > 1 || nb > 1) return true;
+    for (int i = 0; i < 4; i++) if (w[i] != o.w[i]) return true;
+    return false;
+  }
+};
+
+bool unexpected_base_at_snp_column(const gklb_pdhmm_batch* b, bool cross, long long n_read_rows, long long n_hap_rows) {
+  static const std::array<uint8_t, 256> plain = [] {
+    std::array<uint8_t, 256> t{};
+    for (const char* c = "ACGTacgtN"; *c; c++) t[(uint8_t)*c] = 1;
+    return t;
+  }();
+  std::vector<long long> odd_reads;
+  for (long long r = 0; r < n_read_rows; r++) {
+    const uint8_t* x = reinterpret_cast<const uint8_t*>(b->read_bases) + r * (long long)b->max_read;
+    const long long len = b->read_lengths[r];
+    uint8_t odd = 0;   // branch-free byte compares: the host compiler vectorises this loop
+    for (long long i = 0; i < len; i++) {
+      const uint8_t u = x[i] & 0xDF;
+      odd |= (uint8_t)!((u == 'A') | (u == 'C') | (u == 'G') | (u == 'T') | (x[i] == 'N'));
+    }
+    if (odd) odd_reads.push_back(r);
+  }
+  if (odd_reads.empty()) return false;
+  auto odd_bytes = [&](long long r) {
+    ByteSet s;
+    const uint8_t* x = reinterpret_cast<const uint8_t*>(b->read_bases) + r * (long long)b->max_read;
+    for (long long i = 0; i < b->read_lengths[r]; i++)
+      if (!plain[x[i]]) s.add(x[i]);
+    return s;
+  };
+  auto snp_bytes = [&](long long h) {
+    ByteSet s;
+    const uint8_t* y = reinterpret_cast<const uint8_t*>(b->hap_bases) + h * (long long)b->max_hap;
+    const int8_t* f = b->hap_pdbases + h * (long long)b->max_hap;
+    for (long long j = 0; j < b->hap_lengths[h]; j++)
+      if ((f[j] & 1) && y[j] != 'N') s.add(y[j]);
+    return s;
+  };
+  if (cross) {
+    ByteSet reads, haps;
+    for (long long r : odd_reads) reads.merge(odd_bytes(r));
+    for (long long h = 0; h < n_hap_rows; h++) haps.merge(snp_bytes(h));
+    return reads.differs_from(haps);
+  }
+  for (long long k : odd_reads)
+    if (odd_bytes(k).differs_from(snp_bytes(k))) return true;
+  return false;
+}
+
 // n_reads/n_haps > 0: cross layout; else flat with b->n pairs.
 int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, double* out) {
   if (!b || !out) return gklb_internal_fail(GKLB_ERR_INVALID, "null argument");
@@ -217,6 +281,8 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   }
   if (cross) cells = sum_h * sum_r;
   else for (long long k = 0; k < n; k++) cells += b->hap_lengths[k] * b->read_lengths[k];
+  if (unexpected_base_at_snp_column(b, cross, n_read_rows, n_hap_rows))
+    return gklb_internal_fail(GKLB_ERR_INVALID, "Found unexpected base in alt alleles");
 
   constexpr int gpw = 32 / kG;
   const size_t col_pitch = ((size_t)b->max_hap + 2 * kPdMargin + 1) & ~(size_t)1;
@@ -370,8 +436,10 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
   cudaEventElapsedTime(&e->stats.h2d_ms, e->ev[0], e->ev[1]);
   cudaEventElapsedTime(&e->stats.kernel_ms, e->ev[1], e->ev[2]);
   cudaEventElapsedTime(&e->stats.d2h_ms, e->ev[2], e->ev[3]);
-  if (flags[1])  // pdhmm-serial.cc:184-198 -> PDHMM_INPUT_DATA_ERROR -> IllegalArgumentException
+  if (flags[1] & 1u)  // pdhmm-serial.cc:184-198 -> PDHMM_INPUT_DATA_ERROR -> IllegalArgumentException
     return gklb_internal_fail(GKLB_ERR_INVALID, "insertion, deletion or gcp quality is negative");
+  if (flags[1] & 2u)  // pdhmm-serial.cc:432-441 -> PDHMM_FAILURE -> RuntimeException
+    return gklb_internal_fail(GKLB_ERR_CUDA, "PDHMM log probability is greater than 0 or not a number");
   return GKLB_OK;
 }
 

@@ -181,6 +181,7 @@ int gklport_pdhmm(const int8_t* hap_bases, const int8_t* hap_pdbases, const int8
       const int64_t ho = k * (int64_t)max_hap, ro = k * (int64_t)max_read;
       result[k] = one_pair(hap_bases + ho, hap_pdbases + ho, (int)hap_lengths[k], read_bases + ro, read_qual + ro,
                            read_ins_qual + ro, read_del_qual + ro, gcp + ro, (int)read_lengths[k], carry_state, work, &st);
+      if (!(result[k] <= 0.0)) st = PDHMM_FAILURE; /* pdhmm-serial.cc:432-441: above 0 or not a number */
       if (st != PDHMM_SUCCESS) {
 #ifdef _OPENMP
 #pragma omp critical

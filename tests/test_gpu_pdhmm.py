@@ -152,30 +152,30 @@ def test_single_pass_kernel_cross_layout_blocks():
     assert np.abs(flat_out - ref).max() <= 1e-9
 
 
-def test_two_reads_per_warp_kernel_corners():
-    """k_pdhmm3 (cross layout, reads of at most 105 rows): odd read counts, haplotypes that end inside / right after a
-    deletion (deferred to k_pdhmm2 by the host), haplotypes with more kinds of columns than the prior table holds
-    (deferred by the kernel), read bytes outside ACGTacgtN meeting identical haplotype bytes, lower case and N on both
-    sides, adjacent and nested spans.  Against the restatement of the reference's scalar path and against k_pdhmm2
-    alone."""
+def _corner_batch(odd_read_bytes: bool, snp_columns: bool):
     from gkl_b200 import synth
     reads, haps = synth.config5(61, 24, seed=17)
     rng = np.random.default_rng(18)
     reads = [tuple(x.copy() for x in r) for r in reads]
     haps = [(h[0].copy(), h[1].copy()) for h in haps]
+    if not snp_columns:
+        for _, pdb in haps:
+            pdb &= 6   # keep the deletion spans only
     for i, r in enumerate(reads):
         n = len(r[0])
-        if i % 4 == 0:   # odd bytes in the read: lower case, N, and bytes of the "other" class
+        if i % 4 == 0:   # lower case and N in the read; optionally bytes outside ACGTacgtN
             pos = rng.integers(0, n, size=6)
-            r[0][pos[:2]] = ord("n") if i % 8 == 0 else ord("a")
+            r[0][pos[:2]] = ord("a") if i % 8 else ord("t")
             r[0][pos[2:4]] = ord("N")
-            r[0][pos[4:]] = np.array([ord("X"), 0], dtype=np.int8)
+            if odd_read_bytes:
+                r[0][pos[4:]] = np.array([ord("X"), 0 if i % 8 else ord("n")], dtype=np.int8)
         if i % 7 == 0:
             reads[i] = tuple(x[:int(rng.integers(1, n))] for x in r)
     for hidx in (0, 1, 2):   # many kinds of columns: every allele combination on every base, other bytes, N
         hb, pdb = haps[hidx]
         pos = rng.choice(len(hb), size=40, replace=False)
-        pdb[pos[:30]] = (1 | (rng.integers(1, 16, size=30) << 3)).astype(np.int8)
+        if snp_columns:
+            pdb[pos[:30]] = (1 | (rng.integers(1, 16, size=30) << 3)).astype(np.int8)
         hb[pos[30:34]] = ord("N")
         hb[pos[34:37]] = ord("X")
         hb[pos[37:]] = np.array([ord("c"), ord("g"), 0], dtype=np.int8)
@@ -186,11 +186,23 @@ def test_two_reads_per_warp_kernel_corners():
     haps[7][1][10] |= 2; haps[7][1][14] |= 2; haps[7][1][20] |= 4; haps[7][1][21] |= 4   # nested start, double end
     haps[8] = (haps[8][0][:1], np.array([0], dtype=np.int8))
     haps[9] = (haps[9][0][:17], haps[9][1][:17])
+    return reads, haps
+
+
+@pytest.mark.parametrize("odd_read_bytes,snp_columns", [(False, True), (True, False)])
+def test_two_reads_per_warp_kernel_corners(odd_read_bytes, snp_columns):
+    """k_pdhmm3 (cross layout, reads of at most 105 rows): odd read counts, haplotypes that end inside / right after a
+    deletion (deferred to k_pdhmm2 by the host), haplotypes with more kinds of columns than the prior table holds
+    (deferred by the kernel), lower case and N on both sides, adjacent and nested spans; and, without SNP columns (where
+    the reference would reject them), read bytes outside ACGTacgtN meeting identical haplotype bytes.  Against the
+    restatement of the reference's scalar path and against k_pdhmm2 alone."""
+    reads, haps = _corner_batch(odd_read_bytes, snp_columns)
     flat = pb.PdhmmBatch.cross(reads, haps)
     rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
     hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
     for row_state in ("carry", "reset"):
-        ref = oracle.port_pdhmm(flat, row_state == "carry", threads=oracle.host_threads())[0]
+        ref, rc, _ = oracle.port_pdhmm(flat, row_state == "carry", threads=oracle.host_threads())
+        assert rc == 0
         got = {}
         for kernel in ("3", "2"):
             os.environ["GKLB_PDHMM_ROW_STATE"] = row_state
@@ -209,3 +221,23 @@ def test_two_reads_per_warp_kernel_corners():
             assert launches == (2 if kernel == "3" else 1)
         assert np.abs(got["3"] - ref).max() <= 1e-9
         assert np.abs(got["3"] - got["2"]).max() <= 1e-9   # k_pdhmm3 folds the deletion state: not bit-identical
+
+
+def test_unexpected_read_base_at_an_snp_column_is_rejected_like_the_reference(hmm):
+    """pdhmm-serial.cc:228-252: a read byte outside ACGTacgt (and not N, and not equal to the haplotype byte) on a column
+    with SNP alleles is PDHMM_INPUT_DATA_ERROR -> IllegalArgumentException (IntelPDHMM.cc:102-105,222-226), for both
+    entry points; the same bytes without such a column are fine."""
+    reads, haps = _corner_batch(True, True)
+    flat = pb.PdhmmBatch.cross(reads, haps)
+    assert oracle.port_pdhmm(flat, True, threads=oracle.host_threads())[1] == 2   # PDHMM_INPUT_DATA_ERROR
+    rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
+    hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
+    with pytest.raises(IllegalArgumentException):
+        hmm.computeLikelihoods(rd, hp, np.zeros(len(rd) * len(hp)))
+    with pytest.raises(IllegalArgumentException):
+        hmm.compute_batch(flat)
+    # one pair of the flat layout whose odd byte only meets an identical haplotype byte on the SNP column: accepted
+    one = pb.PdhmmBatch.from_pairs([(np.frombuffer(b"ACXGT", dtype=np.int8), np.array([0, 0, 33, 0, 0], dtype=np.int8),
+                                     np.frombuffer(b"ACXGT", dtype=np.int8), *(np.full(5, q, dtype=np.int8) for q in (30, 40, 40, 10)))])
+    ref, rc, _ = oracle.port_pdhmm(one, True, threads=1)
+    assert rc == 0 and np.abs(hmm.compute_batch(one) - ref).max() <= 1e-9
