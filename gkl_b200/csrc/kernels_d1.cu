@@ -9,9 +9,9 @@ namespace gklb {
 
 void kernel_entries_d1(std::vector<KernelEntry>& v) {
   const KernelEntry e[] = {
-      E_D1(8, 4, 8, false, 3),  E_D1(8, 5, 8, false, 3),  E_D1(8, 6, 8, false, 3),  E_D1(8, 7, 8, false, 3),
-      E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 8, false, 3), E_D1(16, 6, 8, false, 3), E_D1(16, 7, 8, false, 3),
-      E_D1(16, 8, 8, false, 3), E_D1(32, 5, 8, false, 3), E_D1(32, 6, 8, false, 3), E_D1(32, 7, 8, false, 3),
+      E_D1(8, 4, 12, false, 3),  E_D1(8, 5, 12, false, 3),  E_D1(8, 6, 12, false, 3),  E_D1(8, 7, 12, false, 3),
+      E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 12, false, 3), E_D1(16, 6, 12, false, 3), E_D1(16, 7, 12, false, 3),
+      E_D1(16, 8, 8, false, 3), E_D1(32, 5, 12, false, 3), E_D1(32, 6, 12, false, 3), E_D1(32, 7, 12, false, 3),
       E_D1(32, 8, 8, false, 3), E_D1(32, 8, 8, true, 3),
   };
   for (const auto& x : e) v.push_back(x);
