@@ -224,7 +224,10 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b, int region, int re
     ClassInst c;
     if (h2) {
       c.G = h2_G(ci); c.K = h2_K(ci);
-      c.kf = find_kernel(POL_H2, c.G, c.K, kH2Warps, 0, -1);
+      // launches of a single class run 12 warps per SM where the class fits 168 registers (K <= 10); the multi-class
+      // kernel and the rerun kernels stay at kH2Warps whatever the entry says
+      c.kf = (c.K <= 10) ? find_kernel(POL_H2, c.G, c.K, 12, 0, -1) : nullptr;
+      if (!c.kf) c.kf = find_kernel(POL_H2, c.G, c.K, kH2Warps, 0, -1);
       c.cfg_f = ci;
       c.cfg_d = d1_cfg_for_rows(c.G * c.K);
       c.kd = find_kernel(POL_D1, kClassesD1[c.cfg_d].G, kClassesD1[c.cfg_d].K, -1, 0, -1);

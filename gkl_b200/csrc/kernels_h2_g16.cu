@@ -6,7 +6,6 @@ void kernel_entries_h2_g16(std::vector<KernelEntry>& v) {
 #ifdef GKLB_EXPERIMENTAL
   v.push_back(GKLB_E_H2(16, 7, 12));
   v.push_back(GKLB_E_H2(16, 7, 16));
-  v.push_back(GKLB_E_H2(16, 10, 12));
 #endif
 }
 }  // namespace gklb

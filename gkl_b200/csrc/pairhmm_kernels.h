@@ -53,6 +53,8 @@ void kernel_entries_misc(std::vector<KernelEntry>& v);
 #define GKLB_H2_ROW_ENTRIES(v, G)                                                                             \
   v.push_back(GKLB_E_H2(G, 8, 8)); v.push_back(GKLB_E_H2(G, 9, 8)); v.push_back(GKLB_E_H2(G, 10, 8));          \
   v.push_back(GKLB_E_H2(G, 11, 8)); v.push_back(GKLB_E_H2(G, 12, 8)); v.push_back(GKLB_E_H2(G, 13, 8));        \
-  v.push_back(GKLB_E_H2(G, 14, 8)); v.push_back(GKLB_E_H2(G, 15, 8)); v.push_back(GKLB_E_H2(G, 16, 8));
+  v.push_back(GKLB_E_H2(G, 14, 8)); v.push_back(GKLB_E_H2(G, 15, 8)); v.push_back(GKLB_E_H2(G, 16, 8));        \
+  /* up to 10 rows per lane fit 168 registers: a third warp per scheduler for single-class launches */         \
+  v.push_back(GKLB_E_H2(G, 8, 12)); v.push_back(GKLB_E_H2(G, 9, 12)); v.push_back(GKLB_E_H2(G, 10, 12));
 
 }  // namespace gklb
