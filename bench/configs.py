@@ -279,7 +279,11 @@ def config4(n_gpus: int, reads: int = 1_000_000, haps: int = 256) -> dict:
                      "against": f"{kind} ({detail})"}
     peak, peak_src = PEAKS['fp32']()
     ach = cells * FLOP_PER_CELL / (m["phases_ms_max_over_devices"]["kernels"] * 1e-3) / 1e12 / n_gpus
-    res["roofline"] = {"bound": "fp32", "kernel": "k_h2_tasks<16,10,8> + k_sweep_list<VD1> (all kernels of the slowest device)",
+    probe = native.Engine(0, False)   # the sweep kernel the engine picks for this shape (a shard plans the same classes)
+    probe.stage(synth.config4(2000, haps))
+    sweep_name = probe.sweep_kernel()
+    probe.close()
+    res["roofline"] = {"bound": "fp32", "kernel": f"{sweep_name} + k_sweep_list<VD1> (all kernels of the slowest device)",
                        "achieved": ach, "peak": peak, "unit": "TFLOP/s per GPU", "frac": ach / peak, "peak_source": peak_src,
                        "traffic": None}
     res["cpu_baseline"] = {"value": sample.cells() / secs / 1e9, "unit": "GCUPS", "cores": threads, "kind": kind,
