@@ -242,7 +242,10 @@ def config4(n_gpus: int, reads: int = 1_000_000, haps: int = 256) -> dict:
     m = ok["direct" if "direct" in ok else fastest]
     res["value"] = m["kernels_gcups"]
     res["unit"] = "GCUPS"
-    res["value_note"] = "cells / slowest device's kernel phase (CUDA events) inside the sharded call"
+    res["value_note"] = ("cells / slowest device's kernel phase (CUDA events) inside the sharded call; direct mode: a device's "
+                         "shard runs as up to 12 pieces on two engines in turn, the kernel phase is the span from the first "
+                         "piece's first kernel to the last piece's last kernel, and the h2d/d2h figures are the first piece's way in "
+                         "and the last piece's way out (the other copies run under the kernels of the neighbouring piece)")
     res["e2e"] = {"value": m["e2e_gcups"], "unit": "GCUPS", "seconds": m["e2e_s"],
                   "api": "gklb_pairhmm_compute, pageable host buffers, best of 2 after warm-up",
                   "h2d_bytes": int(b.input_bytes() * 1 + 8 * (reads + haps + 2)), "d2h_bytes": 8 * reads * haps}

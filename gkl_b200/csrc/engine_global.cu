@@ -77,7 +77,8 @@ std::vector<int> configured_devices() {
 }
 
 // Borrow an engine.  device_hint < 0: the least busy configured device.
-int acquire(int device_hint, gklb_engine** out) {
+// wait = false: give up (GKLB_ERR_STATE, no message) instead of waiting for an engine of a fully booked device
+int acquire(int device_hint, gklb_engine** out, bool wait = true) {
   std::unique_lock<std::mutex> lk(g_mu);
   if (!g_inited) return fail(GKLB_ERR_STATE, "gklb_pairhmm_init has not been called");
   for (;;) {
@@ -130,6 +131,7 @@ int acquire(int device_hint, gklb_engine** out) {
       *out = e;
       return GKLB_OK;
     }
+    if (!wait) return GKLB_ERR_STATE;
     g_cv.wait(lk);
   }
 }
@@ -156,6 +158,10 @@ void free_idle_engines_locked() {
 
 // Batches below this many cells per device are not worth splitting: one GPU finishes them in about a millisecond.
 const long long kMinCellsPerDevice = 4000000000LL;
+// direct sharding: a device's shard is cut into pieces of about this many cells (~30 ms of kernels), at most kMaxPieces,
+// handled by two engines in turn so that the copies of one piece overlap the kernels of the other
+const long long kCellsPerPiece = 100000000000LL;
+const int kMaxPieces = 12;
 
 }  // namespace
 
@@ -216,7 +222,12 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
   } else {
     n_dev = 1;
   }
-  if (n_dev <= 1) {
+  long long batch_cells = 0;
+  if (batch->n_reads > 0 && batch->n_haps > 0)
+    batch_cells = (long long)batch->read_off[batch->n_reads] * (long long)batch->hap_off[batch->n_haps];
+  const char* mode = getenv("GKLB_SHARD");
+  const bool nccl = mode && !strcmp(mode, "nccl");
+  if (n_dev <= 1 && (nccl || batch_cells < 2 * kCellsPerPiece)) {
     gklb_engine* e = nullptr;
     if ((rc = acquire(-1, &e))) return rc;
     {
@@ -233,63 +244,126 @@ int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods) {
   // Reads are sharded into contiguous ranges balanced by total length (every read meets every haplotype, so
   // cells are proportional to read length); range g gets a contiguous slab of the read-major output
   // (JavaData.h:94-105).
-  const int64_t total = batch->read_off[batch->n_reads];
-  std::vector<int> cut(n_dev + 1, 0);
-  {
-    int r = 0;
-    for (int g = 1; g < n_dev; g++) {
-      const int64_t target = total * g / n_dev;
-      while (r < batch->n_reads && batch->read_off[r] < target) r++;
-      cut[g] = std::max(r, cut[g - 1]);
+  auto split = [&](int lo, int hi, int parts, std::vector<int>* cuts) {   // [lo, hi) into `parts` ranges of equal length
+    cuts->assign((size_t)parts + 1, lo);
+    const int64_t base = batch->read_off[lo], span = batch->read_off[hi] - base;
+    int r = lo;
+    for (int g = 1; g < parts; g++) {
+      const int64_t target = base + span * g / parts;
+      while (r < hi && batch->read_off[r] < target) r++;
+      (*cuts)[g] = std::max(r, (*cuts)[g - 1]);
     }
-    cut[n_dev] = batch->n_reads;
-  }
+    (*cuts)[parts] = hi;
+  };
+  std::vector<int> cut;
+  split(0, batch->n_reads, n_dev, &cut);
   std::vector<gklb_engine*> engines(n_dev, nullptr);
   for (int g = 0; g < n_dev; g++) {
-    if ((rc = acquire(devices[g], &engines[g]))) {
+    if ((rc = acquire(n_dev == 1 ? -1 : devices[g], &engines[g]))) {
       for (int k = 0; k < g; k++) release(engines[k]);
       return rc;
     }
   }
   gklb_pairhmm_stats total_stats{};
-  const char* mode = getenv("GKLB_SHARD");
-  if (mode && !strcmp(mode, "nccl")) {
+  if (nccl) {
     rc = sharded_compute_nccl(engines, batch, cut, likelihoods, &total_stats);
   } else {
     // direct: each device copies its shard and the panel over its own PCIe link and writes its slab straight into
-    // the caller's array; the shards never meet on one GPU
-    std::vector<std::vector<int64_t>> offs(n_dev);
-    std::vector<gklb_pairhmm_batch> sub(n_dev);
-    std::vector<int> rcs(n_dev, GKLB_OK);
-    std::vector<std::string> errs(n_dev);
+    // the caller's array; the shards never meet on one GPU.  A shard of more than two pieces' worth of work is cut into
+    // pieces that two host threads, each with an engine of its own on that device, take in turn: the copies of one
+    // piece (in and out, pageable memory on the caller's side) run under the kernels of the other.
+    const int64_t hap_total = batch->hap_off[batch->n_haps];
+    std::vector<std::vector<int>> pieces(n_dev);
+    std::vector<gklb_engine*> second(n_dev, nullptr);
+    for (int g = 0; g < n_dev; g++) {
+      const long long cells_g = (long long)(batch->read_off[cut[g + 1]] - batch->read_off[cut[g]]) * hap_total;
+      int np = (int)std::max(1LL, std::min<long long>(kMaxPieces, cells_g / kCellsPerPiece));
+      np = std::max(1, std::min(np, cut[g + 1] - cut[g]));
+      // never wait for the second engine while holding the first (concurrent callers would deadlock): without it
+      // the shard runs as one piece
+      if (np >= 2 && acquire(gklb_engine_device(engines[g]), &second[g], false) != GKLB_OK) { second[g] = nullptr; np = 1; }
+      split(cut[g], cut[g + 1], np, &pieces[g]);
+    }
+    // k_first / k_last: when the device's first kernel could start and its last kernel ended, against an event recorded
+    // on the device before the first piece -- with two engines taking turns the per-piece kernel times overlap (a
+    // piece's kernels wait for the other engine's), so the device's kernel phase is the span, not the sum
+    struct DevAcc {
+      std::mutex mu; gklb_pairhmm_stats st{}; int rc = GKLB_OK; std::string err;
+      cudaEvent_t origin = nullptr; float k_first = 1e30f, k_last = 0.f;
+    };
+    std::vector<DevAcc> acc(n_dev);
+    for (int g = 0; g < n_dev; g++) {
+      if (!second[g]) continue;
+      if (cudaSetDevice(gklb_engine_device(engines[g])) != cudaSuccess ||
+          cudaEventCreate(&acc[g].origin) != cudaSuccess ||
+          cudaEventRecord(acc[g].origin, engines[g]->stream) != cudaSuccess) {
+        if (acc[g].origin) cudaEventDestroy(acc[g].origin);
+        acc[g].origin = nullptr;
+      }
+    }
+    auto run_pieces = [&](int g, gklb_engine* e, int first, int stride) {
+      const int np = (int)pieces[g].size() - 1;
+      std::vector<int64_t> offs;
+      for (int k = first; k < np; k += stride) {
+        const int lo = pieces[g][k], hi = pieces[g][k + 1];
+        if (hi == lo) continue;
+        const int64_t base = batch->read_off[lo];
+        offs.resize((size_t)(hi - lo) + 1);
+        for (int r = lo; r <= hi; r++) offs[r - lo] = batch->read_off[r] - base;
+        gklb_pairhmm_batch sub = *batch;
+        sub.n_reads = hi - lo;
+        sub.read_off = offs.data();
+        sub.read_bases = batch->read_bases + base;
+        sub.read_quals = batch->read_quals + base;
+        sub.ins_gop = batch->ins_gop + base;
+        sub.del_gop = batch->del_gop + base;
+        sub.gcp = batch->gcp + base;
+        double* slab = likelihoods + (size_t)lo * batch->n_haps;
+        int prc;
+        gklb_pairhmm_stats st;
+        float k0 = 0.f, k1 = 0.f;
+        {
+          std::lock_guard<std::mutex> lk(e->mu);
+          prc = do_compute(e, &sub, 1, &slab);
+          st = e->stats;
+          if (!prc && acc[g].origin &&
+              (cudaEventElapsedTime(&k0, acc[g].origin, e->ev[1]) != cudaSuccess ||
+               cudaEventElapsedTime(&k1, acc[g].origin, e->ev[2]) != cudaSuccess))
+            k0 = k1 = 0.f;
+        }
+        std::lock_guard<std::mutex> lk(acc[g].mu);
+        if (k1 > 0.f) { acc[g].k_first = std::min(acc[g].k_first, k0); acc[g].k_last = std::max(acc[g].k_last, k1); }
+        if (prc) {   // the last error is thread-local: carry it to the caller's thread
+          if (!acc[g].rc) { acc[g].rc = prc; acc[g].err = last_error_string(); }
+          return;
+        }
+        gklb_pairhmm_stats& a = acc[g].st;
+        a.pairs += st.pairs; a.cells += st.cells; a.fallback_pairs += st.fallback_pairs; a.fp64_pairs += st.fp64_pairs;
+        a.kernel_launches += st.kernel_launches;
+        a.n_classes = std::max(a.n_classes, st.n_classes);
+        // what is not hidden under another piece's kernels: the first piece's way in, the last piece's way out
+        if (k == 0) a.h2d_ms = st.h2d_ms;
+        if (k == np - 1) a.d2h_ms = st.d2h_ms;
+        a.kernel_ms += st.kernel_ms;   // one piece: its kernel time; several: replaced by the span below
+      }
+    };
     std::vector<std::thread> th;
     for (int g = 0; g < n_dev; g++) {
-      const int lo = cut[g], hi = cut[g + 1];
-      const int64_t base = batch->read_off[lo];
-      offs[g].resize((size_t)(hi - lo) + 1);
-      for (int r = lo; r <= hi; r++) offs[g][r - lo] = batch->read_off[r] - base;
-      sub[g] = *batch;
-      sub[g].n_reads = hi - lo;
-      sub[g].read_off = offs[g].data();
-      sub[g].read_bases = batch->read_bases + base;
-      sub[g].read_quals = batch->read_quals + base;
-      sub[g].ins_gop = batch->ins_gop + base;
-      sub[g].del_gop = batch->del_gop + base;
-      sub[g].gcp = batch->gcp + base;
-    }
-    for (int g = 0; g < n_dev; g++) {
-      th.emplace_back([&, g] {
-        if (sub[g].n_reads == 0) return;
-        std::lock_guard<std::mutex> lk(engines[g]->mu);
-        double* slab = likelihoods + (size_t)cut[g] * batch->n_haps;
-        rcs[g] = do_compute(engines[g], &sub[g], 1, &slab);
-        if (rcs[g]) errs[g] = last_error_string();  // the last error is thread-local: carry it to the caller's thread
-      });
+      const int workers = second[g] ? 2 : 1;
+      th.emplace_back(run_pieces, g, engines[g], 0, workers);
+      if (second[g]) th.emplace_back(run_pieces, g, second[g], 1, workers);
     }
     for (auto& t : th) t.join();
+    for (auto* e : second)
+      if (e) release(e);
+    for (int g = 0; g < n_dev; g++) {
+      if (!acc[g].origin) continue;
+      if (acc[g].k_last > acc[g].k_first) acc[g].st.kernel_ms = acc[g].k_last - acc[g].k_first;
+      cudaEventDestroy(acc[g].origin);
+    }
     for (int g = 0; g < n_dev && rc == GKLB_OK; g++) {
-      if (rcs[g]) { set_last_error(errs[g]); rc = rcs[g]; break; }
-      const gklb_pairhmm_stats& st = engines[g]->stats;
+      if (acc[g].rc) { set_last_error(acc[g].err); rc = acc[g].rc; break; }
+      const gklb_pairhmm_stats& st = acc[g].st;
       total_stats.pairs += st.pairs;
       total_stats.cells += st.cells;
       total_stats.fallback_pairs += st.fallback_pairs;

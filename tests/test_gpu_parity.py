@@ -463,3 +463,21 @@ def test_narrowed_result_reconstructs_the_likelihoods_exactly(eng):
     got[idx] = val
     assert np.array_equal(got, want)
     assert count == int((want < -64.0).sum()) or abs(count - int((want < -64.0).sum())) < 50
+
+
+def test_big_single_device_call_is_pipelined_in_pieces_and_bit_identical():
+    """gklb_pairhmm_compute cuts a shard of more than ~3e11 cells into pieces that two engines on the device take in
+    turn (the copies of one piece run under the kernels of the other); nothing but the schedule may change."""
+    native.global_init(False, 1)
+    try:
+        big = synth.config2(42000, 256)   # 3.2e11 cells -> two pieces
+        assert big.cells() > 3.0e11
+        out = native.global_compute(big)
+        st = native.global_stats()
+        assert st.pairs == big.n_reads * big.n_haps and st.cells == big.cells()
+        one = native.Engine(0, False)
+        assert np.array_equal(one.compute(big), out)
+        assert one.stats().kernel_launches < st.kernel_launches   # the pieces launched separately
+        one.close()
+    finally:
+        native.global_done()
