@@ -481,3 +481,33 @@ def test_big_single_device_call_is_pipelined_in_pieces_and_bit_identical():
         one.close()
     finally:
         native.global_done()
+
+
+def test_concurrent_big_calls_share_the_engine_pool_without_deadlock():
+    """Three threads, each with a call big enough to want two engines of the device's pool of four: the second engine is
+    only taken when free, the first one is waited for; every caller gets the single-engine result."""
+    import threading
+    native.global_init(False, 1)
+    try:
+        big = synth.config2(28000, 256)   # 2.1e11 cells -> two pieces
+        one = native.Engine(0, False)
+        want = one.compute(big)
+        one.close()
+        outs, errs = [None] * 3, []
+
+        def work(i):
+            try:
+                outs[i] = native.global_compute(big)
+            except Exception as ex:  # noqa: BLE001
+                errs.append(ex)
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(3)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=120)
+        assert not any(t.is_alive() for t in th) and not errs
+        for o in outs:
+            assert np.array_equal(o, want)
+    finally:
+        native.global_done()
