@@ -241,3 +241,66 @@ def test_unexpected_read_base_at_an_snp_column_is_rejected_like_the_reference(hm
                                      np.frombuffer(b"ACXGT", dtype=np.int8), *(np.full(5, q, dtype=np.int8) for q in (30, 40, 40, 10)))])
     ref, rc, _ = oracle.port_pdhmm(one, True, threads=1)
     assert rc == 0 and np.abs(hmm.compute_batch(one) - ref).max() <= 1e-9
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_fuzz_cross_batches_against_the_scalar_restatement(seed):
+    """Random cross-layout batches for k_pdhmm3 (both instantiations) and its deferrals: random PD bytes (SNP alleles
+    in every combination, nested / unclosed / adjacent deletion spans, spans at both ends), N and lower case on both
+    sides, ragged lengths from 1, qualities over a wide range; both row-state modes."""
+    rng = np.random.default_rng(7000 + seed)
+    max_read = 105 if seed % 2 == 0 else 155
+    n_reads, n_haps = int(rng.integers(1, 48)), int(rng.integers(1, 14))
+    letters = np.frombuffer(b"ACGT", dtype=np.int8)
+    haps = []
+    for _ in range(n_haps):
+        L = int(rng.integers(1, 320))
+        hb = letters[rng.integers(0, 4, size=L)].copy()
+        u = rng.random(L)
+        hb[u < 0.02] = ord("N")
+        low = (u > 0.02) & (u < 0.05)
+        hb[low] |= 0x20
+        pdb = np.zeros(L, dtype=np.int8)
+        v = rng.random(L)
+        snp = v < 0.06
+        pdb[snp] = (1 | (rng.integers(1, 16, size=int(snp.sum())) << 3)).astype(np.int8)
+        pdb[(v > 0.06) & (v < 0.085)] |= 2
+        pdb[(v > 0.085) & (v < 0.11)] |= 4
+        pdb[(v > 0.11) & (v < 0.115)] |= 6
+        if rng.random() < 0.3:
+            pdb[-1] |= int(rng.choice([2, 4, 6]))
+        if rng.random() < 0.3:
+            pdb[0] |= int(rng.choice([2, 4, 6]))
+        haps.append((hb, pdb))
+    reads = []
+    for _ in range(n_reads):
+        R = int(rng.integers(1, max_read + 1))
+        hb = haps[int(rng.integers(0, n_haps))][0]
+        s = int(rng.integers(0, max(1, len(hb) - R + 1)))
+        rb = np.resize(hb[s:s + R].copy() if len(hb[s:s + R]) else letters, R).astype(np.int8)
+        rb[rb == ord("n")] = ord("N")
+        mut = rng.random(R) < 0.05
+        rb[mut] = letters[rng.integers(0, 4, size=int(mut.sum()))]
+        rb[rng.random(R) < 0.02] = ord("N")
+        q = lambda lo, hi: rng.integers(lo, hi, size=R).astype(np.int8)
+        reads.append((rb, q(2, 61), q(5, 61), q(5, 61), q(1, 30)))
+    flat = pb.PdhmmBatch.cross(reads, haps)
+    rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
+    hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
+    for row_state in ("carry", "reset"):
+        ref, rc, _ = oracle.port_pdhmm(flat, row_state == "carry", threads=oracle.host_threads())
+        assert rc == 0
+        os.environ["GKLB_PDHMM_ROW_STATE"] = row_state
+        try:
+            h = IntelPDHMM()
+            h.initialize(None)
+            out = np.zeros(len(rd) * len(hp))
+            h.computeLikelihoods(rd, hp, out)
+            name = h.kernel_name()
+            h.done()
+        finally:
+            os.environ.pop("GKLB_PDHMM_ROW_STATE")
+        assert name.startswith("k_pdhmm3<16,7" if max_read == 105 and max(len(r[0]) for r in reads) <= 105 else "k_pdhmm3")
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(out), ok)
+        assert np.abs(out[ok] - ref[ok]).max() <= 1e-9, (seed, row_state)
