@@ -511,3 +511,17 @@ def test_concurrent_big_calls_share_the_engine_pool_without_deadlock():
             assert np.array_equal(o, want)
     finally:
         native.global_done()
+
+
+@pytest.mark.parametrize("read_len", [30, 36, 40, 66, 70, 78, 130, 142, 158])
+def test_single_class_launches_of_the_twelve_warp_kernels(eng, read_len):
+    """Uniform read lengths put a whole batch into one class; classes of up to 10 rows per lane then run as
+    k_h2_tasks<G, K, 12> (12 warps per SM) instead of the multi-class kernel the mixed-length tests exercise."""
+    b = synth.config2(600, 24, read_len)
+    out = eng.compute(b)
+    name = eng.sweep_kernel()
+    assert name.startswith("k_h2_tasks<") and name.endswith(",12>"), name
+    ref = checker(b)
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(out), ok)
+    assert rel(out[ok], ref[ok]).max() <= REL_TOL
