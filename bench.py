@@ -142,11 +142,42 @@ def measured_hbm_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def dram_traffic_record():
-    """DRAM bytes per launch of the dominant kernel: an ncu-derived constant (ncu cannot run inside a timed bench), so
-    it carries the commit and the capture it came from."""
+def dram_traffic_record(reads: int, haps: int, live: bool = True):
+    """DRAM bytes per launch of the dominant kernel.  Measured live when ncu is usable on this box: one launch of the
+    sweep on the same workload in a child process, after the timed region (ncu replays the kernel, so nothing timed
+    runs under it).  Falls back to the committed capture (profiles/r2_traffic.json, which names its commit)."""
+    import csv
+    import io
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if live and os.path.exists(ncu) and not os.environ.get("GKLB_BENCH_NO_NCU"):
+        cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units",
+               "base", "-k", "regex:k_h2|k_sweep_tasks", "-s", "2", "-c", "1", "--csv", sys.executable,
+               str(ROOT / "bench" / "profile_c2.py"), str(reads), "101", str(haps)]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=str(ROOT))
+            vals, kernel = {}, None
+            rows = list(csv.reader(io.StringIO(r.stdout)))
+            hdr = next((row for row in rows if "Metric Name" in row), None)
+            if hdr:
+                ni, vi, ki = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Kernel Name")
+                for row in rows[rows.index(hdr) + 1:]:
+                    if len(row) > vi and row[ni].startswith("dram__bytes"):
+                        vals[row[ni]] = float(row[vi].replace(",", ""))
+                        kernel = row[ki]
+            if len(vals) == 2:
+                total = vals["dram__bytes_read.sum"] + vals["dram__bytes_write.sum"]
+                return {"kernel": kernel, "workload": f"{reads} x {haps}, one launch, measured by this run",
+                        "dram_bytes_read": vals["dram__bytes_read.sum"], "dram_bytes_write": vals["dram__bytes_write.sum"],
+                        "dram_bytes_per_launch": total, "how": " ".join(cmd[:13]) + " python bench/profile_c2.py ...",
+                        "note": "the likelihoods stay in the 126 MB L2 until the device->host copy, so DRAM sees mostly "
+                                "the input records"}
+        except Exception:  # noqa: BLE001 -- no counters permission, ncu missing, timeout: use the committed capture
+            pass
     try:
-        return json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+        rec = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())
+        rec["note"] = "committed capture (ncu was not usable in this run); " + rec.get("note", "")
+        return rec
     except Exception:
         return None
 
@@ -343,7 +374,7 @@ def run_ours(args):
         sweep_per_launch_ms = sweep_ms / max(1, args.steps)
         ach_tf = cells * FLOP_PER_CELL / (sweep_per_launch_ms * 1e-3) / 1e12
         ach_gbs = algorithmic_bytes(b) / (sweep_per_launch_ms * 1e-3) / 1e9
-        traffic = dram_traffic_record()
+        traffic = dram_traffic_record(args.reads, args.haps, live=(world == 1))
         cpu_gcups, cpu_info = cpu_arm(b, 1, 1)
         cpu_out = cpu_info["out"]
         import oracle  # the CPU arm: one more figure, a single host thread on a 300-read slice of the same batch
