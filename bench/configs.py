@@ -29,6 +29,33 @@ FLOP_PER_CELL = 12
 PEAKS = {}  # {'fp32': fn, 'fp64': fn} -> (TFLOP/s, source); set by bench.py (bench.py and bench/ share a name)
 
 
+def _live_dram_bytes(kernel_regex: str, child: list):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch matching kernel_regex, from a child ncu capture (after
+    the timed region; ncu replays the kernel, nothing timed runs under it).  None when ncu is not usable."""
+    import csv
+    import io
+    import shutil
+    import subprocess
+    import sys
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu) or os.environ.get("GKLB_BENCH_NO_NCU"):
+        return None
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
+           "-k", f"regex:{kernel_regex}", "-s", "1", "-c", "1", "--csv", sys.executable, *child]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+        rows = list(csv.reader(io.StringIO(r.stdout)))
+        hdr = next((row for row in rows if "Metric Name" in row), None)
+        if not hdr:
+            return None
+        ni, vi = hdr.index("Metric Name"), hdr.index("Metric Value")
+        vals = [float(row[vi].replace(",", "")) for row in rows[rows.index(hdr) + 1:]
+                if len(row) > vi and row[ni].startswith("dram__bytes")]
+        return sum(vals) if len(vals) == 2 else None
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def _rel(gpu: np.ndarray, cpu: np.ndarray) -> float:
     fin = np.isfinite(cpu)
     if not np.array_equal(np.isfinite(gpu), fin):
@@ -175,6 +202,7 @@ def config5(device: int = 0) -> dict:
         cpu_gcups = sample.cells() / secs / 1e9
     peak, peak_src = PEAKS['fp64']()
     ach = cells * FLOP_PER_CELL / (kernel_ms * 1e-3) / 1e12
+    traffic = _live_dram_bytes("k_pdhmm3", [str(Path(__file__).resolve().parent / "profile_c5.py"), str(R)])
     return {
         "workload": "configs[4]: PDHMM, 10000 reads (len 101) x 128 haplotypes (len 200-400) with PD flag bytes",
         "cells": cells, "pairs": R * H, "value": cells / kernel_ms / 1e6, "unit": "GCUPS", "dtype": "f64",
@@ -188,7 +216,10 @@ def config5(device: int = 0) -> dict:
                    "against": f"restatement of pdhmm-serial.cc (bit-identical to GKL's scalar path), every pair, {t_chk:.1f} s",
                    "max_abs_diff_vs_gkl_fastest_on_cpu_sample": dev_avx, "tolerance": "1e-4 absolute (IntelPDHMMUnitTest.java:33)"},
         "roofline": {"bound": "fp64", "kernel": kernel_name, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                     "frac": ach / peak, "peak_source": peak_src, "flop_per_cell": FLOP_PER_CELL, "traffic": None},
+                     "frac": ach / peak, "peak_source": peak_src, "flop_per_cell": FLOP_PER_CELL,
+                     "traffic": traffic, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, child "
+                     "ncu capture after the timed region (null: ncu not usable); algorithmic bytes "
+                     f"{int(2 * H * ops.max_hap + 5 * R * ops.max_read + 8 * R * H)}"},
         "cpu_baseline": {"value": cpu_gcups, "unit": "GCUPS", "cores": threads, "kind": kind,
                          "sample": f"first {n_cpu} reads x all haplotypes ({detail})"},
     }
