@@ -150,7 +150,9 @@ def dram_traffic_record(reads: int, haps: int, live: bool = True):
     import io
     import shutil
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
-    if live and os.path.exists(ncu) and not os.environ.get("GKLB_BENCH_NO_NCU"):
+    under_profiler = any(os.environ.get(k) for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                                                      "NV_NSIGHT_INJECTION_TRANSPORT_TYPE"))
+    if live and os.path.exists(ncu) and not under_profiler and not os.environ.get("GKLB_BENCH_NO_NCU"):
         cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units",
                "base", "-k", "regex:k_h2|k_sweep_tasks", "-s", "2", "-c", "1", "--csv", sys.executable,
                str(ROOT / "bench" / "profile_c2.py"), str(reads), "101", str(haps)]

@@ -38,7 +38,9 @@ def _live_dram_bytes(kernel_regex: str, child: list):
     import subprocess
     import sys
     ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
-    if not os.path.exists(ncu) or os.environ.get("GKLB_BENCH_NO_NCU"):
+    under_profiler = any(os.environ.get(k) for k in ("CUDA_INJECTION64_PATH", "NV_COMPUTE_PROFILER_PERFWORKS_DIR",
+                                                      "NV_NSIGHT_INJECTION_TRANSPORT_TYPE"))
+    if not os.path.exists(ncu) or under_profiler or os.environ.get("GKLB_BENCH_NO_NCU"):
         return None
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "--print-units", "base",
            "-k", f"regex:{kernel_regex}", "-s", "1", "-c", "1", "--csv", sys.executable, *child]
