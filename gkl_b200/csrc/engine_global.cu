@@ -10,7 +10,10 @@
 // the idle engines' device memory, and a later compute simply creates engines again.
 // Large batches (more than ~4e9 cells per device) are sharded over reads across the configured devices inside
 // the one call (GKLB_SHARD=direct: one host thread per device, each device copies its shard over its own PCIe
-// link and writes its slab of the caller's array; GKLB_SHARD=nccl: see engine_nccl.cu).
+// link and writes its slab of the caller's array -- a shard of more than ~2e11 cells as pieces that two engines on
+// the device take in turn, so that the copies of one piece run under the kernels of the other; GKLB_SHARD=nccl: see
+// engine_nccl.cu).  Multi-region calls (gklb_pairhmm_compute_multi) are cut into jobs of bounded size, one per device
+// when there is enough work.
 #include <stdlib.h>
 #include <string.h>
 
