@@ -63,8 +63,9 @@ __device__ __forceinline__ double pd_gap(double a, double ca, double b, double c
 }
 
 // pdhmm-serial.cc:411,432-441: log10(sum) - log10(initial condition); a result above 0 or a NaN is PDHMM_FAILURE
-__device__ __forceinline__ void pd_store_result(const PdhmmParams& p, long long item, double sum) {
-  const double r = log10(sum) - p.log10_init;
+__device__ __forceinline__ void pd_store_result(const PdhmmParams& p, long long item, double sum, int shift = 0) {
+  // shift: the kernel ran with the initial condition lowered by that many bits (0.30102999566398120 = log10 2)
+  const double r = log10(sum) - (p.log10_init - (double)shift * 0.30102999566398120);
   if (!(r <= 0.0)) atomicOr(p.error_flag, 2u);
   p.out[item] = r;
 }
@@ -863,12 +864,28 @@ __device__ __forceinline__ int pd_assign_column_ids(int lane, int H, int max_hap
 // k_pdhmm3 keeps the deletion state divided by its row's match-to-deletion probability (Y = D / tMD): the update
 // becomes one fused multiply-add, Y' = M + Y * tDD, and the match state reads it back through bD = tMD(row above) * tIM.
 // Y never exceeds the sum of its row's match values, which the total probability mass bounds by the initial condition.
-__device__ __forceinline__ double pd_match_y(double prior, double dM, double dI, double dY, double tMM, double tIM,
-                                             double bD) {
-  return __dmul_rn(prior, fma(dY, bD, fma(dI, tIM, __dmul_rn(dM, tMM))));
+//
+// WFOLD: the insertion state is folded the same way, W = I / tMI(row): W' = M(up) + W(up) * kap with
+// kap = tII * tMI(row above) / tMI(row), and the match state reads it through bI = tMI(row above) * tIM -- six fp64
+// operations per cell instead of seven.  W's scale crosses rows: W(j) <= (max tMI / min tMI over the read) * sum of the
+// match values above, so the host only selects this variant when every read's insertion qualities span at most 30 dB
+// (a factor 2^10), and the kernel then runs with the initial condition lowered by kPdWFoldShift bits, which keeps W
+// below 2^1013 for any haplotype and read length; the result subtracts the same shift.  Values that the reference
+// still holds as fp64 denormals would be lost 24 bits earlier: the host also requires the likelihood's lower bound
+// (one match, one gap open, gap extensions) to stay far above that range (pdhmm_engine.cu: wfold_ok).
+constexpr int kPdWFoldShift = 24;
+__device__ __forceinline__ double pd_match_y(double prior, double dM, double dI, double dY, double tMM, double cI,
+                                             double bD) {   // cI: tIM, or bI when the insertion state is folded
+  return __dmul_rn(prior, fma(dY, bD, fma(dI, cI, __dmul_rn(dM, tMM))));
+}
+// the insertion update: I' = M(up) * tMI + I(up) * tII, or folded W' = M(up) + W(up) * kap
+template <bool WFOLD>
+__device__ __forceinline__ double pd_ins(double tM, double tI, double tMI, double c) {   // c: tII, or kap
+  if constexpr (WFOLD) return fma(tI, c, tM);
+  else return pd_gap(tM, tMI, tI, c);
 }
 
-template <int G, int K, int WARPS, int NID>
+template <int G, int K, int WARPS, int NID, bool WFOLD>
 __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, int read_block, int n_blocks,
                                                           unsigned int n_tasks, uint8_t* deferred) {
   static_assert(G == 16 || G == 32, "one or two reads per warp");
@@ -917,7 +934,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
       if (lane == 0) deferred[hi] = 1;
       continue;
     }
-    const double init = p.init_cond / (double)H;
+    const double init = (WFOLD ? scalbn(p.init_cond, -kPdWFoldShift) : p.init_cond) / (double)H;
     const int n_steps = H + G - 1;
 
     for (long long r0 = r_begin; r0 < r_end; r0 += GPW) {
@@ -933,7 +950,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
 #pragma unroll
       for (int j = 0; j < K; j++) {
         const int row = t * K + j - n_pad;
-        tMM[j] = tIM[j] = tMI[j] = 0.0;
+        tMM[j] = tIM[j] = 0.0;
+        tMI[j] = WFOLD ? 1.0 : 0.0;   // folded: the scale of a padding row's (zero) insertion state
         tII[j] = tMD[j] = 1.0;
         pMa[j] = pMi[j] = 0.0;
         rbit[j] = 0;
@@ -967,6 +985,21 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           bD[j] = __dmul_rn(above, tIM[j]);
           above = tMD[j];
         }
+      }
+      // WFOLD: cI = bI (what the match state multiplies the W of the row above with), cW = kap; else tIM and tII
+      double cI[K], cW[K];
+      const double tMI_last = tMI[K - 1];
+      if constexpr (WFOLD) {
+        double above = shfl_up_d(tMI[K - 1], G);
+#pragma unroll
+        for (int j = 0; j < K; j++) {
+          cI[j] = __dmul_rn(above, tIM[j]);
+          cW[j] = __ddiv_rn(__dmul_rn(tII[j], above), tMI[j]);
+          above = tMI[j];
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < K; j++) { cI[j] = tIM[j]; cW[j] = tII[j]; }
       }
       double M[K], I[K], D[K];   // D holds Y
 #pragma unroll
@@ -1008,14 +1041,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
 #pragma unroll
         for (int j = 0; j < K; j++) {
           const double prior = pt[j * 32];
-          const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
+          const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], cI[j], bD[j]);
           const double nD = fma(Di[j], tII[j], Mi[j]);
-          const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
+          const double nI = pd_ins<WFOLD>(tM, tI, tMI[j], cW[j]);
           dM = Mi[j]; dI = Ii[j]; dD = Di[j];
           Mo[j] = nM; Io[j] = nI; Do[j] = nD;
           tM = nM; tI = nI;
         }
-        const double add = Mo[K - 1] + Io[K - 1];
+        const double add = WFOLD ? fma(Io[K - 1], tMI_last, Mo[K - 1]) : Mo[K - 1] + Io[K - 1];
         if constexpr (decltype(masked)::value) sum += (c <= H) ? add : 0.0;
         else sum += add;
         gM = uM; gI = uI; gD = uD;
@@ -1058,9 +1091,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
 #pragma unroll
           for (int j = 0; j < K; j++) {
             const double prior = pt[j * 32];
-            const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], tIM[j], bD[j]);
+            const double nM = pd_match_y(prior, dM, dI, dD, tMM[j], cI[j], bD[j]);
             const double nD = fma(Di[j], tII[j], Mi[j]);
-            const double nI = pd_gap(tM, tMI[j], tI, tII[j]);
+            const double nI = pd_ins<WFOLD>(tM, tI, tMI[j], cW[j]);
             dM = Mi[j]; dI = Ii[j]; dD = Di[j];
             Mo[j] = nM; Io[j] = nI; Do[j] = nD;
             tM = nM; tI = nI;
@@ -1070,14 +1103,14 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           double tM = uM, tI = uI, tbM = ubM, tbI = ubI;
 #pragma unroll
           for (int j = 0; j < K; j++) {
-            const double nI = pd_gap(dmax(tbM, tM), tMI[j], dmax(tbI, tI), tII[j]);
+            const double nI = pd_ins<WFOLD>(dmax(tbM, tM), dmax(tbI, tI), tMI[j], cW[j]);
             Io[j] = del_end ? nI : Io[j];
             tM = Mo[j]; tI = Io[j];
             tbM = tw_me[(3 * j) * 32]; tbI = tw_me[(3 * j + 1) * 32];
           }
         }
         {
-          const double add = Mo[K - 1] + Io[K - 1];
+          const double add = WFOLD ? fma(Io[K - 1], tMI_last, Mo[K - 1]) : Mo[K - 1] + Io[K - 1];
           sum += inrange ? add : 0.0;
         }
         gM = uM; gI = uI; gD = uD; gbM = ubM; gbI = ubI; gbD = ubD;
@@ -1128,7 +1161,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_pdhmm3(const PdhmmParams p, i
           s++;
         }
       }
-      if (t == G - 1 && mine) pd_store_result(p, item, sum);
+      if (t == G - 1 && mine) pd_store_result(p, item, sum, WFOLD ? kPdWFoldShift : 0);
     }
   }
 }

@@ -44,11 +44,14 @@ constexpr int kNumV2 = (int)(sizeof(kV2) / sizeof(kV2[0]));
 // k_pdhmm3 instantiations (cross layout only): lanes per read, rows per lane, warps per CTA, longest read (lane 0 of a
 // read stays all padding).  Two 101-base reads per warp, or one read of up to 155 rows.
 // `ids`: kinds of columns the per-pair prior table holds, one of them "no column" (haplotypes with more go to k_pdhmm2).
-struct V3Config { int G, K, warps, ids, max_read; const void* fn; };
+struct V3Config { int G, K, warps, ids, max_read; const void* fn; const void* fn_wfold; };
+#define GKLB_V3(G, K, W, N)                                                          \
+  {G, K, W, N, G * K - K, reinterpret_cast<const void*>(&k_pdhmm3<G, K, W, N, false>), \
+   reinterpret_cast<const void*>(&k_pdhmm3<G, K, W, N, true>)}
 const V3Config kV3[] = {
-    {16, 7, 8, 11, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 11>)},   // haplotypes of up to ~470 columns
-    {16, 7, 8, 9, 16 * 7 - 7, reinterpret_cast<const void*>(&k_pdhmm3<16, 7, 8, 9>)},
-    {32, 5, 8, 11, 32 * 5 - 5, reinterpret_cast<const void*>(&k_pdhmm3<32, 5, 8, 11>)},
+    GKLB_V3(16, 7, 8, 11),   // haplotypes of up to ~470 columns
+    GKLB_V3(16, 7, 8, 9),
+    GKLB_V3(32, 5, 8, 11),
 };
 constexpr int kNumV3 = (int)(sizeof(kV3) / sizeof(kV3[0]));
 size_t v3_smem(const V3Config& c, size_t col_pitch) {
@@ -121,6 +124,7 @@ struct PdEngine {
   // k_pdhmm3 takes the haplotypes whose rows all start NORMAL, k_pdhmm2 the deferred rest (same task space)
   bool use_v3 = false, allow_v3 = true;
   int v3 = 0;  // index into kV3
+  bool wfold = false;  // the variant with the folded insertion state (wfold_ok)
   int n_deferred = 0;
   size_t v3_smem_bytes = 0;
   int v3_grid = 0;
@@ -170,7 +174,8 @@ int launch(PdEngine* e) {
       // second launch always follows (a few microseconds when nothing was deferred)
       uint8_t* deferred = static_cast<uint8_t*>(e->deferred.p);
       void* args3[] = {&e->last, &e->read_block, &e->n_blocks, &e->n_tasks, &deferred};
-      CU(cudaLaunchKernel(kV3[e->v3].fn, dim3(e->v3_grid), dim3(kV3[e->v3].warps * 32), args3, e->v3_smem_bytes, e->stream));
+      CU(cudaLaunchKernel(e->wfold ? kV3[e->v3].fn_wfold : kV3[e->v3].fn, dim3(e->v3_grid), dim3(kV3[e->v3].warps * 32), args3,
+                          e->v3_smem_bytes, e->stream));
       e->stats.kernel_launches++;
       only = deferred;
       void* args2[] = {&e->last, &e->read_block2, &e->n_blocks2, &e->n_tasks2, &only};
@@ -252,6 +257,32 @@ bool unexpected_base_at_snp_column(const gklb_pdhmm_batch* b, bool cross, long l
   for (long long k : odd_reads)
     if (odd_bytes(k).differs_from(snp_bytes(k))) return true;
   return false;
+}
+
+// May k_pdhmm3 fold the insertion state (pdhmm_device.cuh, WFOLD)?  Per read: the insertion qualities span at most
+// 30 dB (the folded state's scale crosses rows by that ratio), and the likelihood's lower bound -- one (mis)match, one
+// gap open, gap extensions for the other rows, whatever the haplotype -- stays some 40 decades above the range the
+// lowered initial condition gives up (results under about -607).  One pass over three of the read arrays.
+bool wfold_ok(const gklb_pdhmm_batch* b, long long n_read_rows) {
+  if (const char* w = getenv("GKLB_PDHMM_WFOLD"))
+    if (!strcmp(w, "0")) return false;
+  for (long long r = 0; r < n_read_rows; r++) {
+    const long long len = b->read_lengths[r], o = r * (long long)b->max_read;
+    const uint8_t* iq = reinterpret_cast<const uint8_t*>(b->read_ins_qual) + o;
+    const uint8_t* gq = reinterpret_cast<const uint8_t*>(b->gcp) + o;
+    const uint8_t* qq = reinterpret_cast<const uint8_t*>(b->read_qual) + o;
+    uint8_t mn = 255, mx = 0, qmax = 0;
+    unsigned gsum = 0;
+    for (long long i = 0; i < len; i++) {
+      mn = std::min(mn, iq[i]);
+      mx = std::max(mx, iq[i]);
+      qmax = std::max(qmax, qq[i]);
+      gsum += gq[i];
+    }
+    if (mx - mn > 30 || mx > 127) return false;                      // bytes above 127 are negative qualities: error path
+    if (gsum + (unsigned)qmax + (unsigned)mx + 80u > 5600u) return false;   // decades * 10, incl. log10(3 H)
+  }
+  return true;
 }
 
 // n_reads/n_haps > 0: cross layout; else flat with b->n pairs.
@@ -397,6 +428,7 @@ int compute(PdEngine* e, const gklb_pdhmm_batch* b, int n_reads, int n_haps, dou
       e->n_blocks = (int)((n_reads + e->read_block - 1) / e->read_block);
       tasks = (long long)e->n_blocks * n_haps;
       e->use_v3 = true;
+      e->wfold = wfold_ok(b, n_read_rows);
       {
         const long long resident = (long long)kV2[e->v2].warps * e->num_sms;
         long long rb2 = std::max<long long>(1, (long long)n_reads * std::max(1, e->n_deferred) / (2 * resident));
@@ -470,7 +502,10 @@ int create_pd_engine(PdEngine** out) {
   CU(cudaFuncSetAttribute(reinterpret_cast<const void*>(&k_pdhmm<kG, kK, kWarps, true>),
                           cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
   for (const V2Config& c : kV2) CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-  for (const V3Config& c : kV3) CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  for (const V3Config& c : kV3) {
+    CU(cudaFuncSetAttribute(c.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+    CU(cudaFuncSetAttribute(c.fn_wfold, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+  }
   const PdTables& t = pd_tables();
   CU(e->tables.ensure(sizeof(double) * (kMaxQual + 1 + kMmSizePd)));
   CU(cudaMemcpy(e->tables.p, t.q2err, sizeof(t.q2err), cudaMemcpyHostToDevice));
@@ -603,7 +638,8 @@ const char* gklb_pdhmm_kernel_name(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   const PdEngine* e = g_last;
   if (!e || !e->have_last) return "";
-  if (e->use_v2 && e->use_v3) snprintf(name, sizeof(name), "k_pdhmm3<%d,%d,%d>", kV3[e->v3].G, kV3[e->v3].K, kV3[e->v3].warps);
+  if (e->use_v2 && e->use_v3)
+    snprintf(name, sizeof(name), "k_pdhmm3<%d,%d,%d%s>", kV3[e->v3].G, kV3[e->v3].K, kV3[e->v3].warps, e->wfold ? ",wfold" : "");
   else if (e->use_v2) snprintf(name, sizeof(name), "k_pdhmm2<%d,%d>", kV2[e->v2].K, kV2[e->v2].warps);
   else snprintf(name, sizeof(name), "k_pdhmm<%d,%d,%d>", kG, kK, kWarps);
   return name;

@@ -283,7 +283,9 @@ def test_fuzz_cross_batches_against_the_scalar_restatement(seed):
         rb[mut] = letters[rng.integers(0, 4, size=int(mut.sum()))]
         rb[rng.random(R) < 0.02] = ord("N")
         q = lambda lo, hi: rng.integers(lo, hi, size=R).astype(np.int8)
-        reads.append((rb, q(2, 61), q(5, 61), q(5, 61), q(1, 30)))
+        # insertion qualities within 30 dB let the engine pick the kernel variant with the folded insertion state
+        ins = q(18, 46) if seed % 4 < 2 else q(5, 61)
+        reads.append((rb, q(2, 61), ins, q(5, 61), q(1, 30)))
     flat = pb.PdhmmBatch.cross(reads, haps)
     rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
     hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
@@ -301,6 +303,48 @@ def test_fuzz_cross_batches_against_the_scalar_restatement(seed):
         finally:
             os.environ.pop("GKLB_PDHMM_ROW_STATE")
         assert name.startswith("k_pdhmm3<16,7" if max_read == 105 and max(len(r[0]) for r in reads) <= 105 else "k_pdhmm3")
+        assert name.endswith(",wfold>") == (seed % 4 < 2)
         ok = np.isfinite(ref)
         assert np.array_equal(np.isfinite(out), ok)
         assert np.abs(out[ok] - ref[ok]).max() <= 1e-9, (seed, row_state)
+
+
+def test_folded_insertion_state_variant_against_the_unfolded_one():
+    """k_pdhmm3<..., wfold> (insertion qualities within 30 dB, the config-5 shape) against the variant without the fold
+    (GKLB_PDHMM_WFOLD=0) and the scalar restatement; a read whose insertion qualities span more switches the fold off
+    for the batch."""
+    from gkl_b200 import synth
+    reads, haps = synth.config5(90, 20, seed=23)
+    flat = pb.PdhmmBatch.cross(reads, haps)
+    ref, rc, _ = oracle.port_pdhmm(flat, True, threads=oracle.host_threads())
+    assert rc == 0
+    rd = [PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads]
+    hp = [PDHaplotypeDataHolder(h[0].tobytes(), h[1].tobytes()) for h in haps]
+    got, names = {}, {}
+    for mode in ("1", "0"):
+        os.environ["GKLB_PDHMM_WFOLD"] = mode
+        try:
+            h = IntelPDHMM()
+            h.initialize(None)
+            out = np.zeros(len(rd) * len(hp))
+            h.computeLikelihoods(rd, hp, out)
+            got[mode], names[mode] = out, h.kernel_name()
+            h.done()
+        finally:
+            os.environ.pop("GKLB_PDHMM_WFOLD")
+    assert names["1"].endswith(",wfold>") and not names["0"].endswith(",wfold>")
+    assert np.abs(got["1"] - ref).max() <= 1e-9 and np.abs(got["0"] - ref).max() <= 1e-9
+    assert np.abs(got["1"] - got["0"]).max() <= 1e-9
+    wide = list(reads)
+    r0 = tuple(x.copy() for x in wide[0])
+    r0[2][0], r0[2][1] = 5, 60   # 55 dB between two insertion qualities of one read
+    wide[0] = r0
+    h = IntelPDHMM()
+    h.initialize(None)
+    out = np.zeros(len(rd) * len(hp))
+    h.computeLikelihoods([PDReadDataHolder(*(x.tobytes() for x in r)) for r in wide], hp, out)
+    name = h.kernel_name()
+    h.done()
+    assert not name.endswith(",wfold>")
+    ref2 = oracle.port_pdhmm(pb.PdhmmBatch.cross(wide, haps), True, threads=oracle.host_threads())[0]
+    assert np.abs(out - ref2).max() <= 1e-9
