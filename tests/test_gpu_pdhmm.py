@@ -348,3 +348,39 @@ def test_folded_insertion_state_variant_against_the_unfolded_one():
     assert not name.endswith(",wfold>")
     ref2 = oracle.port_pdhmm(pb.PdhmmBatch.cross(wide, haps), True, threads=oracle.host_threads())[0]
     assert np.abs(out - ref2).max() <= 1e-9
+
+
+def test_folded_insertion_state_at_the_top_of_the_fp64_range():
+    """The fold's scale argument at its limits: insertion qualities alternating over exactly 30 dB, gap continuation
+    penalties of 1 and 2 (long geometric sums of the folded states), haplotypes of 1..8 columns (the initial condition 2^1020 / H
+    at its largest) and full-length reads -- no overflow, same values as the scalar restatement."""
+    rng = np.random.default_rng(77)
+    letters = np.frombuffer(b"ACGT", dtype=np.int8)
+    haps = []
+    for L in (1, 1, 2, 3, 5, 8, 40, 300):
+        hb = letters[rng.integers(0, 4, size=L)].copy()
+        pdb = np.zeros(L, dtype=np.int8)
+        if L >= 3:
+            pdb[1] = 33
+        haps.append((hb, pdb))
+    reads = []
+    for k in range(24):
+        R = 105 if k % 3 else int(rng.integers(1, 106))
+        rb = letters[rng.integers(0, 4, size=R)].copy()
+        lo, hi = (15, 45) if k % 2 else (0, 30)
+        ins = np.where(np.arange(R) % 2 == (k // 2) % 2, lo, hi).astype(np.int8)
+        gcp = np.full(R, 0 if k % 8 == 7 else 1 + (k % 3 == 0), dtype=np.int8)   # 0: no way back from an insertion
+        reads.append((rb, rng.integers(2, 61, size=R).astype(np.int8), ins, rng.integers(0, 61, size=R).astype(np.int8), gcp))
+    flat = pb.PdhmmBatch.cross(reads, haps)
+    ref, rc, _ = oracle.port_pdhmm(flat, True, threads=oracle.host_threads())
+    assert rc == 0 and np.isfinite(ref).mean() > 0.8
+    h = IntelPDHMM()
+    h.initialize(None)
+    out = np.zeros(len(reads) * len(haps))
+    h.computeLikelihoods([PDReadDataHolder(*(x.tobytes() for x in r)) for r in reads],
+                         [PDHaplotypeDataHolder(x[0].tobytes(), x[1].tobytes()) for x in haps], out)
+    name = h.kernel_name()
+    h.done()
+    assert name.endswith(",wfold>")
+    ok = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(out), ok) and np.abs(out[ok] - ref[ok]).max() <= 1e-9
