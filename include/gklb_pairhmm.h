@@ -108,7 +108,9 @@ GKLB_API int gklb_pairhmm_init(int use_double, int max_threads);
  * borrows its own engine from the pool, on the least busy configured device (Spark executors call
  * computeLikelihoods from several threads, IntelPairHmm.java:65 synchronises only load()).  With several
  * devices, batches of more than ~4e9 cells per device are sharded over reads inside the call (env GKLB_SHARD =
- * direct | nccl, see engine_global.cu / engine_nccl.cu). */
+ * direct | nccl, see engine_global.cu / engine_nccl.cu); in the direct mode a device's share of more than ~2e11
+ * cells runs as pieces on two engines in turn, so that the copies of one piece overlap the kernels of the other.
+ * The result does not depend on any of this (bit-identical to a single engine's). */
 GKLB_API int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likelihoods);
 
 /* Several regions in one call (what a GATK-side queue that coalesces active regions would call;
@@ -116,7 +118,9 @@ GKLB_API int gklb_pairhmm_compute(const gklb_pairhmm_batch* batch, double* likel
  * are staged with one host->device copy and share the launches: the tasks of every region of a launch group are
  * pulled from one queue, so many small regions fill the GPU like one large batch.  likelihoods[r] receives
  * region r's matrix (double[n_reads * n_haps]); results are bit-identical to one gklb_pairhmm_compute per region.
- * Regions with no reads or no haplotypes are skipped. */
+ * Regions with no reads or no haplotypes are skipped.  Through this (global) entry point the regions are cut into
+ * jobs of at most ~192 MB of staging, one job per configured device when every job still holds about a millisecond
+ * of work; a region large enough to shard goes through gklb_pairhmm_compute on its own. */
 GKLB_API int gklb_pairhmm_compute_multi(const gklb_pairhmm_batch* batches, int n_batches, double* const* likelihoods);
 
 /* doneNative.  Drops one reference; the last one frees the idle engines (device memory, streams, events).
@@ -124,7 +128,9 @@ GKLB_API int gklb_pairhmm_compute_multi(const gklb_pairhmm_batch* batches, int n
 GKLB_API int gklb_pairhmm_done(void);
 
 /* Number of devices the global surface was initialised with, engines currently alive in the pool, and the
- * counters of the last compute call that finished (summed over devices; phase times are the maximum). */
+ * counters of the last compute call that finished (summed over devices; phase times are the maximum over the devices --
+ * for a device that ran its share in pieces: the first piece's way in, the span of its kernels, the last piece's way
+ * out). */
 GKLB_API int gklb_pairhmm_devices_in_use(void);
 GKLB_API int gklb_pairhmm_engines_alive(void);
 GKLB_API int gklb_pairhmm_last_stats(gklb_pairhmm_stats* out);
