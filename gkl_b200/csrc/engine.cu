@@ -77,16 +77,16 @@ namespace {
 //   fp64 kernels (useDoublePrecision, rerun): rows per pass = G * K from this table
 struct ClassDef { int G, K; };
 const ClassDef kClassesD1[] = {{8, 4},  {8, 5},  {8, 6},  {8, 7},  {8, 8},  {16, 5}, {16, 6},
-                               {16, 7}, {16, 8}, {32, 5}, {32, 6}, {32, 7}, {32, 8}};
+                               {16, 7}, {16, 8}, {32, 5}, {32, 6}, {32, 7}, {32, 8}, {32, 9}, {32, 10}};
 const int kNumClassesD1 = (int)(sizeof(kClassesD1) / sizeof(kClassesD1[0]));
 //   fp32 H2 kernels: G = 4, 8, 16 lanes x K = 8..16 rows (32..64 rows in steps of 4, 72..128 in steps of 8,
-//   144..256 in steps of 16); cfg = gi * 9 + (K - 8)
-const int kNumClassesH2 = 27;
+//   144..256 in steps of 16) and G = 32 x K = 9, 10 (288 and 320 rows); cfg = gi * 9 + (K - 8), cfg 27 is unused
+const int kNumClassesH2 = 30;
 inline int h2_G(int cfg) { return 4 << (cfg / 9); }
 inline int h2_K(int cfg) { return 8 + cfg % 9; }
 const int kH2Warps = 8;
 const int kMultiG = 32, kMultiK = 8;
-const int kSinglePassMax = 256;
+const int kSinglePassMax = 320;  // 32 x 10: the largest single-pass class of both tables
 const int kSmemMax = 232448;  // 227 KB opt-in dynamic shared memory per CTA on sm_100
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -165,7 +165,7 @@ int plan_classes(gklb_engine* e, const gklb_pairhmm_batch* b, int region, int re
     } else if (L <= kSinglePassMax) {
       int ci = 0;
       if (h2) {
-        const int gi = L <= 64 ? 0 : L <= 128 ? 1 : 2;
+        const int gi = L <= 64 ? 0 : L <= 128 ? 1 : L <= 256 ? 2 : 3;
         ci = gi * 9 + std::max(0, (L + (4 << gi) - 1) / (4 << gi) - 8);
       } else {
         while (kClassesD1[ci].G * kClassesD1[ci].K < L) ci++;
@@ -573,7 +573,7 @@ void fill_h2_class(gklb_engine* e, const EntryInst& en, int warps, bool resident
   cls->fb_pairs = counters + en.counter0 + 2;
   cls->fb_count = counters + en.counter0 + 1;
   cls->fb_items = e->d_fb.p ? static_cast<uint2*>(e->d_fb.p) + en.fb_off : nullptr;
-  cls->use_r2 = use_r2_env() ? 1 : 0;
+  cls->use_r2 = e->r2_on ? 1 : 0;
   cls->n_rec = c.n_rec;
   cls->rows = c.rows;
   cls->stride = c.stride;
@@ -817,7 +817,7 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
     std::vector<int> h2all;  // every H2 entry, forced ones included (their lists have the same format)
     for (int i = 0; i < n_ent; i++)
       if (cls_of(ents[i]).kf->policy == POL_H2) h2all.push_back(i);
-    if (!use_r2_env()) {
+    if (!e->r2_on) {
       // the H2 sweep appended its flagged pairs straight to the fp64 lists
     } else if (h2_mega) {
       R2MegaParams mp;
@@ -897,7 +897,7 @@ int build_plan(gklb_engine* e, uint8_t* hm) {
 
 }  // namespace
 
-bool use_r2() { return use_r2_env(); }
+bool use_r2(const gklb_engine* e) { return e->r2_on; }
 
 void read_fallback_count(gklb_engine* e) {
   int64_t fb = 0, f64 = 0;
@@ -1007,6 +1007,9 @@ int do_stage(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, bool hap_
   for (int r = 0; r < k; r++)
     if (e->regions[r].n_reads && (rc = plan_classes(e, &batches[r], r, e->regions[r].read_base))) return rc;
   tm.lap(1);
+  e->r2_on = use_r2_env();
+  for (auto& c : e->classes)
+    if (c.kf && c.kf->policy == POL_H2 && c.G > 16) e->r2_on = false;   // no range-extended kernels for 32 lanes
   const long long budget = image_budget(e);
   for (int r = 0; r < k; r++)
     if (e->regions[r].n_reads && (rc = plan_tiles(e, &hb[r], r, budget))) return rc;

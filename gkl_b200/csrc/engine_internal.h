@@ -124,6 +124,7 @@ struct gklb_engine {
   bool use_double = false;
   int num_sms = 0;
   cudaStream_t own_stream = nullptr, stream = nullptr;
+  bool r2_on = false;  // staged job: GKLB_R2=1 and every H2 class has an R2 kernel (G <= 16)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   std::vector<cudaEvent_t> kev;  // pairs of events around each forward-sweep launch of the last run
   int kev_used = 0;
@@ -173,7 +174,7 @@ int do_submit(gklb_engine* e, const gklb_pairhmm_batch* batches, int k, double* 
 int do_wait(gklb_engine* e);
 // stats.fallback_pairs / fp64_pairs from the counters last copied to e->h_counters
 void read_fallback_count(gklb_engine* e);
-bool use_r2();  // GKLB_R2=1: the H2 sweep's flagged pairs go through the range-extended fp32 rerun
+bool use_r2(const gklb_engine* e);  // this job's flagged pairs go through the range-extended fp32 rerun (GKLB_R2=1)
 // Write the haplotype bases of the staged (single-region) job's panel images from a device buffer laid out like the
 // batch's hap_bases arena (kernels on the engine's stream).
 int fill_panels_from_device(gklb_engine* e, const uint8_t* hap_bases_dev);

@@ -160,7 +160,7 @@ int enqueue_narrow(gklb_engine* e, float* f32, uint32_t* idx, double* val, unsig
     const ClassInst& c = e->classes[en.cls];
     const Tile& t = e->tiles[en.tile];
     const unsigned int* cnt = static_cast<const unsigned int*>(e->d_counters.p) + en.counter0;
-    if (c.kf->policy == POL_H2 && use_r2()) {  // the H2 sweep's flagged pairs are rerun items (record, pair | mask)
+    if (c.kf->policy == POL_H2 && use_r2(e)) {  // the H2 sweep's flagged pairs are rerun items (record, pair | mask)
       k_collect_overrides_r2<<<e->num_sms, 256, 0, e->stream>>>(
           static_cast<const uint2*>(e->d_r2.p) + en.r2_off, cnt, reinterpret_cast<const int32_t*>(dm + c.meta_rid),
           dm + t.pmeta_off, t.n_pairs, H, static_cast<const double*>(e->d_out.p), idx, val, cursor, cap);

@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
 // fills the GPU with a single launch instead of a dozen serialised under-filled ones.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxMegaClasses = 1024;  // (class, panel) entries of one multi-class launch
-constexpr int kCfgMulti = 13;  // configuration index of the multi-pass class (32 x 8 rows per pass)
+constexpr int kCfgMulti = 15;  // configuration index of the multi-pass class (32 x 8 rows per pass)
 
 struct MegaParams {
   int n_classes;
@@ -1023,6 +1023,8 @@ __device__ __noinline__ uint32_t mega_item(const SweepParams& p, unsigned int wi
     case 10: ctx.slot_parity = FN<P, 32, 6, false, WARPS>(__VA_ARGS__); break;                 \
     case 11: ctx.slot_parity = FN<P, 32, 7, false, WARPS>(__VA_ARGS__); break;                 \
     case 12: ctx.slot_parity = FN<P, 32, 8, false, WARPS>(__VA_ARGS__); break;                 \
+    case 13: ctx.slot_parity = FN<P, 32, 9, false, WARPS>(__VA_ARGS__); break;                 \
+    case 14: ctx.slot_parity = FN<P, 32, 10, false, WARPS>(__VA_ARGS__); break;                \
     default: ctx.slot_parity = FN<P, 32, 8, true, WARPS>(__VA_ARGS__); break;                  \
   }
 

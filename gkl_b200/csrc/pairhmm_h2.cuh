@@ -396,6 +396,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_h2_mega(const __grid_constant
       GKLB_H2_ROW(4, 0)
       GKLB_H2_ROW(8, 9)
       GKLB_H2_ROW(16, 18)
+      case 28: mega_task_h2<32, 9>(m, c, local, ctx); break;    // 32 lanes: 288 and 320 rows only
+      case 29: mega_task_h2<32, 10>(m, c, local, ctx); break;
       default: break;
     }
     ctx.slot_parity ^= 1;  // every task waits once on the warp's slot barrier

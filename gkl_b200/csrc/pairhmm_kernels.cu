@@ -119,6 +119,7 @@ const KernelEntry* kernel_table(int* n) {
     kernel_entries_h2_g4(v);
     kernel_entries_h2_g8(v);
     kernel_entries_h2_g16(v);
+    kernel_entries_h2_g32(v);
     kernel_entries_d1(v);
     kernel_entries_misc(v);
     return v;

@@ -45,6 +45,7 @@ cudaError_t launch_fill_pair_panel(uint8_t* image, int n_pairs, const int64_t* h
 void kernel_entries_h2_g4(std::vector<KernelEntry>& v);
 void kernel_entries_h2_g8(std::vector<KernelEntry>& v);
 void kernel_entries_h2_g16(std::vector<KernelEntry>& v);
+void kernel_entries_h2_g32(std::vector<KernelEntry>& v);
 void kernel_entries_d1(std::vector<KernelEntry>& v);
 void kernel_entries_misc(std::vector<KernelEntry>& v);
 

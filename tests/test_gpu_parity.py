@@ -122,9 +122,9 @@ def test_fuzz_small_batches(eng, eng_d, seed):
 
 
 def test_every_length_class_boundary(eng):
-    # one read at each class capacity and one past it (32, 33, 40, 41, ... 256, 257, 512, 513)
+    # one read at each class capacity and one past it (32, 33, 40, 41, ... 256, 257, 288, 289, 320, 321, 512, 513)
     rng = np.random.default_rng(7)
-    lens = sorted({c + d for c in (32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 512) for d in (0, 1)} | {1, 2})
+    lens = sorted({c + d for c in (32, 40, 48, 56, 64, 80, 96, 112, 128, 160, 192, 224, 256, 288, 320, 512) for d in (0, 1)} | {1, 2})
     hap = synth.ACGT[rng.integers(0, 4, size=300)]
     reads = [hap[:min(L, 300)] if L <= 300 else np.concatenate([hap, synth.ACGT[rng.integers(0, 4, size=L - 300)]])
              for L in lens]
@@ -513,7 +513,7 @@ def test_concurrent_big_calls_share_the_engine_pool_without_deadlock():
         native.global_done()
 
 
-@pytest.mark.parametrize("read_len", [30, 36, 40, 66, 70, 78, 130, 142, 158])
+@pytest.mark.parametrize("read_len", [30, 36, 40, 66, 70, 78, 130, 142, 158, 280, 301])
 def test_single_class_launches_of_the_twelve_warp_kernels(eng, read_len):
     """Uniform read lengths put a whole batch into one class; classes of up to 10 rows per lane then run as
     k_h2_tasks<G, K, 12> (12 warps per SM) instead of the multi-class kernel the mixed-length tests exercise."""
@@ -525,3 +525,16 @@ def test_single_class_launches_of_the_twelve_warp_kernels(eng, read_len):
     ok = np.isfinite(ref)
     assert np.array_equal(np.isfinite(out), ok)
     assert rel(out[ok], ref[ok]).max() <= REL_TOL
+
+
+def test_reads_of_257_to_320_rows_take_the_single_pass_classes(eng, eng_d):
+    """2 x 300 sequencing: reads of 257..320 rows run as 32 lanes x 9 / 10 rows in one pass, in the fp32 sweep and in
+    the fp64 kernels (rerun and useDoublePrecision); mixed with shorter and longer reads they share the multi-class
+    launches with the other classes and with the multi-pass class."""
+    b = synth.random_batch(91, 90, 14, read_len=(240, 340), hap_len=(260, 420), low_quality=0.05, unrelated=0.3)
+    for e, dbl, tol in ((eng, False, REL_TOL), (eng_d, True, 1e-9)):
+        out, ref = e.compute(b), checker(b, dbl)
+        ok = np.isfinite(ref)
+        assert np.array_equal(np.isfinite(out), ok)
+        assert rel(out[ok], ref[ok]).max() <= tol
+    assert eng.stats().fallback_pairs > 0
