@@ -76,8 +76,8 @@ namespace {
 // passes of the multi-pass kernel.
 //   fp64 kernels (useDoublePrecision, rerun): rows per pass = G * K from this table
 struct ClassDef { int G, K; };
-const ClassDef kClassesD1[] = {{8, 4},  {8, 5},  {8, 6},  {8, 7},  {8, 8},  {16, 5}, {16, 6},
-                               {16, 7}, {16, 8}, {32, 5}, {32, 6}, {32, 7}, {32, 8}, {32, 9}, {32, 10}};
+const ClassDef kClassesD1[] = {{8, 4},  {8, 5},  {8, 6},  {8, 7},  {8, 8},  {16, 5},  {16, 6}, {16, 7}, {16, 8},
+                               {16, 9}, {16, 10}, {32, 5}, {32, 6}, {32, 7}, {32, 8}, {32, 9}, {32, 10}};
 const int kNumClassesD1 = (int)(sizeof(kClassesD1) / sizeof(kClassesD1[0]));
 //   fp32 H2 kernels: G = 4, 8, 16 lanes x K = 8..16 rows (32..64 rows in steps of 4, 72..128 in steps of 8,
 //   144..256 in steps of 16) and G = 32 x K = 9, 10 (288 and 320 rows); cfg = gi * 9 + (K - 8), cfg 27 is unused

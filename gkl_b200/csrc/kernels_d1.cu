@@ -11,7 +11,7 @@ void kernel_entries_d1(std::vector<KernelEntry>& v) {
   const KernelEntry e[] = {
       E_D1(8, 4, 12, false, 3),  E_D1(8, 5, 12, false, 3),  E_D1(8, 6, 12, false, 3),  E_D1(8, 7, 12, false, 3),
       E_D1(8, 8, 8, false, 3),  E_D1(16, 5, 12, false, 3), E_D1(16, 6, 12, false, 3), E_D1(16, 7, 12, false, 3),
-      E_D1(16, 8, 8, false, 3), E_D1(32, 5, 12, false, 3), E_D1(32, 6, 12, false, 3), E_D1(32, 7, 12, false, 3),
+      E_D1(16, 8, 8, false, 3), E_D1(16, 9, 8, false, 3), E_D1(16, 10, 8, false, 3), E_D1(32, 5, 12, false, 3), E_D1(32, 6, 12, false, 3), E_D1(32, 7, 12, false, 3),
       E_D1(32, 8, 8, false, 3), E_D1(32, 9, 8, false, 3), E_D1(32, 10, 8, false, 3),  // 288 / 320 rows: 2 x 300 reads in one pass
       E_D1(32, 8, 8, true, 3),
   };

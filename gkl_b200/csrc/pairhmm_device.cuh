@@ -979,7 +979,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) k_sweep_list(const SweepParams 
 // fills the GPU with a single launch instead of a dozen serialised under-filled ones.
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxMegaClasses = 1024;  // (class, panel) entries of one multi-class launch
-constexpr int kCfgMulti = 15;  // configuration index of the multi-pass class (32 x 8 rows per pass)
+constexpr int kCfgMulti = 17;  // configuration index of the multi-pass class (32 x 8 rows per pass)
 
 struct MegaParams {
   int n_classes;
@@ -1019,12 +1019,14 @@ __device__ __noinline__ uint32_t mega_item(const SweepParams& p, unsigned int wi
     case 6: ctx.slot_parity = FN<P, 16, 6, false, WARPS>(__VA_ARGS__); break;                  \
     case 7: ctx.slot_parity = FN<P, 16, 7, false, WARPS>(__VA_ARGS__); break;                  \
     case 8: ctx.slot_parity = FN<P, 16, 8, false, WARPS>(__VA_ARGS__); break;                  \
-    case 9: ctx.slot_parity = FN<P, 32, 5, false, WARPS>(__VA_ARGS__); break;                  \
-    case 10: ctx.slot_parity = FN<P, 32, 6, false, WARPS>(__VA_ARGS__); break;                 \
-    case 11: ctx.slot_parity = FN<P, 32, 7, false, WARPS>(__VA_ARGS__); break;                 \
-    case 12: ctx.slot_parity = FN<P, 32, 8, false, WARPS>(__VA_ARGS__); break;                 \
-    case 13: ctx.slot_parity = FN<P, 32, 9, false, WARPS>(__VA_ARGS__); break;                 \
-    case 14: ctx.slot_parity = FN<P, 32, 10, false, WARPS>(__VA_ARGS__); break;                \
+    case 9: ctx.slot_parity = FN<P, 16, 9, false, WARPS>(__VA_ARGS__); break;                  \
+    case 10: ctx.slot_parity = FN<P, 16, 10, false, WARPS>(__VA_ARGS__); break;                \
+    case 11: ctx.slot_parity = FN<P, 32, 5, false, WARPS>(__VA_ARGS__); break;                 \
+    case 12: ctx.slot_parity = FN<P, 32, 6, false, WARPS>(__VA_ARGS__); break;                 \
+    case 13: ctx.slot_parity = FN<P, 32, 7, false, WARPS>(__VA_ARGS__); break;                 \
+    case 14: ctx.slot_parity = FN<P, 32, 8, false, WARPS>(__VA_ARGS__); break;                 \
+    case 15: ctx.slot_parity = FN<P, 32, 9, false, WARPS>(__VA_ARGS__); break;                 \
+    case 16: ctx.slot_parity = FN<P, 32, 10, false, WARPS>(__VA_ARGS__); break;                \
     default: ctx.slot_parity = FN<P, 32, 8, true, WARPS>(__VA_ARGS__); break;                  \
   }
 
